@@ -1,0 +1,123 @@
+/*
+ * wunet_b200.h — C ABI of the B200-native Wave-U-Net forward path.
+ *
+ * This is the drop-in boundary for ONE hot path of haoxiangsnr/Wave-U-Net-for-Speech-Enhancement:
+ * `Model.forward` (reference model/unet_basic.py:77-100) together with the parameter tree that
+ * `Model.__init__` (model/unet_basic.py:33-75) defines.  Every entry point takes plain pointers and
+ * sizes; there are no torch types here.  The Python shim
+ * (wave_u_net_for_speech_enhancement_b200/unet_basic.py) binds these with ctypes and exposes the
+ * reference's `Model(n_layers, channels_interval)` nn.Module surface on top.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative WUNET_E* code on failure; the message is
+ *     available from wunet_last_error() (thread-local), which the shim turns into RuntimeError
+ *     (the reference's error convention is Python exceptions).
+ *   - "dev" pointers are device pointers on the context's device; "host" pointers are host memory.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream). Nothing here
+ *     synchronises the device except wunet_forward_host().
+ *   - there is NO CPU fallback: without a CUDA device wunet_create() fails.
+ */
+#ifndef WUNET_B200_H
+#define WUNET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WUNET_OK 0
+#define WUNET_EINVAL (-1)   /* bad argument (shape, null pointer, T not a multiple of 2^n_layers ...) */
+#define WUNET_ECUDA (-2)    /* a CUDA runtime / driver call failed */
+#define WUNET_ESTATE (-3)   /* call order (forward before set_weights ...) */
+#define WUNET_ENOMEM (-4)   /* workspace too small / allocation failed */
+
+/* arithmetic of the convolution path */
+#define WUNET_PREC_FP32 0   /* fp32 operands, fp32 FFMA accumulate: parity <= 1e-4 vs reference (config 2) */
+#define WUNET_PREC_BF16 1   /* bf16 operands/activations, fp32 accumulate on tcgen05 tensor cores (config 3) */
+
+typedef struct wunet_ctx wunet_ctx;
+
+/* Version / build info string (static storage). */
+const char *wunet_version(void);
+
+/* Last error message of the calling thread (static thread-local storage, never NULL). */
+const char *wunet_last_error(void);
+
+/*
+ * Replaces: Model.__init__(n_layers=12, channels_interval=24)   model/unet_basic.py:33-75
+ * Builds the channel plan (encoder_in/out :38-39, middle :52-57, decoder_in/out :59-62, out :72-75)
+ * for `device` (CUDA ordinal). No weights yet.
+ */
+int wunet_create(int n_layers, int channels_interval, int device, wunet_ctx **out);
+void wunet_destroy(wunet_ctx *ctx);
+
+/* Number of conv+BN+LeakyReLU blocks = 2*n_layers+1 (encoder[0..n-1], middle, decoder[0..n-1]). */
+int wunet_num_blocks(const wunet_ctx *ctx);
+/* Channel plan of block i (forward order): Cin, Cout, kernel size.  (model/unet_basic.py:38-39,59-62) */
+int wunet_block_shape(const wunet_ctx *ctx, int block, int *cin, int *cout, int *ksize);
+
+/*
+ * Replaces: the parameter reads that nn.Conv1d / nn.BatchNorm1d do inside Model.forward
+ * (model/unet_basic.py:10-12, :23-25, :53-55, :73) and load_state_dict (enhancement.py:41,
+ * trainer/base_trainer.py:77-79).
+ * All arrays have wunet_num_blocks() entries of DEVICE pointers to contiguous fp32 tensors in the
+ * reference's shapes: conv_w[i] = [Cout,Cin,K], conv_b/bn_* [Cout]; out_w = [1,ci+1,1], out_b = [1].
+ * The library packs them (layout change, eval-BatchNorm folded to scale/shift with eps=1e-5, bf16
+ * copies) into its own device buffers on `stream`; the caller's tensors are only read during the
+ * call's stream work and may change afterwards (call again to refresh — the shim does so whenever a
+ * parameter's version/data_ptr changes, e.g. after optimizer.step(), load_state_dict, .cpu()/.to()).
+ */
+int wunet_set_weights(wunet_ctx *ctx, const float *const *conv_w, const float *const *conv_b,
+                      const float *const *bn_weight, const float *const *bn_bias,
+                      const float *const *bn_running_mean, const float *const *bn_running_var,
+                      const float *out_w, const float *out_b, void *stream);
+
+/* Bytes of device scratch wunet_forward() needs for a [B,1,T] batch at `precision`. 0 on error. */
+size_t wunet_workspace_bytes(const wunet_ctx *ctx, int B, int T, int precision);
+
+/*
+ * Replaces: Model.forward(input)   model/unet_basic.py:77-100   (eval-mode BatchNorm)
+ *   x_dev [B,1,T] fp32 contiguous  ->  y_dev [B,1,T] fp32 contiguous, values in (-1,1).
+ * T must be a multiple of 2^n_layers (the reference raises from torch.cat at :95 otherwise)
+ * -> WUNET_EINVAL.  Enqueues kernels on `stream` and returns; `workspace` must stay alive until
+ * they finish.  Call sites this serves: trainer/trainer.py:75, enhancement.py:66.
+ */
+int wunet_forward(wunet_ctx *ctx, const float *x_dev, float *y_dev, int B, int T, int precision,
+                  void *workspace, size_t workspace_bytes, void *stream);
+
+/*
+ * Same operator with HOST buffers (the end-to-end form used by enhancement.py:64-66, which does
+ * `model(chunk).detach().cpu()`): copies x_host -> device, runs the forward, copies y back and
+ * waits for it.  Uses context-owned, grow-only device buffers and a context-owned stream.
+ * x_host/y_host should be pinned for full PCIe rate; pageable memory also works.
+ */
+int wunet_forward_host(wunet_ctx *ctx, const float *x_host, float *y_host, int B, int T, int precision);
+
+/*
+ * Test/diagnostic hook: copy the full-resolution output of block `block` from the workspace of the
+ * LAST wunet_forward() call (same ctx, same workspace, B, T, precision) to out_dev as fp32
+ * [B,Cout,L] (the reference's NCL layout) — what a forward hook on encoder[i] / middle /
+ * decoder[j] would see.  Used by the per-level parity tests.
+ */
+int wunet_read_level(wunet_ctx *ctx, int block, const void *workspace, int B, int T, int precision,
+                     float *out_dev, void *stream);
+
+/*
+ * Measurement hooks (bench.py's per-level roofline): when enabled, wunet_forward() records a CUDA
+ * event on the launch stream before the first kernel and after every block (2n+1 conv blocks, then
+ * the 1x1+tanh head when it is a separate launch).  wunet_profile_read() waits for the last event
+ * and returns the per-block device time in milliseconds: ms[i] = block i, ms[2n+1] = head (0 when the
+ * head is fused into the last decoder block).  *count receives the number of entries written.
+ */
+int wunet_profile_enable(wunet_ctx *ctx, int enable);
+int wunet_profile_read(wunet_ctx *ctx, float *ms, int capacity, int *count);
+
+/* Number of kernel launches the last wunet_forward()/wunet_forward_host() enqueued. */
+int wunet_last_launch_count(const wunet_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WUNET_B200_H */

@@ -1,0 +1,154 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu). The CUDA path is called through the C ABI
+(via the drop-in module's ctypes shim) and compared with the oracle and the committed golden vectors
+generated from the live reference module."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import wunet_oracle as wo
+from wave_u_net_for_speech_enhancement_b200 import Model, _lib
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-4     # BASELINE.json north_star: <= 1e-4 max-abs fp32 vs the reference forward
+BF16_TOL = 3e-2     # bf16 operands/activations through 25 conv blocks (SURVEY §8c measured 6e-4..1.4e-3 for
+                    # operand rounding alone; bf16 *storage* of every activation adds to it). Stated, not hidden.
+
+
+def make_model(n, ci, st, precision):
+    m = Model(n, ci, precision=precision)
+    m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in st.items()}, strict=True)
+    return m.to("cuda:0").eval()
+
+
+def run(m, x):
+    with torch.no_grad():
+        y = m(torch.from_numpy(x).to("cuda:0"))
+    torch.cuda.synchronize()
+    return y.cpu().numpy()
+
+
+@pytest.fixture(scope="module")
+def full(golden_dir):
+    return np.load(os.path.join(golden_dir, "full_n12_c24_b2.npz"))
+
+
+@pytest.fixture(scope="module")
+def state_full():
+    return wo.make_state(12, 24, seed=0)
+
+
+def test_extension_is_loaded_not_a_fallback():
+    lib = _lib.load()
+    assert b"sm_100a" in lib.wunet_version()
+    assert torch.cuda.get_device_capability(0)[0] == 10
+
+
+def test_fp32_small_config_all_levels(golden_dir):
+    g = np.load(os.path.join(golden_dir, "small_n4_c8.npz"))
+    n, ci, T, B = int(g["n_layers"]), int(g["channels_interval"]), int(g["T"]), int(g["B"])
+    st = wo.make_state(n, ci, seed=int(g["state_seed"]))
+    x = wo.make_input(B, T, seed=int(g["input_seed"]))
+    m = make_model(n, ci, st, "fp32")
+    y = run(m, x)
+    for i in range(2 * n + 1):
+        lv = m.read_level(i, B, T).cpu().numpy()
+        assert lv.shape == g[f"level_{i}"].shape
+        assert np.abs(lv - g[f"level_{i}"]).max() <= FP32_TOL, f"level {i}"
+    assert np.abs(y - g["y"]).max() <= FP32_TOL
+
+
+def test_fp32_full_config_vs_golden_and_oracle(full, state_full):
+    x = wo.make_input(2, 16384, seed=int(full["input_seed"]))
+    m = make_model(12, 24, state_full, "fp32")
+    y = run(m, x)
+    for i in range(25):
+        lv = m.read_level(i, 2, 16384).cpu().numpy()
+        idx = full[f"probe_idx_{i}"]
+        err = np.abs(lv[0][:, idx] - full[f"probe_{i}"]).max()
+        assert err <= FP32_TOL, f"level {i}: {err}"
+        a = np.abs(lv.astype(np.float64)).sum()
+        assert abs(a - float(full[f"abssum_{i}"])) <= 1e-5 * a + 1e-2, f"level {i} abssum"
+    err = np.abs(y - full["y"]).max()
+    assert err <= FP32_TOL, err
+    assert m.last_launch_count() == 26
+
+
+def test_fp32_config2_batch64_vs_oracle_subset(state_full):
+    """BASELINE.json configs[1]: B=64, T=16384 fp32, <= 1e-4. The oracle checks 4 of the 64 frames in full
+    (frames are independent in eval mode); batch-permutation invariance covers the rest."""
+    B = 64
+    x = wo.make_input(B, 16384, seed=4321)
+    m = make_model(12, 24, state_full, "fp32")
+    y = run(m, x)
+    pick = [0, 17, 42, 63]
+    want = wo.COracle(12, 24).forward(state_full, x[pick])
+    assert np.abs(y[pick] - want).max() <= FP32_TOL
+    perm = np.random.default_rng(0).permutation(B)
+    y2 = run(m, x[perm])
+    assert np.array_equal(y2, y[perm]), "eval forward must be batch-permutation invariant, bit for bit"
+    assert np.isfinite(y).all() and np.abs(y).max() < 1.0
+
+
+def test_fp32_edge_vectors(golden_dir, state_full):
+    g = np.load(os.path.join(golden_dir, "edges_n12_c24.npz"))
+    m = make_model(12, 24, state_full, "fp32")
+    for name, xe in wo.edge_inputs(16384).items():
+        assert np.abs(run(m, xe) - g[name]).max() <= FP32_TOL, name
+    for Tx in (4096, 20480):
+        y = run(m, wo.make_input(1, Tx, seed=77 + Tx))
+        assert np.abs(y - g[f"T{Tx}"]).max() <= FP32_TOL, Tx
+
+
+def test_fp32_b1_loop_equals_batched(state_full):
+    """enhancement.py:64-66 forwards one chunk at a time; stacking chunks on the batch axis is equivalent."""
+    x = wo.make_input(3, 16384, seed=99)
+    m = make_model(12, 24, state_full, "fp32")
+    yb = run(m, x)
+    for b in range(3):
+        assert np.abs(run(m, x[b:b + 1]) - yb[b:b + 1]).max() <= 1e-6
+
+
+def test_bad_length_raises(state_full):
+    m = make_model(12, 24, state_full, "fp32")
+    with pytest.raises(_lib.WunetError, match="multiple of 2"):
+        m(torch.zeros(1, 1, 16000, device="cuda:0"))
+
+
+def test_weight_cache_invalidation(state_full):
+    m = make_model(12, 24, state_full, "fp32")
+    x = wo.make_input(1, 4096, seed=5)
+    y0 = run(m, x)
+    with torch.no_grad():
+        m.out[0].bias.add_(0.25)                      # in-place update bumps _version (optimizer.step does this)
+    y1 = run(m, x)
+    assert np.abs(y1 - y0).max() > 1e-3
+    st2 = wo.make_state(12, 24, seed=5)
+    m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in st2.items()})
+    y2 = run(m, x)
+    assert np.abs(y2 - wo.COracle().forward(st2, x)).max() <= FP32_TOL
+    m.cpu(); m.to("cuda:0")                           # base_trainer.py:103-124 does this around checkpointing
+    assert np.array_equal(run(m, x), y2)
+
+
+def test_forward_host_matches_device_path(state_full):
+    m = make_model(12, 24, state_full, "fp32")
+    x = wo.make_input(4, 16384, seed=8)
+    xh = torch.from_numpy(x).pin_memory()
+    yh = m.forward_host(xh)
+    assert np.array_equal(yh.numpy(), run(m, x))
+
+
+def test_bf16_full_config(full, state_full):
+    x = wo.make_input(2, 16384, seed=int(full["input_seed"]))
+    m = make_model(12, 24, state_full, "bf16")
+    try:
+        y = run(m, x)
+    except _lib.WunetError as e:
+        if "not built yet" in str(e):
+            pytest.skip("tcgen05 path not built yet")
+        raise
+    err = np.abs(y - full["y"]).max()
+    assert err <= BF16_TOL, err

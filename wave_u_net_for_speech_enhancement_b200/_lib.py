@@ -1,0 +1,61 @@
+"""ctypes binding of libwunet_b200.so (the C ABI in include/wunet_b200.h). No torch types cross this boundary."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libwunet_b200.so")
+
+PREC_FP32 = 0
+PREC_BF16 = 1
+PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16}
+
+_lib = None
+
+
+class WunetError(RuntimeError):
+    """Raised when a libwunet_b200 call returns a negative status (message from wunet_last_error())."""
+
+
+def load() -> ctypes.CDLL:
+    """Load the CUDA library; there is deliberately no fallback if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise ImportError(
+            f"{SO_PATH} is missing: build it with `python -m wave_u_net_for_speech_enhancement_b200.build` "
+            "(needs nvcc; sm_100a only). This package has no CPU / PyTorch fallback for the forward path.")
+    lib = ctypes.CDLL(SO_PATH)
+    vp, ci, cs = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
+    lib.wunet_version.restype = ctypes.c_char_p
+    lib.wunet_last_error.restype = ctypes.c_char_p
+    lib.wunet_create.argtypes = [ci, ci, ci, ctypes.POINTER(vp)]
+    lib.wunet_destroy.argtypes = [vp]
+    lib.wunet_destroy.restype = None
+    lib.wunet_num_blocks.argtypes = [vp]
+    lib.wunet_block_shape.argtypes = [vp, ci, ctypes.POINTER(ci), ctypes.POINTER(ci), ctypes.POINTER(ci)]
+    lib.wunet_set_weights.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.wunet_workspace_bytes.argtypes = [vp, ci, ci, ci]
+    lib.wunet_workspace_bytes.restype = cs
+    lib.wunet_forward.argtypes = [vp, vp, vp, ci, ci, ci, vp, cs, vp]
+    lib.wunet_forward_host.argtypes = [vp, vp, vp, ci, ci, ci]
+    lib.wunet_read_level.argtypes = [vp, ci, vp, ci, ci, ci, vp, vp]
+    lib.wunet_last_launch_count.argtypes = [vp]
+    lib.wunet_profile_enable.argtypes = [vp, ci]
+    lib.wunet_profile_read.argtypes = [vp, vp, ci, ctypes.POINTER(ci)]
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise WunetError(f"libwunet_b200: {load().wunet_last_error().decode()} (status {rc})")
+
+
+EXPORTED_SYMBOLS = [
+    "wunet_version", "wunet_last_error", "wunet_create", "wunet_destroy", "wunet_num_blocks", "wunet_block_shape",
+    "wunet_set_weights", "wunet_workspace_bytes", "wunet_forward", "wunet_forward_host", "wunet_read_level",
+    "wunet_last_launch_count", "wunet_profile_enable", "wunet_profile_read",
+]

@@ -1,0 +1,381 @@
+// wunet_api.cu — the C ABI declared in include/wunet_b200.h: context, weight packing, workspace
+// carving and the kernel sequence of Model.forward (reference model/unet_basic.py:77-100).
+#include "../../include/wunet_b200.h"
+#include "wunet_common.cuh"
+#include "wunet_tc.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+using namespace wunet;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t e__ = (expr);                                                                        \
+        if (e__ != cudaSuccess)                                                                          \
+            return fail(WUNET_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Block {
+    int cin, cout, k;
+    float *wp = nullptr, *scale = nullptr, *shift = nullptr;   // fp32 packed
+};
+
+}  // namespace
+
+struct wunet_ctx {
+    int n = 0, ci = 0, device = 0;
+    std::vector<Block> blocks;         // 2n+1
+    float *out_w = nullptr, *out_b = nullptr;   // device copies [ci+1], [1]
+    bool have_weights = false;
+    int last_launches = 0;
+    TcState *tc = nullptr;             // bf16 / tcgen05 path state (packed weights, tensor maps)
+    bool profile = false;              // record per-block events (wunet_profile_enable)
+    std::vector<cudaEvent_t> ev;       // 2n+3 events
+    int ev_recorded = 0;
+    // forward_host resources (grow-only)
+    cudaStream_t hstream = nullptr;
+    float *hx = nullptr, *hy = nullptr;
+    size_t hx_cap = 0;
+    void *hws = nullptr;
+    size_t hws_cap = 0;
+};
+
+namespace {
+
+// offsets (bytes) of every block's full-resolution fp32 NCL output inside the fp32 workspace
+void fp32_layout(const wunet_ctx *c, int B, int T, std::vector<size_t> &off, size_t &total)
+{
+    const int n = c->n;
+    off.resize(2 * n + 1);
+    size_t cur = 0;
+    for (int i = 0; i < 2 * n + 1; ++i) {
+        const int L = (i <= n) ? (T >> i) : (T >> (2 * n - i));
+        off[i] = cur;
+        cur += align_up((size_t)B * c->blocks[i].cout * L * sizeof(float), 256);
+    }
+    total = cur;
+}
+
+int level_len(const wunet_ctx *c, int block, int T)
+{
+    const int n = c->n;
+    return (block <= n) ? (T >> block) : (T >> (2 * n - block));
+}
+
+int check_shape(const wunet_ctx *c, int B, int T)
+{
+    if (!c) return fail(WUNET_EINVAL, "null context");
+    if (B < 1 || T < 1) return fail(WUNET_EINVAL, "B and T must be positive (B=%d, T=%d)", B, T);
+    if (T % (1 << c->n) != 0)
+        return fail(WUNET_EINVAL,
+                    "input length T=%d is not a multiple of 2^n_layers=%d (the reference raises from torch.cat, "
+                    "model/unet_basic.py:95)", T, 1 << c->n);
+    if (T % 4 != 0) return fail(WUNET_EINVAL, "T=%d must be a multiple of 4", T);
+    return WUNET_OK;
+}
+
+cudaEvent_t *prof_events(wunet_ctx *c)
+{
+    if (!c->profile) return nullptr;
+    const size_t need = 2 * (size_t)c->n + 3;
+    while (c->ev.size() < need) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+        c->ev.push_back(e);
+    }
+    c->ev_recorded = 0;
+    return c->ev.data();
+}
+
+int forward_fp32(wunet_ctx *c, const float *x, float *y, int B, int T, void *ws, cudaStream_t st)
+{
+    const int n = c->n;
+    std::vector<size_t> off;
+    size_t total;
+    fp32_layout(c, B, T, off, total);
+    char *base = static_cast<char *>(ws);
+    auto lvl = [&](int i) { return reinterpret_cast<float *>(base + off[i]); };
+    int launches = 0;
+    cudaEvent_t *ev = prof_events(c);
+    if (ev) cudaEventRecord(ev[0], st);
+    for (int i = 0; i <= n; ++i) {                       // encoder (model/unet_basic.py:82-86) + middle (:88)
+        const Block &bk = c->blocks[i];
+        ConvArgs a{};
+        a.src0 = (i == 0) ? x : lvl(i - 1);
+        a.src1 = nullptr;
+        a.wp = bk.wp; a.scale = bk.scale; a.shift = bk.shift;
+        a.out = lvl(i);
+        a.B = B; a.L = T >> i;
+        a.Cin = bk.cin; a.Cin0 = bk.cin; a.Cin1 = 0; a.Cout = bk.cout;
+        a.up_scale = 0.f;
+        const int r = launch_conv_fp32(a, bk.k, i == 0 ? SRC_DIRECT : SRC_DECIM, st);
+        if (r < 0) return fail(WUNET_ECUDA, "encoder block %d launch failed: %s", i, cudaGetErrorString(cudaGetLastError()));
+        launches += r;
+        if (ev) cudaEventRecord(ev[i + 1], st);
+    }
+    for (int j = 0; j < n; ++j) {                        // decoder (model/unet_basic.py:91-96)
+        const Block &bk = c->blocks[n + 1 + j];
+        const int e = n - 1 - j;
+        ConvArgs a{};
+        a.src0 = lvl(n + j);                             // previous block's output (middle for j=0)
+        a.src1 = lvl(e);                                 // skip = full-resolution encoder output
+        a.wp = bk.wp; a.scale = bk.scale; a.shift = bk.shift;
+        a.out = lvl(n + 1 + j);
+        a.B = B; a.L = T >> e;
+        a.Cin0 = c->blocks[n + j].cout; a.Cin1 = c->blocks[e].cout; a.Cin = a.Cin0 + a.Cin1; a.Cout = bk.cout;
+        if (a.Cin != bk.cin) return fail(WUNET_ESTATE, "decoder %d channel plan mismatch", j);
+        const int Lin = a.L / 2;
+        a.up_scale = (a.L > 1) ? (float)(Lin - 1) / (float)(a.L - 1) : 0.f;
+        const int r = launch_conv_fp32(a, bk.k, SRC_UPCAT, st);
+        if (r < 0) return fail(WUNET_ECUDA, "decoder block %d launch failed: %s", j, cudaGetErrorString(cudaGetLastError()));
+        launches += r;
+        if (ev) cudaEventRecord(ev[n + 2 + j], st);
+    }
+    {                                                    // out (model/unet_basic.py:98-99)
+        const int r = launch_out_fp32(lvl(2 * n), x, c->out_w, c->out_b, y, B, c->ci, T, st);
+        if (r < 0) return fail(WUNET_ECUDA, "out launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        launches += r;
+        if (ev) { cudaEventRecord(ev[2 * n + 2], st); c->ev_recorded = 2 * n + 3; }
+    }
+    c->last_launches = launches;
+    return WUNET_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *wunet_version(void) { return "wunet_b200 0.1 (sm_100a; fp32 FFMA + bf16 tcgen05 paths)"; }
+
+const char *wunet_last_error(void) { return g_err; }
+
+int wunet_create(int n_layers, int channels_interval, int device, wunet_ctx **out)
+{
+    if (!out) return fail(WUNET_EINVAL, "out is null");
+    *out = nullptr;
+    if (n_layers < 1 || n_layers > 16 || channels_interval < 1 || channels_interval > 1024)
+        return fail(WUNET_EINVAL, "unsupported n_layers=%d / channels_interval=%d", n_layers, channels_interval);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(WUNET_ECUDA, "no CUDA device available (this library has no CPU fallback)");
+    }
+    if (device < 0 || device >= ndev) return fail(WUNET_EINVAL, "device %d out of range (have %d)", device, ndev);
+    wunet_ctx *c = new (std::nothrow) wunet_ctx();
+    if (!c) return fail(WUNET_ENOMEM, "out of host memory");
+    c->n = n_layers; c->ci = channels_interval; c->device = device;
+    const int n = n_layers, ci = channels_interval;
+    // channel plan: model/unet_basic.py:38-39 (encoder), :52-57 (middle), :59-62 (decoder)
+    for (int i = 0; i < n; ++i) c->blocks.push_back(Block{i == 0 ? 1 : i * ci, (i + 1) * ci, 15});
+    c->blocks.push_back(Block{n * ci, n * ci, 15});
+    for (int j = 0; j < n; ++j) c->blocks.push_back(Block{j == 0 ? 2 * n * ci : (2 * (n - j) + 1) * ci, (n - j) * ci, 5});
+    *out = c;
+    return WUNET_OK;
+}
+
+void wunet_destroy(wunet_ctx *c)
+{
+    if (!c) return;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(c->device);
+    for (auto &b : c->blocks) { cudaFree(b.wp); cudaFree(b.scale); cudaFree(b.shift); }
+    cudaFree(c->out_w); cudaFree(c->out_b);
+    tc_destroy(c->tc);
+    for (auto e : c->ev) cudaEventDestroy(e);
+    if (c->hstream) cudaStreamDestroy(c->hstream);
+    cudaFree(c->hx); cudaFree(c->hy); cudaFree(c->hws);
+    cudaSetDevice(prev);
+    delete c;
+}
+
+int wunet_num_blocks(const wunet_ctx *c) { return c ? (int)c->blocks.size() : fail(WUNET_EINVAL, "null context"); }
+
+int wunet_block_shape(const wunet_ctx *c, int block, int *cin, int *cout, int *ksize)
+{
+    if (!c || block < 0 || block >= (int)c->blocks.size()) return fail(WUNET_EINVAL, "bad block index %d", block);
+    if (cin) *cin = c->blocks[block].cin;
+    if (cout) *cout = c->blocks[block].cout;
+    if (ksize) *ksize = c->blocks[block].k;
+    return WUNET_OK;
+}
+
+int wunet_set_weights(wunet_ctx *c, const float *const *conv_w, const float *const *conv_b,
+                      const float *const *bn_weight, const float *const *bn_bias,
+                      const float *const *bn_running_mean, const float *const *bn_running_var, const float *out_w,
+                      const float *out_b, void *stream)
+{
+    if (!c) return fail(WUNET_EINVAL, "null context");
+    if (!conv_w || !conv_b || !bn_weight || !bn_bias || !bn_running_mean || !bn_running_var || !out_w || !out_b)
+        return fail(WUNET_EINVAL, "null parameter array");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CUDA_TRY(cudaSetDevice(c->device));
+    for (size_t i = 0; i < c->blocks.size(); ++i) {
+        Block &b = c->blocks[i];
+        if (!conv_w[i] || !conv_b[i] || !bn_weight[i] || !bn_bias[i] || !bn_running_mean[i] || !bn_running_var[i])
+            return fail(WUNET_EINVAL, "null parameter pointer for block %zu", i);
+        const size_t wn = (size_t)b.cout * b.cin * b.k;
+        if (!b.wp) {
+            CUDA_TRY(cudaMalloc(&b.wp, wn * sizeof(float)));
+            CUDA_TRY(cudaMalloc(&b.scale, b.cout * sizeof(float)));
+            CUDA_TRY(cudaMalloc(&b.shift, b.cout * sizeof(float)));
+        }
+        if (launch_pack_fp32(conv_w[i], conv_b[i], bn_weight[i], bn_bias[i], bn_running_mean[i], bn_running_var[i],
+                             b.wp, b.scale, b.shift, b.cout, b.cin, b.k, st) < 0)
+            return fail(WUNET_ECUDA, "pack kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    if (!c->out_w) {
+        CUDA_TRY(cudaMalloc(&c->out_w, (c->ci + 1) * sizeof(float)));
+        CUDA_TRY(cudaMalloc(&c->out_b, sizeof(float)));
+    }
+    CUDA_TRY(cudaMemcpyAsync(c->out_w, out_w, (c->ci + 1) * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(c->out_b, out_b, sizeof(float), cudaMemcpyDeviceToDevice, st));
+    // bf16 / tcgen05 path: repack from the folded fp32 copies
+    {
+        std::vector<TcBlockSrc> src(c->blocks.size());
+        for (size_t i = 0; i < c->blocks.size(); ++i)
+            src[i] = TcBlockSrc{c->blocks[i].cin, c->blocks[i].cout, c->blocks[i].k, conv_w[i], c->blocks[i].scale,
+                                c->blocks[i].shift};
+        const int r = tc_set_weights(&c->tc, c->n, c->ci, src.data(), (int)src.size(), c->out_w, c->out_b, st);
+        if (r != 0) return fail(WUNET_ECUDA, "tcgen05 weight packing failed: %s", tc_error());
+    }
+    c->have_weights = true;
+    return WUNET_OK;
+}
+
+size_t wunet_workspace_bytes(const wunet_ctx *c, int B, int T, int precision)
+{
+    if (check_shape(c, B, T) != WUNET_OK) return 0;
+    if (precision == WUNET_PREC_FP32) {
+        std::vector<size_t> off;
+        size_t total;
+        fp32_layout(c, B, T, off, total);
+        return total;
+    }
+    if (precision == WUNET_PREC_BF16) return tc_workspace_bytes(c->n, c->ci, B, T);
+    fail(WUNET_EINVAL, "unknown precision %d", precision);
+    return 0;
+}
+
+int wunet_forward(wunet_ctx *c, const float *x, float *y, int B, int T, int precision, void *workspace,
+                  size_t workspace_bytes, void *stream)
+{
+    int rc = check_shape(c, B, T);
+    if (rc != WUNET_OK) return rc;
+    if (!c->have_weights) return fail(WUNET_ESTATE, "wunet_forward called before wunet_set_weights");
+    if (!x || !y || !workspace) return fail(WUNET_EINVAL, "null buffer");
+    const size_t need = wunet_workspace_bytes(c, B, T, precision);
+    if (need == 0) return WUNET_EINVAL;
+    if (workspace_bytes < need) return fail(WUNET_ENOMEM, "workspace too small: %zu < %zu bytes", workspace_bytes, need);
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (precision == WUNET_PREC_FP32) return forward_fp32(c, x, y, B, T, workspace, st);
+    int launches = 0;
+    cudaEvent_t *ev = prof_events(c);
+    const int r = tc_forward(c->tc, x, y, B, T, workspace, st, &launches, ev);
+    if (ev && r == 0) c->ev_recorded = 2 * c->n + 3;
+    if (r != 0) return fail(WUNET_ECUDA, "tcgen05 forward failed: %s", tc_error());
+    c->last_launches = launches;
+    return WUNET_OK;
+}
+
+int wunet_forward_host(wunet_ctx *c, const float *x_host, float *y_host, int B, int T, int precision)
+{
+    int rc = check_shape(c, B, T);
+    if (rc != WUNET_OK) return rc;
+    if (!x_host || !y_host) return fail(WUNET_EINVAL, "null host buffer");
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (!c->hstream) CUDA_TRY(cudaStreamCreateWithFlags(&c->hstream, cudaStreamNonBlocking));
+    const size_t nbytes = (size_t)B * T * sizeof(float);
+    if (c->hx_cap < nbytes) {
+        cudaFree(c->hx); cudaFree(c->hy);
+        c->hx = c->hy = nullptr; c->hx_cap = 0;
+        CUDA_TRY(cudaMalloc(&c->hx, nbytes));
+        CUDA_TRY(cudaMalloc(&c->hy, nbytes));
+        c->hx_cap = nbytes;
+    }
+    const size_t need = wunet_workspace_bytes(c, B, T, precision);
+    if (need == 0) return WUNET_EINVAL;
+    if (c->hws_cap < need) {
+        cudaFree(c->hws);
+        c->hws = nullptr; c->hws_cap = 0;
+        CUDA_TRY(cudaMalloc(&c->hws, need));
+        c->hws_cap = need;
+    }
+    CUDA_TRY(cudaMemcpyAsync(c->hx, x_host, nbytes, cudaMemcpyHostToDevice, c->hstream));
+    rc = wunet_forward(c, c->hx, c->hy, B, T, precision, c->hws, c->hws_cap, c->hstream);
+    if (rc != WUNET_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(y_host, c->hy, nbytes, cudaMemcpyDeviceToHost, c->hstream));
+    CUDA_TRY(cudaStreamSynchronize(c->hstream));
+    return WUNET_OK;
+}
+
+int wunet_read_level(wunet_ctx *c, int block, const void *workspace, int B, int T, int precision, float *out_dev,
+                     void *stream)
+{
+    int rc = check_shape(c, B, T);
+    if (rc != WUNET_OK) return rc;
+    if (block < 0 || block >= (int)c->blocks.size() || !workspace || !out_dev)
+        return fail(WUNET_EINVAL, "bad block index / null buffer");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int L = level_len(c, block, T);
+    if (precision == WUNET_PREC_FP32) {
+        std::vector<size_t> off;
+        size_t total;
+        fp32_layout(c, B, T, off, total);
+        CUDA_TRY(cudaMemcpyAsync(out_dev, static_cast<const char *>(workspace) + off[block],
+                                 (size_t)B * c->blocks[block].cout * L * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        return WUNET_OK;
+    }
+    if (precision == WUNET_PREC_BF16) {
+        const int r = tc_read_level(c->tc, block, workspace, B, T, out_dev, st);
+        if (r != 0) return fail(WUNET_ECUDA, "tc_read_level failed: %s", tc_error());
+        return WUNET_OK;
+    }
+    return fail(WUNET_EINVAL, "unknown precision %d", precision);
+}
+
+int wunet_last_launch_count(const wunet_ctx *c) { return c ? c->last_launches : 0; }
+
+int wunet_profile_enable(wunet_ctx *c, int enable)
+{
+    if (!c) return fail(WUNET_EINVAL, "null context");
+    c->profile = enable != 0;
+    c->ev_recorded = 0;
+    return WUNET_OK;
+}
+
+int wunet_profile_read(wunet_ctx *c, float *ms, int capacity, int *count)
+{
+    if (!c || !ms || !count) return fail(WUNET_EINVAL, "null argument");
+    if (c->ev_recorded < 2) return fail(WUNET_ESTATE, "no profiled forward recorded (call wunet_profile_enable, then wunet_forward)");
+    const int nseg = c->ev_recorded - 1;
+    if (capacity < nseg) return fail(WUNET_EINVAL, "capacity %d < %d", capacity, nseg);
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaEventSynchronize(c->ev[c->ev_recorded - 1]));
+    for (int i = 0; i < nseg; ++i) CUDA_TRY(cudaEventElapsedTime(&ms[i], c->ev[i], c->ev[i + 1]));
+    *count = nseg;
+    return WUNET_OK;
+}
+
+}  // extern "C"

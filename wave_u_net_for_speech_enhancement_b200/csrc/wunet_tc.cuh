@@ -1,0 +1,29 @@
+// wunet_tc.cuh — interface of the bf16 / tcgen05 tensor-core path (implemented in wunet_tc.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+namespace wunet {
+
+struct TcState;   // packed bf16 weights, TMA tensor maps, per-shape plans
+
+// One conv block as the tensor-core path sees it: the ORIGINAL fp32 weights [Cout][Cin][K] plus the
+// folded eval-BatchNorm scale/shift that the fp32 packer already produced.
+struct TcBlockSrc {
+    int cin, cout, k;
+    const float *w;       // device, [Cout][Cin][K] fp32 (reference layout)
+    const float *scale;   // device, [Cout]
+    const float *shift;   // device, [Cout]
+};
+
+const char *tc_error();
+int tc_set_weights(TcState **st, int n_layers, int ci, const TcBlockSrc *blocks, int nblocks, const float *out_w,
+                   const float *out_b, cudaStream_t stream);
+size_t tc_workspace_bytes(int n_layers, int ci, int B, int T);
+// events: null, or 2n+3 events: [0] before the first kernel, [i+1] after block i, [2n+2] after the head
+int tc_forward(TcState *st, const float *x, float *y, int B, int T, void *ws, cudaStream_t stream, int *launches,
+               cudaEvent_t *events);
+int tc_read_level(TcState *st, int block, const void *ws, int B, int T, float *out_ncl, cudaStream_t stream);
+void tc_destroy(TcState *st);
+
+}  // namespace wunet

@@ -1,0 +1,305 @@
+"""
+Drop-in replacement for the reference's ``model/unet_basic.py`` (``Model``), forward path on B200.
+
+Selected through the reference's own plugin loader (``util/utils.py:55-72``) by changing ONLY the
+``"module"`` string of the ``"model"`` stanza (``config/train/train.json:22-26``)::
+
+    "model": {"module": "wave_u_net_for_speech_enhancement_b200.unet_basic", "main": "Model", "args": {}}
+
+Surface kept identical to the reference:
+
+* constructor ``Model(n_layers=12, channels_interval=24)``            (model/unet_basic.py:33)
+* ``state_dict()``: the same 177 keys/shapes/dtypes, ``parameters()`` in the same registration
+  order (conv.weight, conv.bias, bn.weight, bn.bias per block; encoder → middle → decoder → out), so
+  reference checkpoints (``trainer/base_trainer.py:83-124``) and index-keyed Adam state interchange;
+* ``forward(input[B,1,T]) -> [B,1,T]`` fp32, T a multiple of 2**n_layers   (model/unet_basic.py:77-100)
+
+The sub-modules below exist ONLY as parameter/buffer containers with the reference's names; their
+``forward`` is never called on the product path.  ``Model.forward`` hands device pointers to the
+hand-written sm_100a kernels in ``libwunet_b200.so`` through the C ABI (``include/wunet_b200.h``).
+There is no CPU or PyTorch fallback for the eval forward: a CPU tensor or a missing library raises.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+__all__ = ["Model", "DownSamplingLayer", "UpSamplingLayer"]
+
+
+def _conv_bn_act(cin: int, cout: int, k: int, inplace: bool) -> nn.Sequential:
+    # index 0 = Conv1d, 1 = BatchNorm1d, 2 = LeakyReLU  -> keys "<prefix>.0.weight", "<prefix>.1.running_mean", ...
+    return nn.Sequential(
+        nn.Conv1d(cin, cout, kernel_size=k, stride=1, padding=(k - 1) // 2),
+        nn.BatchNorm1d(cout),
+        nn.LeakyReLU(negative_slope=0.1, inplace=inplace),
+    )
+
+
+class DownSamplingLayer(nn.Module):
+    """Parameter container named like the reference's encoder block (model/unet_basic.py:6-17)."""
+
+    def __init__(self, channel_in: int, channel_out: int, kernel_size: int = 15):
+        super().__init__()
+        self.main = _conv_bn_act(channel_in, channel_out, kernel_size, inplace=False)
+
+    def forward(self, ipt):  # pragma: no cover - only the opt-in torch training path calls this
+        return self.main(ipt)
+
+
+class UpSamplingLayer(nn.Module):
+    """Parameter container named like the reference's decoder block (model/unet_basic.py:19-30)."""
+
+    def __init__(self, channel_in: int, channel_out: int, kernel_size: int = 5):
+        super().__init__()
+        self.main = _conv_bn_act(channel_in, channel_out, kernel_size, inplace=True)
+
+    def forward(self, ipt):  # pragma: no cover
+        return self.main(ipt)
+
+
+class Model(nn.Module):
+    """Wave-U-Net whose eval forward runs on hand-written sm_100a kernels.
+
+    Extra keyword arguments (not in the reference; configs pass ``"args": {}`` so defaults apply):
+
+    precision      "fp32" (default; FFMA path, <=1e-4 vs the reference) or "bf16" (tcgen05 path).
+    train_backend  "none" (default): a forward in training mode raises
+                   NotImplementedError — the training step is SURVEY §8(f) row N1, not built yet.
+                   "torch": opt-in composite of torch ops with the reference's semantics so that the
+                   unchanged ``trainer/trainer.py`` loop can be driven for boundary tests; it is not
+                   part of the measured hot path.
+    """
+
+    def __init__(self, n_layers: int = 12, channels_interval: int = 24, precision: str = "fp32",
+                 train_backend: str = "none"):
+        super().__init__()
+        if precision not in _lib.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}, got {precision!r}")
+        if train_backend not in ("none", "torch"):
+            raise ValueError("train_backend must be 'none' or 'torch'")
+        self.n_layers = n_layers
+        self.channels_interval = channels_interval
+        self.precision = precision
+        self.train_backend = train_backend
+        n, ci = n_layers, channels_interval
+
+        enc_in = [1] + [i * ci for i in range(1, n)]
+        enc_out = [(i + 1) * ci for i in range(n)]
+        self.encoder = nn.ModuleList(DownSamplingLayer(a, b) for a, b in zip(enc_in, enc_out))
+        self.middle = _conv_bn_act(n * ci, n * ci, 15, inplace=True)
+        dec_out = enc_out[::-1]
+        dec_in = [2 * n * ci] + [(2 * (n - j) + 1) * ci for j in range(1, n)]
+        self.decoder = nn.ModuleList(UpSamplingLayer(a, b) for a, b in zip(dec_in, dec_out))
+        self.out = nn.Sequential(nn.Conv1d(ci + 1, 1, kernel_size=1, stride=1), nn.Tanh())
+
+        # native state (not part of state_dict)
+        self._ctx: Optional[ctypes.c_void_p] = None
+        self._ctx_device: Optional[int] = None
+        self._weights_key: Optional[Tuple] = None
+        self._workspaces: Dict[Tuple, torch.Tensor] = {}
+        self._last_ws: Optional[Tuple] = None
+
+    # ------------------------------------------------------------------------------------------
+    # native plumbing
+    # ------------------------------------------------------------------------------------------
+    def _blocks(self):
+        return [e.main for e in self.encoder] + [self.middle] + [d.main for d in self.decoder]
+
+    def _context(self, device: torch.device) -> ctypes.c_void_p:
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        if self._ctx is not None and self._ctx_device == idx:
+            return self._ctx
+        self._release()
+        lib = _lib.load()
+        ctx = ctypes.c_void_p()
+        _lib.check(lib.wunet_create(self.n_layers, self.channels_interval, idx, ctypes.byref(ctx)))
+        self._ctx, self._ctx_device = ctx, idx
+        self._weights_key = None
+        return ctx
+
+    def _release(self):
+        if self.__dict__.get("_ctx") is not None:
+            try:
+                _lib.load().wunet_destroy(self._ctx)
+            except Exception:  # pragma: no cover - interpreter shutdown
+                pass
+        self._ctx = None
+        self._ctx_device = None
+        self._weights_key = None
+        self._workspaces = {}
+        self._last_ws = None
+
+    def __del__(self):
+        self._release()
+
+    def _param_tensors(self):
+        ts = []
+        for blk in self._blocks():
+            conv, bn = blk[0], blk[1]
+            ts += [conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var]
+        ts += [self.out[0].weight, self.out[0].bias]
+        return ts
+
+    def _sync_weights(self, ctx, device: torch.device):
+        """(Re)pack the library's weight copies when any parameter/buffer changed: optimizer.step()
+        and load_state_dict bump ``_version``; .cpu()/.to() change ``data_ptr``."""
+        ts = self._param_tensors()
+        key = tuple((t.data_ptr(), t._version) for t in ts)
+        if key == self._weights_key:
+            return
+        for t in ts:
+            if t.device != device:
+                raise RuntimeError(f"parameter on {t.device} but input on {device}: call model.to(device) first")
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                raise RuntimeError("libwunet_b200 needs contiguous float32 parameters")
+        nb = len(self._blocks())
+        arrs = []
+        for slot in range(6):
+            arrs.append((ctypes.c_void_p * nb)(*[ts[6 * i + slot].data_ptr() for i in range(nb)]))
+        stream = torch.cuda.current_stream(device).cuda_stream
+        _lib.check(_lib.load().wunet_set_weights(ctx, *arrs, ts[-2].data_ptr(), ts[-1].data_ptr(), stream))
+        self._weights_key = key
+
+    def _workspace(self, ctx, B: int, T: int, prec: int, device: torch.device) -> torch.Tensor:
+        key = (B, T, prec, device.index)
+        ws = self._workspaces.get(key)
+        if ws is None:
+            nbytes = _lib.load().wunet_workspace_bytes(ctx, B, T, prec)
+            if nbytes == 0:
+                _lib.check(-1)
+            self._workspaces = {}          # keep one shape resident (frames are fixed-length in practice)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            self._workspaces[key] = ws
+        self._last_ws = key
+        return ws
+
+    # ------------------------------------------------------------------------------------------
+    # forward
+    # ------------------------------------------------------------------------------------------
+    def forward(self, input: torch.Tensor) -> torch.Tensor:  # noqa: A002 - reference argument name
+        if self.training:
+            if self.train_backend == "torch":
+                return self._forward_torch_reference_semantics(input)
+            raise NotImplementedError(
+                "libwunet_b200 implements the eval-mode forward (SURVEY §8 rows a–e). Training-mode BatchNorm / "
+                "autograd (row N1) is not built yet: call model.eval(), or construct the model with "
+                "train_backend='torch' to opt into the composite PyTorch training path.")
+        # eval mode: like enhancement.py:66 (`model(chunk).detach().cpu()`, no torch.no_grad()) the result is
+        # returned detached — the native path records no autograd graph.
+        return self._forward_native(input)
+
+    def _check_input(self, x: torch.Tensor):
+        if x.dim() != 3 or x.size(1) != 1:
+            raise RuntimeError(f"expected input of shape [B, 1, T], got {tuple(x.shape)}")
+        if x.dtype != torch.float32:
+            raise RuntimeError(f"expected float32 input, got {x.dtype}")
+
+    def _forward_native(self, x: torch.Tensor) -> torch.Tensor:
+        self._check_input(x)
+        if not x.is_cuda:
+            raise RuntimeError("wave_u_net_for_speech_enhancement_b200 has no CPU fallback: move the model and the "
+                               "input to a CUDA (sm_100a) device")
+        x = x.contiguous()
+        B, _, T = x.shape
+        lib = _lib.load()
+        with torch.cuda.device(x.device):
+            ctx = self._context(x.device)
+            self._sync_weights(ctx, x.device)
+            prec = _lib.PRECISIONS[self.precision]
+            ws = self._workspace(ctx, B, T, prec, x.device)
+            y = torch.empty_like(x)
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+            _lib.check(lib.wunet_forward(ctx, x.data_ptr(), y.data_ptr(), B, T, prec, ws.data_ptr(), ws.numel(), stream))
+        return y
+
+    @torch.no_grad()
+    def forward_host(self, x_host: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """End-to-end form of enhancement.py:64-66 (``model(chunk).detach().cpu()``): host tensor in,
+        host tensor out; H2D copy, kernels and D2H copy are enqueued by ``wunet_forward_host``.
+        Parameters must already live on a CUDA device. Pinned tensors give full copy bandwidth."""
+        self._check_input(x_host)
+        if x_host.is_cuda:
+            raise RuntimeError("forward_host takes a host tensor")
+        if self.training:
+            raise NotImplementedError("forward_host is eval-only")
+        x_host = x_host.contiguous()
+        device = self.out[0].weight.device
+        if device.type != "cuda":
+            raise RuntimeError("no CPU fallback: move the model to a CUDA device first")
+        B, _, T = x_host.shape
+        if out is None:
+            out = torch.empty_like(x_host, pin_memory=x_host.is_pinned())
+        with torch.cuda.device(device):
+            ctx = self._context(device)
+            cur = torch.cuda.current_stream(device)
+            self._sync_weights(ctx, device)
+            cur.synchronize()                      # packing ran on torch's stream; forward_host uses its own
+            _lib.check(_lib.load().wunet_forward_host(ctx, x_host.data_ptr(), out.data_ptr(), B, T,
+                                                      _lib.PRECISIONS[self.precision]))
+        return out
+
+    @torch.no_grad()
+    def read_level(self, block: int, B: int, T: int) -> torch.Tensor:
+        """Diagnostic: full-resolution output of block ``block`` (0..2n: encoder i / middle / decoder j)
+        of the LAST native forward with this (B, T), as fp32 [B, Cout, L] — what a forward hook on the
+        reference's encoder[i] / middle / decoder[j] returns. Used by the per-level parity tests."""
+        prec = _lib.PRECISIONS[self.precision]
+        device = self.out[0].weight.device
+        key = (B, T, prec, device.index)
+        if self._ctx is None or key not in self._workspaces:
+            raise RuntimeError("read_level: run a native forward with this (B, T) first")
+        n = self.n_layers
+        cout = self._blocks()[block][0].out_channels
+        L = (T >> block) if block <= n else (T >> (2 * n - block))
+        out = torch.empty(B, cout, L, dtype=torch.float32, device=device)
+        ws = self._workspaces[key]
+        with torch.cuda.device(device):
+            stream = torch.cuda.current_stream(device).cuda_stream
+            _lib.check(_lib.load().wunet_read_level(self._ctx, block, ws.data_ptr(), B, T, prec, out.data_ptr(), stream))
+        return out
+
+    def profile(self, enable: bool) -> None:
+        """Measurement hook: record per-block CUDA events in subsequent native forwards."""
+        if self._ctx is None:
+            raise RuntimeError("profile(): run a native forward first")
+        _lib.check(_lib.load().wunet_profile_enable(self._ctx, 1 if enable else 0))
+
+    def profile_read(self):
+        """Per-block device times (ms) of the last profiled forward: 2n+1 conv blocks, then the head."""
+        cap = 2 * self.n_layers + 2
+        buf = (ctypes.c_float * cap)()
+        cnt = ctypes.c_int(0)
+        _lib.check(_lib.load().wunet_profile_read(self._ctx, buf, cap, ctypes.byref(cnt)))
+        return [float(buf[i]) for i in range(cnt.value)]
+
+    def last_launch_count(self) -> int:
+        return 0 if self._ctx is None else int(_lib.load().wunet_last_launch_count(self._ctx))
+
+    # ------------------------------------------------------------------------------------------
+    # opt-in composite path with the reference's training semantics (NOT the product hot path)
+    # ------------------------------------------------------------------------------------------
+    def _forward_torch_reference_semantics(self, x: torch.Tensor) -> torch.Tensor:
+        import torch.nn.functional as F
+        skips = []
+        o = x
+        for layer in self.encoder:
+            o = layer(o)
+            skips.append(o)
+            o = o[:, :, ::2]
+        o = self.middle(o)
+        for j, layer in enumerate(self.decoder):
+            o = F.interpolate(o, scale_factor=2, mode="linear", align_corners=True)
+            o = layer(torch.cat([o, skips[self.n_layers - 1 - j]], dim=1))
+        return self.out(torch.cat([o, x], dim=1))
+
+    # nn.Module hooks: any structural move invalidates the native context lazily (keys are checked per call)
+    def _apply(self, fn, *args, **kwargs):
+        r = super()._apply(fn, *args, **kwargs)
+        self._weights_key = None
+        return r
