@@ -1,26 +1,780 @@
-// wunet_tc.cu — bf16 / tcgen05 path (placeholder until the tensor-core kernels land).
+// wunet_tc.cu — bf16 tensor-core path of the Wave-U-Net forward for sm_100a (tcgen05 + TMEM + TMA).
+//
+// Data layout in HBM: every activation is channels-last bf16, [B][L][C] ("NLC"), C = the reference's
+// channel count (24*m). A Conv1d tap shift is then a whole-row shift of the operand tile.
+//
+// Each conv block (reference: [decimate | interpolate+cat] -> Conv1d -> BatchNorm1d(eval) -> LeakyReLU,
+// model/unet_basic.py:83-86, :93-96, :10-13, :23-26) is ONE kernel, an implicit GEMM
+//     D[position, cout] = sum_taps sum_cin  X[position + tap - pad, cin] * W[tap][cout, cin]
+// with M = 128*MT output positions per CTA (TMEM lanes), N = Cout (padded to 16) and the K loop running
+// over 64-channel chunks x taps:
+//   * the input tile (128*MT + K-1 rows x 64 channels, 128B-swizzled) is loaded ONCE per chunk by TMA;
+//     out-of-range rows/channels are zero-filled by TMA = Conv1d zero padding, per frame;
+//     every tap reuses it through a UMMA shared-memory descriptor whose start address is advanced by
+//     tap*128 B (verified on hardware by tools/umma_probe.cu);
+//   * encoder decimation o[:, :, ::2] is a tensor map with a doubled row stride (no copy);
+//   * decoder: the K axis is [upsampled previous output | skip]. The skip half comes by TMA; the upsampled
+//     half (F.interpolate linear, align_corners=True, index math in fp32 like ATen) is produced by four
+//     warps straight into the swizzled operand tile — the interpolated/concatenated tensor never exists in HBM;
+//   * weights stream through a TMA ring, one [N x 64] tile per (chunk, tap), shared by the MT sub-tiles;
+//   * accumulators live in TMEM (MT x N fp32 columns); the epilogue warps read them with tcgen05.ld, apply the
+//     folded BatchNorm scale/shift and LeakyReLU(0.1), and store bf16 NLC rows; the last decoder block also
+//     applies the 1x1 conv over [decoder out | raw input] and tanh (model/unet_basic.py:98-99) so its 24-channel
+//     output never reaches HBM.
+//   * frames shorter than 128 samples (the bottom of the U) are packed several per tile with their own halo
+//     rows; rows that straddle two frames are computed and discarded.
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2-5 = upsample
+// producers during the main loop, then epilogue (TMEM lane quadrant = warp % 4).
 #include "wunet_tc.cuh"
+#include "wunet_common.cuh"
+
+#include <cuda.h>
+#include <cstdarg>
 #include <cstdio>
+#include <cstring>
+#include <map>
+#include <vector>
 
 namespace wunet {
-struct TcState { int dummy; };
-static thread_local char g_tc_err[256] = "";
-const char *tc_error() { return g_tc_err; }
-int tc_set_weights(TcState **st, int, int, const TcBlockSrc *, int, const float *, const float *, cudaStream_t)
+
+namespace {
+
+thread_local char g_tc_err[512] = "";
+int tc_fail(const char *fmt, ...)
 {
-    if (!*st) *st = new TcState{0};
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_tc_err, sizeof(g_tc_err), fmt, ap);
+    va_end(ap);
+    return -1;
+}
+
+constexpr int kThreads = 192;
+constexpr int kMaxBStages = 8;
+constexpr int kSmemLimit = 227 * 1024;
+
+inline int round_up(int v, int a) { return (v + a - 1) / a * a; }
+inline size_t round_up_sz(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// -------------------------------------------------------------------------------------------------
+// device helpers (raw PTX; forms taken from the PTX ISA as shipped in CUDA 12.9)
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// K-major, 128B-swizzled operand: 8-row groups 1024 B apart; base_offset stays 0 for any start row
+// (swizzle acts on absolute shared-memory address bits; tools/umma_probe.cu)
+__device__ __forceinline__ uint64_t sw128_desc(uint32_t saddr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;                       // LBO (ignored for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;             // SBO
+    d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b)
+{
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&h);
+}
+__device__ __forceinline__ float lrelu(float v) { return v >= 0.f ? v : kLreluSlope * v; }
+
+}  // namespace
+
+// -------------------------------------------------------------------------------------------------
+// kernel parameters
+// -------------------------------------------------------------------------------------------------
+struct TcParams {
+    // problem
+    int B, L, Cout, T;
+    int Cin0, Cin1;            // K segments: ENC: Cin0 = Cin, Cin1 = 0; DEC: Cin0 = upsampled prev, Cin1 = skip
+    int nchunks0, nchunks;     // 64-channel chunks in segment 0 / in total
+    // N tiling
+    int Npad, Nh, Nstride;     // padded Cout, columns per CTA, TMEM column stride between sub-tile accumulators
+    // M tiling
+    int MT, packed, S, FR, tiles_per_frame;
+    int nops, R1, a_tx_bytes;  // TMA ops per A chunk, rows advanced per op, bytes per chunk
+    int rows_used;             // smem rows the producers must fill (upsample path)
+    uint32_t a_stage_bytes, b_stage_bytes;
+    int nb;                    // B ring depth
+    uint32_t tmem_cols;
+    // operands
+    const __nv_bfloat16 *prev; // DEC: previous block output [B][L/2][Cin0]
+    int Lin;
+    float up_scale;
+    const float2 *ss;          // [Npad] (scale, shift)
+    __nv_bfloat16 *out;        // [B][L][Cout] or nullptr (fused head without debug store)
+    // fused head (last decoder): y = tanh(out_w[:C] . v + out_w[C] * x + out_b)
+    int head;
+    const float *x;            // [B][T] raw input
+    float *y;                  // [B][T]
+    const float *head_w;       // [C+1]
+    const float *head_b;       // [1]
+};
+
+// smem carve-up (offsets from the 1024-aligned base): A stages | B stages | ss | barriers
+struct SmemMap {
+    uint32_t a, b, ss, bars;
+};
+__host__ __device__ inline SmemMap smem_map(const TcParams &p)
+{
+    SmemMap m;
+    m.a = 0;
+    m.b = 2 * p.a_stage_bytes;
+    m.ss = m.b + p.nb * p.b_stage_bytes;
+    m.bars = m.ss + (uint32_t)p.Nh * 8;
+    m.bars = (m.bars + 15) & ~15u;
+    return m;
+}
+inline size_t smem_total(const TcParams &p) { return smem_map(p).bars + 8 * (4 + 2 * kMaxBStages + 1) + 16 + 1024; }
+
+__device__ __forceinline__ int chunk_k16(const TcParams &p, int c)
+{
+    const int seg_c = (c < p.nchunks0) ? p.Cin0 - 64 * c : p.Cin1 - 64 * (c - p.nchunks0);
+    const int ch = seg_c < 64 ? seg_c : 64;
+    return (ch + 15) >> 4;
+}
+
+// -------------------------------------------------------------------------------------------------
+// the conv kernel
+// -------------------------------------------------------------------------------------------------
+template <int KS, bool UPCAT>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TcParams p)
+{
+    constexpr int PAD = (KS - 1) / 2;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t *base_ptr = smem_raw + (base - smem_u32(smem_raw));
+    const SmemMap sm = smem_map(p);
+    const uint32_t bars = base + sm.bars;
+    // barrier slots (8 B each): a_full[2], a_empty[2], b_full[8], b_empty[8], acc_full, then tmem slot
+    const uint32_t a_full = bars, a_empty = bars + 16, b_full = bars + 32, b_empty = bars + 32 + 8 * kMaxBStages;
+    const uint32_t acc_full = bars + 32 + 16 * kMaxBStages;
+    const uint32_t tmem_slot = acc_full + 8;
+    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(base_ptr + sm.bars + 32 + 16 * kMaxBStages + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.y * p.Nh;
+    const int Nthis = min(p.Nh, p.Npad - n0);
+
+    int b0, l0;
+    if (p.packed) { b0 = blockIdx.x * p.FR; l0 = 0; }
+    else { b0 = blockIdx.x / p.tiles_per_frame; l0 = (blockIdx.x - b0 * p.tiles_per_frame) * 128 * p.MT; }
+
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
+        for (int s = 0; s < 2; ++s) { mbar_init(a_full + 8 * s, UPCAT ? 5 : 1); mbar_init(a_empty + 8 * s, 1); }
+        for (int s = 0; s < p.nb; ++s) { mbar_init(b_full + 8 * s, 1); mbar_init(b_empty + 8 * s, 1); }
+        mbar_init(acc_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    {   // folded BatchNorm scale/shift of this CTA's columns
+        float2 *ss = reinterpret_cast<float2 *>(base_ptr + sm.ss);
+        for (int i = threadIdx.x; i < Nthis; i += kThreads) ss[i] = p.ss[n0 + i];
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ======================= TMA producer =======================
+        if (lane == 0) {
+            int sa = 0, pa = 0, sb = 0, pb = 0;
+            const int lcoord = p.packed ? -PAD : l0 - PAD;
+            for (int c = 0; c < p.nchunks; ++c) {
+                const bool from_tma = !UPCAT || c >= p.nchunks0;
+                mbar_wait(a_empty + 8 * sa, pa ^ 1);
+                if (from_tma) {
+                    const int cc = UPCAT ? c - p.nchunks0 : c;
+                    mbar_expect_tx(a_full + 8 * sa, p.a_tx_bytes);
+                    for (int op = 0; op < p.nops; ++op)
+                        tma_load_3d(base + sm.a + sa * p.a_stage_bytes + op * p.R1 * 128, &tmA, a_full + 8 * sa, cc * 64,
+                                    lcoord + op * p.R1, b0);
+                } else {
+                    mbar_arrive(a_full + 8 * sa);
+                }
+                for (int t = 0; t < KS; ++t) {
+                    mbar_wait(b_empty + 8 * sb, pb ^ 1);
+                    mbar_expect_tx(b_full + 8 * sb, p.Nh * 128);
+                    tma_load_3d(base + sm.b + sb * p.b_stage_bytes, &tmW, b_full + 8 * sb, c * 64, n0, t);
+                    if (++sb == p.nb) { sb = 0; pb ^= 1; }
+                }
+                if (++sa == 2) { sa = 0; pa ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ======================= MMA issuer =======================
+        if (lane == 0) {
+            // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Nthis >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            int sa = 0, pa = 0, sb = 0, pb = 0;
+            for (int c = 0; c < p.nchunks; ++c) {
+                const int nk = chunk_k16(p, c);
+                mbar_wait(a_full + 8 * sa, pa);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_base = base + sm.a + sa * p.a_stage_bytes;
+                for (int t = 0; t < KS; ++t) {
+                    mbar_wait(b_full + 8 * sb, pb);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t b_base = base + sm.b + sb * p.b_stage_bytes;
+                    for (int mt = 0; mt < p.MT; ++mt) {
+                        const uint32_t a_row = a_base + (uint32_t)(mt * 128 + t) * 128;
+                        for (int kk = 0; kk < nk; ++kk)
+                            umma_bf16(tmem_base + mt * p.Nstride, sw128_desc(a_row + kk * 32), sw128_desc(b_base + kk * 32),
+                                      idesc, (c | t | kk) ? 1u : 0u);
+                    }
+                    umma_commit(b_empty + 8 * sb);
+                    if (++sb == p.nb) { sb = 0; pb ^= 1; }
+                }
+                umma_commit(a_empty + 8 * sa);
+                if (++sa == 2) { sa = 0; pa ^= 1; }
+            }
+            umma_commit(acc_full);
+        }
+    } else {
+        // ======================= upsample producers (decoder), then epilogue =======================
+        if (UPCAT) {
+            const int pt = (warp - 2) * 32 + lane;
+            int sa = 0, pa = 0;
+            for (int c = 0; c < p.nchunks; ++c) {
+                mbar_wait(a_empty + 8 * sa, pa ^ 1);
+                if (c < p.nchunks0) {
+                    const int nvec = chunk_k16(p, c) * 2;                    // 16-byte vectors per row
+                    uint8_t *dst = base_ptr + sm.a + sa * p.a_stage_bytes;
+                    const int items = p.rows_used * nvec;
+                    for (int it = pt; it < items; it += 128) {
+                        const int row = it / nvec, vec = it - row * nvec;
+                        int bb, l;
+                        if (p.packed) { const int f = row / p.S; bb = b0 + f; l = row - f * p.S - PAD; }
+                        else { bb = b0; l = l0 - PAD + row; }
+                        const int ch = c * 64 + vec * 8;
+                        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                        if (bb < p.B && l >= 0 && l < p.L && ch < p.Cin0) {
+                            // F.interpolate(scale_factor=2, mode="linear", align_corners=True): ATen index math in fp32
+                            const float s = p.up_scale * (float)l;
+                            const int i0 = (int)s;
+                            const int i1 = i0 + (i0 < p.Lin - 1 ? 1 : 0);
+                            const float lam1 = s - (float)i0, lam0 = 1.f - lam1;
+                            const __nv_bfloat16 *r0 = p.prev + ((size_t)bb * p.Lin + i0) * p.Cin0 + ch;
+                            const __nv_bfloat16 *r1 = p.prev + ((size_t)bb * p.Lin + i1) * p.Cin0 + ch;
+                            const uint4 u0 = __ldg(reinterpret_cast<const uint4 *>(r0));
+                            const uint4 u1 = __ldg(reinterpret_cast<const uint4 *>(r1));
+                            const uint32_t a0[4] = {u0.x, u0.y, u0.z, u0.w}, a1[4] = {u1.x, u1.y, u1.z, u1.w};
+                            uint32_t r[4];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&a0[q]));
+                                const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&a1[q]));
+                                r[q] = pack_bf16(lam0 * f0.x + lam1 * f1.x, lam0 * f0.y + lam1 * f1.y);
+                            }
+                            o = make_uint4(r[0], r[1], r[2], r[3]);
+                        }
+                        *reinterpret_cast<uint4 *>(dst + row * 128 + ((vec ^ (row & 7)) << 4)) = o;
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor core reads
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(a_full + 8 * sa);
+                if (++sa == 2) { sa = 0; pa ^= 1; }
+            }
+        }
+        // ---- epilogue ----
+        mbar_wait(acc_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int q = warp & 3;
+        const float2 *ss = reinterpret_cast<const float2 *>(base_ptr + sm.ss);
+        const int ncc = (Nthis + 31) >> 5;
+        for (int mt = 0; mt < p.MT; ++mt) {
+            const int row = mt * 128 + q * 32 + lane;
+            int bb, l;
+            if (p.packed) { const int f = row / p.S; bb = b0 + f; l = row - f * p.S; if (f >= p.FR) l = p.L; }
+            else { bb = b0; l = l0 + row; }
+            const bool valid = (bb < p.B) && (l < p.L);
+            for (int cc = 0; cc < ncc; ++cc) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * p.Nstride + cc * 32), v);
+                if (!valid) continue;
+                const int colbase = cc * 32;
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float2 s = (colbase + j < Nthis) ? ss[colbase + j] : make_float2(0.f, 0.f);
+                    f[j] = lrelu(fmaf(__uint_as_float(v[j]), s.x, s.y));
+                }
+                if (p.out != nullptr) {
+                    __nv_bfloat16 *orow = p.out + ((size_t)bb * p.L + l) * p.Cout + n0 + colbase;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        if (colbase + g * 8 < Nthis && n0 + colbase + g * 8 < p.Cout) {
+                            const uint4 o = make_uint4(pack_bf16(f[g * 8 + 0], f[g * 8 + 1]), pack_bf16(f[g * 8 + 2], f[g * 8 + 3]),
+                                                       pack_bf16(f[g * 8 + 4], f[g * 8 + 5]), pack_bf16(f[g * 8 + 6], f[g * 8 + 7]));
+                            *reinterpret_cast<uint4 *>(orow + g * 8) = o;
+                        }
+                    }
+                }
+                if (p.head) {
+                    // cat([o, input], 1) -> Conv1d(C+1 -> 1, k=1) -> Tanh   (model/unet_basic.py:98-99)
+                    float acc = __ldg(p.head_b);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < p.Cout) acc = fmaf(__ldg(p.head_w + j), f[j], acc);
+                    acc = fmaf(__ldg(p.head_w + p.Cout), __ldg(p.x + (size_t)bb * p.T + l), acc);
+                    p.y[(size_t)bb * p.T + l] = tanhf(acc);
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols));
+}
+
+// -------------------------------------------------------------------------------------------------
+// enc0: Conv1d(1 -> C, k=15) + BN + LeakyReLU on CUDA cores (Cin = 1: K = 15, HBM-bound), fp32 in, bf16 NLC out
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) enc0_kernel(const float *__restrict__ x, const float *__restrict__ w /*[C][1][15]*/,
+                                                   const float *__restrict__ scale, const float *__restrict__ shift,
+                                                   __nv_bfloat16 *__restrict__ out, int B, int T, int C)
+{
+    constexpr int KS = 15, PAD = 7, PPT = 4;                  // positions per thread
+    extern __shared__ uint8_t smem_raw[];
+    float *ws = reinterpret_cast<float *>(smem_raw);          // [15][C]
+    float *sc = ws + KS * C, *sh = sc + C;
+    float *xs = sh + C;                                       // [256*PPT + 14]
+    const int b = blockIdx.y;
+    const int l0 = blockIdx.x * (256 * PPT);
+    for (int i = threadIdx.x; i < KS * C; i += 256) { const int k = i / C, c = i - k * C; ws[i] = w[c * KS + k]; }
+    for (int i = threadIdx.x; i < C; i += 256) { sc[i] = scale[i]; sh[i] = shift[i]; }
+    for (int i = threadIdx.x; i < 256 * PPT + KS - 1; i += 256) {
+        const int l = l0 - PAD + i;
+        xs[i] = (l >= 0 && l < T) ? x[(size_t)b * T + l] : 0.f;
+    }
+    __syncthreads();
+    // thread handles positions threadIdx.x + 256*j (coalesced-ish stores of C*2 bytes per position)
+    float xv[PPT][KS];
+#pragma unroll
+    for (int j = 0; j < PPT; ++j)
+#pragma unroll
+        for (int k = 0; k < KS; ++k) xv[j][k] = xs[threadIdx.x + 256 * j + k];
+    for (int c0 = 0; c0 < C; c0 += 8) {
+        float acc[PPT][8];
+#pragma unroll
+        for (int j = 0; j < PPT; ++j)
+#pragma unroll
+            for (int m = 0; m < 8; ++m) acc[j][m] = 0.f;
+#pragma unroll
+        for (int k = 0; k < KS; ++k) {
+            const float4 w0 = *reinterpret_cast<const float4 *>(&ws[k * C + c0]);
+            const float4 w1 = *reinterpret_cast<const float4 *>(&ws[k * C + c0 + 4]);
+            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+            for (int j = 0; j < PPT; ++j)
+#pragma unroll
+                for (int m = 0; m < 8; ++m) acc[j][m] = fmaf(wv[m], xv[j][k], acc[j][m]);
+        }
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) {
+            const int l = l0 + threadIdx.x + 256 * j;
+            if (l < T) {
+                float f[8];
+#pragma unroll
+                for (int m = 0; m < 8; ++m) f[m] = lrelu(fmaf(acc[j][m], sc[c0 + m], sh[c0 + m]));
+                const uint4 o = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+                *reinterpret_cast<uint4 *>(out + ((size_t)b * T + l) * C + c0) = o;
+            }
+        }
+    }
+}
+
+// weights [Cout][Cin][K] fp32 -> [K][Npad][Ktot] bf16, K axis = [seg0 padded to 64 | seg1 padded to 64], zero padded
+__global__ void pack_tc_kernel(const float *__restrict__ w, const float *__restrict__ scale, const float *__restrict__ shift,
+                               __nv_bfloat16 *__restrict__ wp, float2 *__restrict__ ss, int Cout, int Cin0, int Cin1, int K,
+                               int Npad, int Ktot)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n = (long long)K * Npad * Ktot;
+    if (i < n) {
+        const int ks = (int)(i % Ktot);
+        const int co = (int)((i / Ktot) % Npad);
+        const int t = (int)(i / ((long long)Ktot * Npad));
+        const int seg1_base = (Cin0 + 63) / 64 * 64;
+        int ci = -1;
+        if (ks < seg1_base) { if (ks < Cin0) ci = ks; }
+        else { if (ks - seg1_base < Cin1) ci = Cin0 + (ks - seg1_base); }
+        float v = 0.f;
+        if (co < Cout && ci >= 0) v = w[((size_t)co * (Cin0 + Cin1) + ci) * K + t];
+        wp[i] = __float2bfloat16(v);
+    }
+    if (i < Npad) ss[i] = (i < Cout) ? make_float2(scale[i], shift[i]) : make_float2(0.f, 0.f);
+}
+
+__global__ void nlc_bf16_to_ncl_f32_kernel(const __nv_bfloat16 *__restrict__ src, float *__restrict__ dst, int B, int L, int C)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;       // index into dst [B][C][L]
+    const long long n = (long long)B * C * L;
+    if (i >= n) return;
+    const int l = (int)(i % L);
+    const int c = (int)((i / L) % C);
+    const int b = (int)(i / ((long long)L * C));
+    dst[i] = __bfloat162float(src[((size_t)b * L + l) * C + c]);
+}
+
+// -------------------------------------------------------------------------------------------------
+// host side
+// -------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct TcLevel {
+    int cin0, cin1, cout, k;
+    int Npad, Ktot;
+    __nv_bfloat16 *wp = nullptr;
+    float2 *ss = nullptr;
+    const float *w_src = nullptr;      // enc0 only: fp32 weights / scale / shift pointers (owned elsewhere)
+    const float *scale = nullptr, *shift = nullptr;
+};
+
+struct TcPlanLevel {
+    TcParams p;
+    CUtensorMap tmA, tmW;
+    dim3 grid;
+    size_t smem;
+    bool upcat;
+};
+
+struct TcPlan {
+    std::vector<TcPlanLevel> lv;       // index 1..2n (0 = enc0 handled separately)
+    std::vector<size_t> off;           // workspace offsets of the 2n+1 block outputs
+};
+
+struct TcState {
+    int n = 0, ci = 0;
+    std::vector<TcLevel> levels;       // 2n+1
+    const float *out_w = nullptr, *out_b = nullptr;
+    EncodeTiledFn encode = nullptr;
+    bool store_last = false;           // WUNET_TC_STORE_LAST=1: also materialise the last decoder block (tests)
+    bool attr_set = false;
+    // plan cache, keyed on (workspace pointer, B, T)
+    const void *plan_ws = nullptr;
+    int plan_B = 0, plan_T = 0;
+    const float *plan_x = nullptr;
+    float *plan_y = nullptr;
+    TcPlan plan;
+};
+
+const char *tc_error() { return g_tc_err; }
+
+static void tc_layout(int n, int ci, int B, int T, std::vector<size_t> &off, size_t &total)
+{
+    off.resize(2 * n + 1);
+    size_t cur = 0;
+    for (int i = 0; i < 2 * n + 1; ++i) {
+        const int L = (i <= n) ? (T >> i) : (T >> (2 * n - i));
+        const int cout = (i < n) ? (i + 1) * ci : (i == n ? n * ci : (2 * n - i + 1) * ci);
+        off[i] = cur;
+        cur += round_up_sz((size_t)B * L * cout * sizeof(__nv_bfloat16), 1024);
+    }
+    total = cur + 1024;
+}
+
+size_t tc_workspace_bytes(int n, int ci, int B, int T)
+{
+    std::vector<size_t> off;
+    size_t total;
+    tc_layout(n, ci, B, T, off, total);
+    return total;
+}
+
+int tc_set_weights(TcState **pst, int n, int ci, const TcBlockSrc *blocks, int nblocks, const float *out_w,
+                   const float *out_b, cudaStream_t stream)
+{
+    if (nblocks != 2 * n + 1) return tc_fail("bad block count");
+    TcState *st = *pst;
+    if (!st) {
+        st = new TcState();
+        st->n = n; st->ci = ci;
+        st->levels.resize(nblocks);
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+            delete st;
+            return tc_fail("cuTensorMapEncodeTiled not available from the driver");
+        }
+        st->encode = reinterpret_cast<EncodeTiledFn>(fn);
+        const char *e = getenv("WUNET_TC_STORE_LAST");
+        st->store_last = e && e[0] == '1';
+        *pst = st;
+    }
+    st->out_w = out_w; st->out_b = out_b;
+    st->plan_ws = nullptr;                               // weights moved: rebuild maps lazily
+    for (int i = 0; i < nblocks; ++i) {
+        TcLevel &lv = st->levels[i];
+        lv.cout = blocks[i].cout; lv.k = blocks[i].k;
+        if (i <= n) { lv.cin0 = blocks[i].cin; lv.cin1 = 0; }
+        else { lv.cin0 = st->levels[i - 1].cout; lv.cin1 = blocks[i].cin - lv.cin0; }
+        lv.Npad = round_up(lv.cout, 16);
+        lv.Ktot = round_up(lv.cin0, 64) + (lv.cin1 ? round_up(lv.cin1, 64) : 0);
+        lv.w_src = blocks[i].w; lv.scale = blocks[i].scale; lv.shift = blocks[i].shift;
+    }
+    if (ci % 8 != 0 || ci > 32) return 0;                // tensor-core path unsupported for this plan; forward reports it
+    for (int i = 1; i < nblocks; ++i) {                  // enc0 runs on CUDA cores from the fp32 weights
+        TcLevel &lv = st->levels[i];
+        const size_t nel = (size_t)lv.k * lv.Npad * lv.Ktot;
+        if (!lv.wp) {
+            if (cudaMalloc(&lv.wp, nel * sizeof(__nv_bfloat16)) != cudaSuccess) return tc_fail("cudaMalloc(wp) failed");
+            if (cudaMalloc(&lv.ss, lv.Npad * sizeof(float2)) != cudaSuccess) return tc_fail("cudaMalloc(ss) failed");
+        }
+        pack_tc_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, stream>>>(blocks[i].w, blocks[i].scale, blocks[i].shift, lv.wp,
+                                                                          lv.ss, lv.cout, lv.cin0, lv.cin1, lv.k, lv.Npad, lv.Ktot);
+        if (cudaGetLastError() != cudaSuccess) return tc_fail("pack_tc_kernel launch failed");
+    }
     return 0;
 }
-size_t tc_workspace_bytes(int, int, int, int) { return 256; }
-int tc_forward(TcState *, const float *, float *, int, int, void *, cudaStream_t, int *, cudaEvent_t *)
+
+static int make_map(TcState *st, CUtensorMap *m, const void *base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1_bytes,
+                    uint64_t s2_bytes, uint32_t b0, uint32_t b1, uint32_t b2)
 {
-    snprintf(g_tc_err, sizeof(g_tc_err), "bf16 tcgen05 path not built yet");
-    return -1;
+    cuuint64_t gdim[3] = {d0, d1, d2};
+    cuuint64_t gstr[2] = {s1_bytes, s2_bytes};
+    cuuint32_t box[3] = {b0, b1, b2};
+    cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = st->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(base), gdim, gstr, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return tc_fail("cuTensorMapEncodeTiled failed (%d): dims %llu,%llu,%llu strides %llu,%llu box %u,%u,%u", (int)r,
+                       (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2, (unsigned long long)s1_bytes,
+                       (unsigned long long)s2_bytes, b0, b1, b2);
+    return 0;
 }
-int tc_read_level(TcState *, int, const void *, int, int, float *, cudaStream_t)
+
+static int build_plan(TcState *st, const float *x, float *y, int B, int T, void *ws)
 {
-    snprintf(g_tc_err, sizeof(g_tc_err), "bf16 tcgen05 path not built yet");
-    return -1;
+    const int n = st->n;
+    TcPlan &pl = st->plan;
+    size_t total;
+    tc_layout(n, st->ci, B, T, pl.off, total);
+    pl.lv.assign(2 * n + 1, TcPlanLevel{});
+    char *base = static_cast<char *>(ws);
+    auto lvl = [&](int i) { return reinterpret_cast<__nv_bfloat16 *>(base + pl.off[i]); };
+    for (int i = 1; i < 2 * n + 1; ++i) {
+        const TcLevel &lv = st->levels[i];
+        TcPlanLevel &P = pl.lv[i];
+        TcParams &p = P.p;
+        memset(&p, 0, sizeof(p));
+        const bool dec = i > n;
+        const int KS = lv.k;
+        const int L = (i <= n) ? (T >> i) : (T >> (2 * n - i));
+        P.upcat = dec;
+        p.B = B; p.L = L; p.Cout = lv.cout; p.T = T;
+        p.Cin0 = lv.cin0; p.Cin1 = lv.cin1;
+        p.nchunks0 = (lv.cin0 + 63) / 64;
+        p.nchunks = p.nchunks0 + (lv.cin1 + 63) / 64;
+        p.Npad = lv.Npad;
+        const int nsplit = lv.Npad > 256 ? 2 : 1;
+        p.Nh = nsplit == 1 ? lv.Npad : round_up(lv.Npad / 2, 16);
+        p.Nstride = round_up(p.Nh, 32);
+        int mtcap = 512 / p.Nstride;
+        if (mtcap > 4) mtcap = 4;
+        if (mtcap == 3) mtcap = 2;
+        p.b_stage_bytes = (uint32_t)round_up(p.Nh * 128, 1024);
+        for (int MT = mtcap; MT >= 1; MT >>= 1) {
+            p.MT = MT;
+            if (L >= 128) {
+                p.packed = 0;
+                int mt_l = 1;
+                while (mt_l * 2 <= MT && L >= 128 * mt_l * 2) mt_l *= 2;
+                p.MT = MT = mt_l;
+                p.tiles_per_frame = (L + 128 * MT - 1) / (128 * MT);
+                const int rows = 128 * MT + KS - 1;
+                p.nops = (rows + 255) / 256;
+                p.R1 = round_up((rows + p.nops - 1) / p.nops, 8);
+                p.S = 0; p.FR = 1;
+                p.rows_used = rows;
+                p.a_stage_bytes = (uint32_t)round_up(p.nops * p.R1 * 128, 1024);
+                p.a_tx_bytes = p.nops * p.R1 * 128;
+                P.grid = dim3((unsigned)(B * p.tiles_per_frame), (unsigned)nsplit, 1);
+            } else {
+                p.packed = 1;
+                p.S = L + KS - 1;
+                // smallest MT whose frame capacity covers the batch, else the largest allowed
+                int FR = (128 * MT - L) / p.S + 1;
+                while (MT > 1 && (128 * (MT / 2) - L) / p.S + 1 >= B) { MT /= 2; FR = (128 * MT - L) / p.S + 1; }
+                if (FR > B) FR = B;
+                if (FR > 256) FR = 256;
+                p.MT = MT; p.FR = FR;
+                p.tiles_per_frame = 0;
+                p.nops = 1; p.R1 = p.S;
+                p.rows_used = FR * p.S;
+                const int rows_alloc = round_up(std::max(FR * p.S, 128 * MT + KS - 1), 8);
+                p.a_stage_bytes = (uint32_t)round_up(rows_alloc * 128, 1024);
+                p.a_tx_bytes = FR * p.S * 128;
+                P.grid = dim3((unsigned)((B + FR - 1) / FR), (unsigned)nsplit, 1);
+            }
+            int nb = ((int)kSmemLimit - 2048 - 2 * (int)p.a_stage_bytes - p.Nh * 8 - 256) / (int)p.b_stage_bytes;
+            if (nb > kMaxBStages) nb = kMaxBStages;
+            p.nb = nb;
+            if (nb >= 2) break;
+            if (MT == 1) return tc_fail("level %d does not fit in shared memory", i);
+        }
+        uint32_t cols = 32;
+        while ((int)cols < p.MT * p.Nstride) cols <<= 1;
+        p.tmem_cols = cols;
+        P.smem = smem_total(p);
+        if (P.smem > (size_t)kSmemLimit) return tc_fail("level %d: smem %zu too large", i, P.smem);
+
+        p.ss = lv.ss;
+        const bool last = (i == 2 * n);
+        p.out = (last && !st->store_last) ? nullptr : lvl(i);
+        p.head = last ? 1 : 0;
+        p.x = x; p.y = y; p.head_w = st->out_w; p.head_b = st->out_b;
+        if (last && lv.cout > 32) return tc_fail("fused head needs channels_interval <= 32");
+        // operand maps
+        if (!dec) {
+            // decimated view of the previous encoder output: element (c, l, b) -> prev[b][2l][c]   (o[:, :, ::2])
+            const int Cp = lv.cin0, Lp = 2 * L;
+            const uint32_t b1 = p.packed ? (uint32_t)p.S : (uint32_t)p.R1, b2 = p.packed ? (uint32_t)p.FR : 1u;
+            if (make_map(st, &P.tmA, lvl(i - 1), Cp, L, B, (uint64_t)2 * Cp * 2, (uint64_t)Lp * Cp * 2, 64, b1, b2)) return -1;
+        } else {
+            const int e = 2 * n - i;                        // skip = encoder e's full-resolution output
+            const int Cs = lv.cin1;
+            const uint32_t b1 = p.packed ? (uint32_t)p.S : (uint32_t)p.R1, b2 = p.packed ? (uint32_t)p.FR : 1u;
+            if (make_map(st, &P.tmA, lvl(e), Cs, L, B, (uint64_t)Cs * 2, (uint64_t)L * Cs * 2, 64, b1, b2)) return -1;
+            p.prev = lvl(i - 1);
+            p.Lin = L / 2;
+            p.up_scale = (L > 1) ? (float)(p.Lin - 1) / (float)(L - 1) : 0.f;
+        }
+        if (make_map(st, &P.tmW, lv.wp, lv.Ktot, lv.Npad, lv.k, (uint64_t)lv.Ktot * 2, (uint64_t)lv.Npad * lv.Ktot * 2, 64,
+                     (uint32_t)p.Nh, 1))
+            return -1;
+    }
+    st->plan_ws = ws; st->plan_B = B; st->plan_T = T; st->plan_x = x; st->plan_y = y;
+    return 0;
 }
-void tc_destroy(TcState *st) { delete st; }
+
+int tc_forward(TcState *st, const float *x, float *y, int B, int T, void *ws, cudaStream_t stream, int *launches,
+               cudaEvent_t *ev)
+{
+    if (!st) return tc_fail("tensor-core state missing");
+    const int n = st->n, ci = st->ci;
+    if (ci % 8 != 0 || ci > 32) return tc_fail("bf16 tcgen05 path needs channels_interval %% 8 == 0 and <= 32 (got %d)", ci);
+    if (!st->attr_set) {
+        cudaFuncSetAttribute(conv_tc_kernel<15, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+        cudaFuncSetAttribute(conv_tc_kernel<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+        st->attr_set = true;
+    }
+    if (st->plan_ws != ws || st->plan_B != B || st->plan_T != T || st->plan_x != x || st->plan_y != y)
+        if (build_plan(st, x, y, B, T, ws)) return -1;
+    TcPlan &pl = st->plan;
+    char *base = static_cast<char *>(ws);
+    int nl = 0;
+    if (ev) cudaEventRecord(ev[0], stream);
+    {   // enc0
+        const TcLevel &lv = st->levels[0];
+        const int C = lv.cout;
+        const size_t smem = (size_t)(15 * C + 2 * C + 256 * 4 + 14) * sizeof(float);
+        dim3 grid((unsigned)((T + 1023) / 1024), (unsigned)B, 1);
+        enc0_kernel<<<grid, 256, smem, stream>>>(x, lv.w_src, lv.scale, lv.shift, reinterpret_cast<__nv_bfloat16 *>(base + pl.off[0]),
+                                                 B, T, C);
+        if (cudaGetLastError() != cudaSuccess) return tc_fail("enc0 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        ++nl;
+        if (ev) cudaEventRecord(ev[1], stream);
+    }
+    for (int i = 1; i < 2 * n + 1; ++i) {
+        TcPlanLevel &P = pl.lv[i];
+        if (P.upcat) conv_tc_kernel<5, true><<<P.grid, kThreads, P.smem, stream>>>(P.tmA, P.tmW, P.p);
+        else conv_tc_kernel<15, false><<<P.grid, kThreads, P.smem, stream>>>(P.tmA, P.tmW, P.p);
+        const cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return tc_fail("conv_tc level %d launch failed: %s", i, cudaGetErrorString(e));
+        ++nl;
+        if (ev) cudaEventRecord(ev[i + 1], stream);
+    }
+    if (ev) cudaEventRecord(ev[2 * n + 2], stream);     // head is fused: zero-length segment
+    if (launches) *launches = nl;
+    return 0;
+}
+
+int tc_read_level(TcState *st, int block, const void *ws, int B, int T, float *out_ncl, cudaStream_t stream)
+{
+    if (!st) return tc_fail("tensor-core state missing");
+    const int n = st->n;
+    if (block == 2 * n && !st->store_last)
+        return tc_fail("the last decoder block is fused with the head and not materialised (set WUNET_TC_STORE_LAST=1)");
+    std::vector<size_t> off;
+    size_t total;
+    tc_layout(n, st->ci, B, T, off, total);
+    const int L = (block <= n) ? (T >> block) : (T >> (2 * n - block));
+    const int C = st->levels[block].cout;
+    const long long nel = (long long)B * C * L;
+    nlc_bf16_to_ncl_f32_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, stream>>>(
+        reinterpret_cast<const __nv_bfloat16 *>(static_cast<const char *>(ws) + off[block]), out_ncl, B, L, C);
+    return cudaGetLastError() == cudaSuccess ? 0 : tc_fail("read_level launch failed");
+}
+
+void tc_destroy(TcState *st)
+{
+    if (!st) return;
+    for (auto &lv : st->levels) { cudaFree(lv.wp); cudaFree(lv.ss); }
+    delete st;
+}
+
 }  // namespace wunet

@@ -136,7 +136,10 @@ class Model(nn.Module):
         self._last_ws = None
 
     def __del__(self):
-        self._release()
+        try:
+            self._release()
+        except Exception:  # interpreter shutdown
+            pass
 
     def _param_tensors(self):
         ts = []
