@@ -13,8 +13,6 @@ from wave_u_net_for_speech_enhancement_b200 import Model, _lib
 pytestmark = pytest.mark.gpu
 
 FP32_TOL = 1e-4     # BASELINE.json north_star: <= 1e-4 max-abs fp32 vs the reference forward
-BF16_TOL = 3e-2     # bf16 operands/activations through 25 conv blocks (SURVEY §8c measured 6e-4..1.4e-3 for
-                    # operand rounding alone; bf16 *storage* of every activation adds to it). Stated, not hidden.
 
 
 def make_model(n, ci, st, precision):
@@ -141,14 +139,78 @@ def test_forward_host_matches_device_path(state_full):
     assert np.array_equal(yh.numpy(), run(m, x))
 
 
-def test_bf16_full_config(full, state_full):
+# ---- bf16 / tcgen05 path (BASELINE.json configs[2]) -------------------------------------------------------
+# Every activation is stored in bf16 (8 mantissa bits: relative rounding 2^-9 = 0.2 %) and every conv uses bf16
+# operands with fp32 accumulation, so the per-level bound is relative to the level's dynamic range:
+BF16_LEVEL_REL = 1.5e-2     # max-abs(level error) / max-abs(level) ; measured 0.3-0.5 %
+BF16_OUT_TOL = 5e-3         # max-abs on the tanh output (|y| <= 0.35 here); measured 6e-4
+
+
+def bf16_model(n, ci, st):
+    os.environ["WUNET_TC_STORE_LAST"] = "1"      # also materialise the last decoder block (normally fused with the head)
+    return make_model(n, ci, st, "bf16")
+
+
+def test_bf16_small_config_all_levels(golden_dir):
+    g = np.load(os.path.join(golden_dir, "small_n4_c8.npz"))
+    n, ci, T, B = int(g["n_layers"]), int(g["channels_interval"]), int(g["T"]), int(g["B"])
+    st = wo.make_state(n, ci, seed=int(g["state_seed"]))
+    x = wo.make_input(B, T, seed=int(g["input_seed"]))
+    m = bf16_model(n, ci, st)
+    y = run(m, x)
+    for i in range(2 * n + 1):
+        lv = m.read_level(i, B, T).cpu().numpy()
+        ref = g[f"level_{i}"]
+        assert np.abs(lv - ref).max() <= BF16_LEVEL_REL * np.abs(ref).max(), f"level {i}"
+    assert np.abs(y - g["y"]).max() <= BF16_OUT_TOL
+
+
+def test_bf16_full_config_all_levels_vs_oracle(full, state_full):
     x = wo.make_input(2, 16384, seed=int(full["input_seed"]))
-    m = make_model(12, 24, state_full, "bf16")
-    try:
-        y = run(m, x)
-    except _lib.WunetError as e:
-        if "not built yet" in str(e):
-            pytest.skip("tcgen05 path not built yet")
-        raise
-    err = np.abs(y - full["y"]).max()
-    assert err <= BF16_TOL, err
+    want, levels = wo.COracle(12, 24).forward(state_full, x, return_levels=True)
+    m = bf16_model(12, 24, state_full)
+    y = run(m, x)
+    for i in range(25):
+        lv = m.read_level(i, 2, 16384).cpu().numpy()
+        err = np.abs(lv - levels[i]).max()
+        assert err <= BF16_LEVEL_REL * np.abs(levels[i]).max(), f"level {i}: {err}"
+    assert np.abs(y - full["y"]).max() <= BF16_OUT_TOL
+    assert np.abs(y - want).max() <= BF16_OUT_TOL
+    assert m.last_launch_count() == 25          # enc0 + 24 fused conv blocks (head fused into the last one)
+
+
+def test_bf16_odd_shapes_vs_oracle(state_full):
+    """T = 4096 (bottom of the U down to L = 1) and 20480 (tile counts not powers of two), batch 5."""
+    for T, B in ((4096, 5), (20480, 3)):
+        x = wo.make_input(B, T, seed=100 + T)
+        want = wo.COracle(12, 24).forward(state_full, x)
+        m = bf16_model(12, 24, state_full)
+        assert np.abs(run(m, x) - want).max() <= BF16_OUT_TOL, T
+
+
+def test_bf16_config3_batch256_properties(state_full):
+    """BASELINE.json configs[2] size (B=256): oracle-checked frames + batch-permutation invariance (bit exact)."""
+    B = 256
+    x = wo.make_input(B, 16384, seed=2468)
+    m = bf16_model(12, 24, state_full)
+    y = run(m, x)
+    pick = [0, 100, 255]
+    want = wo.COracle(12, 24).forward(state_full, x[pick])
+    assert np.abs(y[pick] - want).max() <= BF16_OUT_TOL
+    perm = np.random.default_rng(1).permutation(B)
+    assert np.array_equal(run(m, x[perm]), y[perm])
+    assert np.isfinite(y).all() and np.abs(y).max() < 1.0
+
+
+def test_bf16_edge_vectors(golden_dir, state_full):
+    g = np.load(os.path.join(golden_dir, "edges_n12_c24.npz"))
+    m = bf16_model(12, 24, state_full)
+    for name, xe in wo.edge_inputs(16384).items():
+        assert np.abs(run(m, xe) - g[name]).max() <= BF16_OUT_TOL, name
+
+
+def test_bf16_forward_host_matches_device_path(state_full):
+    m = bf16_model(12, 24, state_full)
+    x = wo.make_input(8, 16384, seed=8)
+    yh = m.forward_host(torch.from_numpy(x).pin_memory())
+    assert np.array_equal(yh.numpy(), run(m, x))

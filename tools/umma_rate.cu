@@ -1,0 +1,134 @@
+// tools/umma_rate.cu — development probe: cycles per tcgen05.mma (M=128, K=16, bf16) versus N and operand layout.
+// Question: for small N, is the MMA rate bounded by the shared-memory read of the 128-row A slice, and does a
+// layout whose K16 slice is compact (32B swizzle / interleaved) lift that bound?
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cstdio>
+#include <cstdint>
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); return 1;} } while (0)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, int layout) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)(layout & 7) << 61;
+    return d;
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xffffffff;\n\tselp.b32 %0, 1, 0, px;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+// mode 0: SW128 (row 128 B, K slice kk at +32kk)          mode 1: SW64 (row 64 B; two sub-tiles of K=32)
+// mode 2: SW32  (row 32 B; four sub-tiles of K=16)         mode 3: INTERLEAVE (plane per 16 B chunk)
+extern "C" __global__ void __launch_bounds__(128) rate_kernel(long long *out, int mode, int N, int nmma, int ROWS)
+{
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int warp = threadIdx.x >> 5;
+    const uint32_t a_bytes = (uint32_t)ROWS * 128, b_bytes = 256 * 128;
+    for (uint32_t i = threadIdx.x; i < (a_bytes + b_bytes) / 4; i += 128) ((uint32_t *)smem)[i] = 0x3c003c00u + (i & 0xff);
+    if (threadIdx.x == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_slot;
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t sA = smem_u32(smem), sB = sA + a_bytes;
+    if (warp == 1 && mode == 4) {
+        // optimized issue: hi word constant, lo word = base + small immediates, 4 K-steps unrolled
+        const uint32_t hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+        const uint32_t a_lo0 = ((sA >> 4) & 0x3FFF) | (1u << 16), b_lo0 = ((sB >> 4) & 0x3FFF) | (1u << 16);
+        long long t0 = clock64();
+        if (elect_one()) {
+            uint32_t acc = 0;
+            for (int i = 0; i < nmma / 8; ++i) {
+                const int tap = i % 15;
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    const uint32_t a_lo = a_lo0 + (uint32_t)(mt * 128 + tap) * 8;
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+                                     "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+                                     ::"r"(tmem + mt * 256), "r"(a_lo + 2 * kk), "r"(hi), "r"(b_lo0 + 2 * kk), "r"(hi), "r"(idesc), "r"(acc) : "memory");
+                        acc = 1;
+                    }
+                }
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+        }
+        __syncwarp();
+        long long t1 = clock64();
+        uint32_t ok;
+        do {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(&bar)), "r"(0) : "memory");
+        } while (!ok);
+        long long t2 = clock64();
+        if ((threadIdx.x & 31) == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+    } else if (warp == 1) {
+        long long t0 = clock64();
+        if (elect_one()) {
+            for (int i = 0; i < nmma; ++i) {
+                const int kk = i & 3, tap = (i >> 2) % 15, mt = (i >> 2) & 1;
+                uint64_t da, db;
+                if (mode == 0) {
+                    da = make_desc(sA + (mt * 128 + tap) * 128 + kk * 32, 16, 1024, 2);
+                    db = make_desc(sB + kk * 32, 16, 1024, 2);
+                } else if (mode == 1) {      // SW64: sub-tile s = kk>>1 of [rows][64B]
+                    da = make_desc(sA + (kk >> 1) * (ROWS * 64) + (mt * 128 + tap) * 64 + (kk & 1) * 32, 16, 512, 4);
+                    db = make_desc(sB + (kk >> 1) * (256 * 64) + (kk & 1) * 32, 16, 512, 4);
+                } else if (mode == 2) {      // SW32: sub-tile kk of [rows][32B]
+                    da = make_desc(sA + kk * (ROWS * 32) + (mt * 128 + tap) * 32, 16, 256, 6);
+                    db = make_desc(sB + kk * (256 * 32), 16, 256, 6);
+                } else {                      // INTERLEAVE: planes [chunk16B][row][16B]
+                    da = make_desc(sA + (2 * kk) * (ROWS * 16) + (mt * 128 + tap) * 16, ROWS * 16, 128, 0);
+                    db = make_desc(sB + (2 * kk) * (256 * 16), 256 * 16, 128, 0);
+                }
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                             ::"r"(tmem + mt * 256), "l"(da), "l"(db), "r"(idesc), "r"(i > 1 ? 1u : 0u) : "memory");
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+        }
+        __syncwarp();
+        long long t1 = clock64();
+        uint32_t ok;
+        do {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(&bar)), "r"(0) : "memory");
+        } while (!ok);
+        long long t2 = clock64();
+        if ((threadIdx.x & 31) == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+int main() {
+    long long *d; CK(cudaMalloc(&d, 16));
+    const int ROWS = 288;
+    const int smem = ROWS * 128 + 256 * 128 + 2048;
+    CK(cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const char *names[5] = {"SW128", "SW64", "SW32", "INTERLEAVE", "SW128-fastissue"};
+    for (int mode = 4; mode < 5; ++mode)
+        for (int N : {16, 32, 48, 64, 96, 128, 192, 256}) {
+            long long h[2];
+            for (int rep = 0; rep < 2; ++rep) {
+                rate_kernel<<<1, 128, smem>>>(d, mode, N, 480, ROWS);
+                cudaError_t e = cudaDeviceSynchronize();
+                if (e != cudaSuccess) { printf("%s N=%d: CUDA error %s\n", names[mode], N, cudaGetErrorString(e)); return 2; }
+                CK(cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost));
+            }
+            printf("%-10s N=%3d  issue %6.1f cyc/MMA   complete %6.1f cyc/MMA   (ideal N/2 = %d)\n", names[mode], N, h[0] / 480.0, h[1] / 480.0, N / 2);
+        }
+    return 0;
+}

@@ -35,6 +35,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     common = [c for c in common if c]
     if verbose:
         common += ["-Xptxas", "-v"]
+    if os.environ.get("WUNET_TC_TRACE"):
+        common += ["-DWUNET_TC_TRACE"]
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     procs = []
     for s in SOURCES:

@@ -32,6 +32,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include <map>
 #include <vector>
 
@@ -49,7 +50,11 @@ int tc_fail(const char *fmt, ...)
     return -1;
 }
 
-constexpr int kThreads = 192;
+constexpr int kEpiWarpsEnc = 8;                   // encoder kernels: two epilogue warps per TMEM lane quadrant
+constexpr int kEpiWarpsDec = 4;                   // decoder kernels: one per quadrant ...
+constexpr int kProducerWarps = 8;                 // ... plus eight upsample-producer warps
+constexpr int kThreadsEnc = 64 + 32 * kEpiWarpsEnc;                    // TMA, MMA, epilogue warps
+constexpr int kThreadsDec = 64 + 32 * (kEpiWarpsDec + kProducerWarps);
 constexpr int kMaxBStages = 8;
 constexpr int kSmemLimit = 227 * 1024;
 
@@ -74,6 +79,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
             : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     } while (!ok);
 }
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -87,6 +100,15 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+// one lane of a fully-converged warp (the code around it stays warp-uniform, so descriptors live in uniform registers)
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xffffffff;\n\tselp.b32 %0, 1, 0, px;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar)
 {
@@ -111,6 +133,29 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
+// Same MMA with the descriptors passed as (lo, hi) words: hi is loop-invariant, lo = base + small offsets, so the
+// issuing lane spends one uniform add per operand per MMA (tools/umma_rate.cu: 40 cyc/MMA at N=32 instead of ~110).
+__device__ __forceinline__ void umma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc,
+                                               uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate) : "memory");
+}
+// all MMAs of one tap: MT sub-tiles x NK K-steps. a_lo/b_lo are descriptor low words (16-byte units).
+template <int NK>
+__device__ __forceinline__ void issue_tap(uint32_t d_col, int MT, uint32_t nstride, uint32_t a_lo, uint32_t b_lo, uint32_t hi,
+                                          uint32_t idesc, uint32_t acc_first)
+{
+    for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+        for (int kk = 0; kk < NK; ++kk)
+            umma_bf16_lohi(d_col, a_lo + 2 * kk, b_lo + 2 * kk, hi, idesc, kk == 0 ? acc_first : 1u);
+        d_col += nstride;
+        a_lo += 128 * 8;                          // next 128-row sub-tile: 128 rows x 128 B = 1024 sixteen-byte units
+    }
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
 {
     asm volatile(
@@ -128,7 +173,17 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b)
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t *>(&h);
 }
+#ifdef WUNET_TC_TRACE
+#define TRACE(role, idx)                                                                      \
+    do {                                                                                      \
+        if (p.trace != nullptr && blockIdx.x == 0 && (idx) < 512) p.trace[(role) * 512 + (idx)++] = clock64(); \
+    } while (0)
+#else
+#define TRACE(role, idx) do { } while (0)
+#endif
 __device__ __forceinline__ float lrelu(float v) { return v >= 0.f ? v : kLreluSlope * v; }
+// tanh(x) = 1 - 2 / (exp(2x) + 1); saturates correctly at +-inf, abs error ~1e-6 (bf16 path only)
+__device__ __forceinline__ float tanh_fast(float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); }
 
 }  // namespace
 
@@ -144,10 +199,13 @@ struct TcParams {
     int Npad, Nh, Nstride;     // padded Cout, columns per CTA, TMEM column stride between sub-tile accumulators
     // M tiling
     int MT, packed, S, FR, tiles_per_frame;
+    int m_tiles, nsplit, nacc; // M tiles in the problem, N halves, accumulator buffers in TMEM
     int nops, R1, a_tx_bytes;  // TMA ops per A chunk, rows advanced per op, bytes per chunk
     int rows_used;             // smem rows the producers must fill (upsample path)
     uint32_t a_stage_bytes, b_stage_bytes;
     int nb;                    // B ring depth
+    int na;                    // A stages (1 or 2)
+    int tg, ngroups;           // taps per weight stage, stages per chunk (= ceil(KS / tg))
     uint32_t tmem_cols;
     // operands
     const __nv_bfloat16 *prev; // DEC: previous block output [B][L/2][Cin0]
@@ -161,6 +219,7 @@ struct TcParams {
     float *y;                  // [B][T]
     const float *head_w;       // [C+1]
     const float *head_b;       // [1]
+    long long *trace;          // WUNET_TC_TRACE builds: per-role clock64 stamps of CTA 0 (development)
 };
 
 // smem carve-up (offsets from the 1024-aligned base): A stages | B stages | ss | barriers
@@ -171,13 +230,13 @@ __host__ __device__ inline SmemMap smem_map(const TcParams &p)
 {
     SmemMap m;
     m.a = 0;
-    m.b = 2 * p.a_stage_bytes;
+    m.b = p.na * p.a_stage_bytes;
     m.ss = m.b + p.nb * p.b_stage_bytes;
-    m.bars = m.ss + (uint32_t)p.Nh * 8;
+    m.bars = m.ss + (uint32_t)p.Npad * 8 + 64 * 4;   // + head weights (<= 33) and bias
     m.bars = (m.bars + 15) & ~15u;
     return m;
 }
-inline size_t smem_total(const TcParams &p) { return smem_map(p).bars + 8 * (4 + 2 * kMaxBStages + 1) + 16 + 1024; }
+inline size_t smem_total(const TcParams &p) { return smem_map(p).bars + 8 * (4 + 2 * kMaxBStages + 4) + 16 + 1024; }
 
 __device__ __forceinline__ int chunk_k16(const TcParams &p, int c)
 {
@@ -190,60 +249,84 @@ __device__ __forceinline__ int chunk_k16(const TcParams &p, int c)
 // the conv kernel
 // -------------------------------------------------------------------------------------------------
 template <int KS, bool UPCAT>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(UPCAT ? kThreadsDec : kThreadsEnc, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TcParams p)
 {
     constexpr int PAD = (KS - 1) / 2;
+    constexpr int NPROD = kProducerWarps * 32;
+    constexpr int kEpilogueWarps = UPCAT ? kEpiWarpsDec : kEpiWarpsEnc;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *base_ptr = smem_raw + (base - smem_u32(smem_raw));
     const SmemMap sm = smem_map(p);
     const uint32_t bars = base + sm.bars;
-    // barrier slots (8 B each): a_full[2], a_empty[2], b_full[8], b_empty[8], acc_full, then tmem slot
+    // barrier slots (8 B each): a_full[2] a_empty[2] b_full[8] b_empty[8] acc_full[2] acc_empty[2] | tmem slot
     const uint32_t a_full = bars, a_empty = bars + 16, b_full = bars + 32, b_empty = bars + 32 + 8 * kMaxBStages;
-    const uint32_t acc_full = bars + 32 + 16 * kMaxBStages;
-    const uint32_t tmem_slot = acc_full + 8;
-    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(base_ptr + sm.bars + 32 + 16 * kMaxBStages + 8);
+    const uint32_t acc_full = bars + 32 + 16 * kMaxBStages, acc_empty = acc_full + 16;
+    const uint32_t tmem_slot = acc_empty + 16;
+    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(base_ptr + sm.bars + 32 + 16 * kMaxBStages + 32);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.y * p.Nh;
-    const int Nthis = min(p.Nh, p.Npad - n0);
-
-    int b0, l0;
-    if (p.packed) { b0 = blockIdx.x * p.FR; l0 = 0; }
-    else { b0 = blockIdx.x / p.tiles_per_frame; l0 = (blockIdx.x - b0 * p.tiles_per_frame) * 128 * p.MT; }
+    const int total_tiles = p.m_tiles * p.nsplit;
 
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
-        for (int s = 0; s < 2; ++s) { mbar_init(a_full + 8 * s, UPCAT ? 5 : 1); mbar_init(a_empty + 8 * s, 1); }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(a_full + 8 * s, UPCAT ? 1 + kProducerWarps : 1);
+            mbar_init(a_empty + 8 * s, 1);
+            mbar_init(acc_full + 8 * s, 1);
+            mbar_init(acc_empty + 8 * s, kEpilogueWarps);
+        }
         for (int s = 0; s < p.nb; ++s) { mbar_init(b_full + 8 * s, 1); mbar_init(b_empty + 8 * s, 1); }
-        mbar_init(acc_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    {   // folded BatchNorm scale/shift of this CTA's columns
+    {   // folded BatchNorm scale/shift of all output columns
         float2 *ss = reinterpret_cast<float2 *>(base_ptr + sm.ss);
-        for (int i = threadIdx.x; i < Nthis; i += kThreads) ss[i] = p.ss[n0 + i];
+        for (int i = threadIdx.x; i < p.Npad; i += blockDim.x) ss[i] = p.ss[i];
+        if (p.head) {
+            float *hw = reinterpret_cast<float *>(base_ptr + sm.ss) + 2 * p.Npad;
+            if ((int)threadIdx.x <= p.Cout) hw[threadIdx.x] = p.head_w[threadIdx.x];
+            if ((int)threadIdx.x == p.Cout + 1) hw[threadIdx.x] = p.head_b[0];
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot_ptr;
 
+    // tile -> (frame / first row, column half)
+    auto tile_coords = [&](int tile, int &b0, int &l0, int &n0) {
+        const int mi = tile / p.nsplit;
+        n0 = (tile - mi * p.nsplit) * p.Nh;
+        if (p.packed) { b0 = mi * p.FR; l0 = 0; }
+        else { b0 = mi / p.tiles_per_frame; l0 = (mi - b0 * p.tiles_per_frame) * 128 * p.MT; }
+    };
+
     if (warp == 0) {
         // ======================= TMA producer =======================
         if (lane == 0) {
             int sa = 0, pa = 0, sb = 0, pb = 0;
-            const int lcoord = p.packed ? -PAD : l0 - PAD;
-            for (int c = 0; c < p.nchunks; ++c) {
-                const bool from_tma = !UPCAT || c >= p.nchunks0;
+            int tr0 = 0; (void)tr0;
+            // A tiles are issued one chunk ahead of the weight stream (across tile boundaries)
+            int a_tile = blockIdx.x, a_c = 0;
+            // returns false if the stage is still in use and blocking == false
+            auto issue_a = [&](bool blocking) -> bool {
+                if (a_tile >= total_tiles) return true;
+                if (!blocking && !mbar_test(a_empty + 8 * sa, pa ^ 1)) return false;
+                int b0, l0, n0;
+                tile_coords(a_tile, b0, l0, n0);
+                const bool from_tma = !UPCAT || a_c >= p.nchunks0;
+                TRACE(0, tr0);
                 mbar_wait(a_empty + 8 * sa, pa ^ 1);
+                TRACE(0, tr0);
                 if (from_tma) {
-                    const int cc = UPCAT ? c - p.nchunks0 : c;
+                    const int cc = UPCAT ? a_c - p.nchunks0 : a_c;
+                    const int lcoord = p.packed ? -PAD : l0 - PAD;
                     mbar_expect_tx(a_full + 8 * sa, p.a_tx_bytes);
                     for (int op = 0; op < p.nops; ++op)
                         tma_load_3d(base + sm.a + sa * p.a_stage_bytes + op * p.R1 * 128, &tmA, a_full + 8 * sa, cc * 64,
@@ -251,113 +334,145 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 } else {
                     mbar_arrive(a_full + 8 * sa);
                 }
-                for (int t = 0; t < KS; ++t) {
-                    mbar_wait(b_empty + 8 * sb, pb ^ 1);
-                    mbar_expect_tx(b_full + 8 * sb, p.Nh * 128);
-                    tma_load_3d(base + sm.b + sb * p.b_stage_bytes, &tmW, b_full + 8 * sb, c * 64, n0, t);
-                    if (++sb == p.nb) { sb = 0; pb ^= 1; }
+                if (++sa == p.na) { sa = 0; pa ^= 1; }
+                if (++a_c == p.nchunks) { a_c = 0; a_tile += gridDim.x; }
+                return true;
+            };
+            issue_a(true);
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                int b0, l0, n0;
+                tile_coords(tile, b0, l0, n0);
+                for (int c = 0; c < p.nchunks; ++c) {
+                    // the weight groups of this chunk go out as soon as their ring slots free up; the A tile of the NEXT
+                    // chunk is slipped in between them the moment its stage is released (it never blocks the weights)
+                    bool a_done = false;
+                    for (int g = 0; g < p.ngroups; ++g) {
+                        if (!a_done) a_done = issue_a(false);
+                        mbar_wait(b_empty + 8 * sb, pb ^ 1);
+                        TRACE(0, tr0);
+                        mbar_expect_tx(b_full + 8 * sb, p.Nh * 128 * p.tg);          // taps past KS are zero-filled by TMA
+                        tma_load_3d(base + sm.b + sb * p.b_stage_bytes, &tmW, b_full + 8 * sb, c * 64, n0, g * p.tg);
+                        if (++sb == p.nb) { sb = 0; pb ^= 1; }
+                    }
+                    if (!a_done) issue_a(true);
                 }
-                if (++sa == 2) { sa = 0; pa ^= 1; }
             }
         }
     } else if (warp == 1) {
         // ======================= MMA issuer =======================
-        if (lane == 0) {
-            // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Nthis >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            int sa = 0, pa = 0, sb = 0, pb = 0;
-            for (int c = 0; c < p.nchunks; ++c) {
-                const int nk = chunk_k16(p, c);
-                mbar_wait(a_full + 8 * sa, pa);
+        // The whole warp runs the (uniform) control flow; one elected lane issues tcgen05.mma / commit.
+        {
+            int sa = 0, pa = 0, sb = 0, pb = 0, it = 0;
+            int tr1 = 0; (void)tr1;
+            const uint32_t tile_bytes = (uint32_t)p.Nh * 128;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                int b0, l0, n0;
+                tile_coords(tile, b0, l0, n0);
+                const int Nthis = min(p.Nh, p.Npad - n0);
+                // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
+                const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Nthis >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+                const int buf = (p.nacc == 2) ? (it & 1) : 0;
+                const uint32_t use = (p.nacc == 2) ? (uint32_t)(it >> 1) : (uint32_t)it;
+                if (lane == 0) TRACE(1, tr1);
+                mbar_wait(acc_empty + 8 * buf, (use & 1) ^ 1);
+                if (lane == 0) TRACE(1, tr1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_base = base + sm.a + sa * p.a_stage_bytes;
-                for (int t = 0; t < KS; ++t) {
-                    mbar_wait(b_full + 8 * sb, pb);
+                const uint32_t acc_col = tmem_base + buf * p.MT * p.Nstride;
+                for (int c = 0; c < p.nchunks; ++c) {
+                    const int nk = chunk_k16(p, c);
+                    mbar_wait(a_full + 8 * sa, pa);
+                    if (lane == 0) TRACE(1, tr1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t b_base = base + sm.b + sb * p.b_stage_bytes;
-                    for (int mt = 0; mt < p.MT; ++mt) {
-                        const uint32_t a_row = a_base + (uint32_t)(mt * 128 + t) * 128;
-                        for (int kk = 0; kk < nk; ++kk)
-                            umma_bf16(tmem_base + mt * p.Nstride, sw128_desc(a_row + kk * 32), sw128_desc(b_base + kk * 32),
-                                      idesc, (c | t | kk) ? 1u : 0u);
-                    }
-                    umma_commit(b_empty + 8 * sb);
-                    if (++sb == p.nb) { sb = 0; pb ^= 1; }
-                }
-                umma_commit(a_empty + 8 * sa);
-                if (++sa == 2) { sa = 0; pa ^= 1; }
-            }
-            umma_commit(acc_full);
-        }
-    } else {
-        // ======================= upsample producers (decoder), then epilogue =======================
-        if (UPCAT) {
-            const int pt = (warp - 2) * 32 + lane;
-            int sa = 0, pa = 0;
-            for (int c = 0; c < p.nchunks; ++c) {
-                mbar_wait(a_empty + 8 * sa, pa ^ 1);
-                if (c < p.nchunks0) {
-                    const int nvec = chunk_k16(p, c) * 2;                    // 16-byte vectors per row
-                    uint8_t *dst = base_ptr + sm.a + sa * p.a_stage_bytes;
-                    const int items = p.rows_used * nvec;
-                    for (int it = pt; it < items; it += 128) {
-                        const int row = it / nvec, vec = it - row * nvec;
-                        int bb, l;
-                        if (p.packed) { const int f = row / p.S; bb = b0 + f; l = row - f * p.S - PAD; }
-                        else { bb = b0; l = l0 - PAD + row; }
-                        const int ch = c * 64 + vec * 8;
-                        uint4 o = make_uint4(0u, 0u, 0u, 0u);
-                        if (bb < p.B && l >= 0 && l < p.L && ch < p.Cin0) {
-                            // F.interpolate(scale_factor=2, mode="linear", align_corners=True): ATen index math in fp32
-                            const float s = p.up_scale * (float)l;
-                            const int i0 = (int)s;
-                            const int i1 = i0 + (i0 < p.Lin - 1 ? 1 : 0);
-                            const float lam1 = s - (float)i0, lam0 = 1.f - lam1;
-                            const __nv_bfloat16 *r0 = p.prev + ((size_t)bb * p.Lin + i0) * p.Cin0 + ch;
-                            const __nv_bfloat16 *r1 = p.prev + ((size_t)bb * p.Lin + i1) * p.Cin0 + ch;
-                            const uint4 u0 = __ldg(reinterpret_cast<const uint4 *>(r0));
-                            const uint4 u1 = __ldg(reinterpret_cast<const uint4 *>(r1));
-                            const uint32_t a0[4] = {u0.x, u0.y, u0.z, u0.w}, a1[4] = {u1.x, u1.y, u1.z, u1.w};
-                            uint32_t r[4];
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&a0[q]));
-                                const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&a1[q]));
-                                r[q] = pack_bf16(lam0 * f0.x + lam1 * f1.x, lam0 * f0.y + lam1 * f1.y);
+                    const uint32_t a_base = base + sm.a + sa * p.a_stage_bytes;
+                    for (int g = 0; g < p.ngroups; ++g) {
+                        mbar_wait(b_full + 8 * sb, pb);
+                        if (lane == 0) TRACE(1, tr1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t b_base = base + sm.b + sb * p.b_stage_bytes;
+                        const int t_end = min(KS, (g + 1) * p.tg);
+                        if (elect_one()) {
+                            // descriptor words: hi = SBO(1024 B) | version 1 | SWIZZLE_128B, lo = (addr >> 4) | LBO(1)
+                            const uint32_t hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+                            uint32_t a_lo = ((a_base >> 4) & 0x3FFFu) | (1u << 16);
+                            uint32_t b_lo = ((b_base >> 4) & 0x3FFFu) | (1u << 16);
+                            a_lo += (uint32_t)(g * p.tg) * 8;                      // tap shift: +128 B per tap
+                            const uint32_t b_step = tile_bytes >> 4;
+                            for (int t = g * p.tg; t < t_end; ++t) {
+                                const uint32_t accf = (c | t) ? 1u : 0u;
+                                switch (nk) {
+                                    case 4: issue_tap<4>(acc_col, p.MT, p.Nstride, a_lo, b_lo, hi, idesc, accf); break;
+                                    case 3: issue_tap<3>(acc_col, p.MT, p.Nstride, a_lo, b_lo, hi, idesc, accf); break;
+                                    case 2: issue_tap<2>(acc_col, p.MT, p.Nstride, a_lo, b_lo, hi, idesc, accf); break;
+                                    default: issue_tap<1>(acc_col, p.MT, p.Nstride, a_lo, b_lo, hi, idesc, accf); break;
+                                }
+                                a_lo += 8;
+                                b_lo += b_step;
                             }
-                            o = make_uint4(r[0], r[1], r[2], r[3]);
+                            umma_commit(b_empty + 8 * sb);
                         }
-                        *reinterpret_cast<uint4 *>(dst + row * 128 + ((vec ^ (row & 7)) << 4)) = o;
+                        __syncwarp();
+                        if (++sb == p.nb) { sb = 0; pb ^= 1; }
                     }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor core reads
+                    if (elect_one()) umma_commit(a_empty + 8 * sa);
+                    __syncwarp();
+                    if (++sa == p.na) { sa = 0; pa ^= 1; }
                 }
+                if (elect_one()) umma_commit(acc_full + 8 * buf);
                 __syncwarp();
-                if (lane == 0) mbar_arrive(a_full + 8 * sa);
-                if (++sa == 2) { sa = 0; pa ^= 1; }
             }
         }
-        // ---- epilogue ----
-        mbar_wait(acc_full, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    } else if (warp < 2 + kEpilogueWarps) {
+        // ======================= epilogue warps (TMEM lane quadrant = warp % 4; two warps share a quadrant) ==========
         const int q = warp & 3;
+        const int half = (warp - 2) >> 2;                 // 0 .. kEpilogueWarps/4 - 1
+        constexpr int NSHARE = kEpilogueWarps / 4;        // warps sharing a quadrant
         const float2 *ss = reinterpret_cast<const float2 *>(base_ptr + sm.ss);
-        const int ncc = (Nthis + 31) >> 5;
-        for (int mt = 0; mt < p.MT; ++mt) {
-            const int row = mt * 128 + q * 32 + lane;
-            int bb, l;
-            if (p.packed) { const int f = row / p.S; bb = b0 + f; l = row - f * p.S; if (f >= p.FR) l = p.L; }
-            else { bb = b0; l = l0 + row; }
-            const bool valid = (bb < p.B) && (l < p.L);
-            for (int cc = 0; cc < ncc; ++cc) {
+        int it = 0;
+        int tr2 = 0; (void)tr2;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            int b0, l0, n0;
+            tile_coords(tile, b0, l0, n0);
+            const int Nthis = min(p.Nh, p.Npad - n0);
+            const int ncc = (Nthis + 31) >> 5;
+            const int buf = (p.nacc == 2) ? (it & 1) : 0;
+            const uint32_t use = (p.nacc == 2) ? (uint32_t)(it >> 1) : (uint32_t)it;
+            if (warp == 2 && lane == 0) TRACE(2, tr2);
+            // fused head: fetch the raw-input samples of this thread's rows before waiting for the accumulators
+            float xin[4] = {0.f, 0.f, 0.f, 0.f};
+            if (p.head) {
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt) {
+                    if (mt < p.MT) {
+                        const int l = l0 + mt * 128 + q * 32 + lane;
+                        if (b0 < p.B && l < p.L) xin[mt] = __ldg(p.x + (size_t)b0 * p.T + l);
+                    }
+                }
+            }
+            mbar_wait(acc_full + 8 * buf, use & 1);
+            if (warp == 2 && lane == 0) TRACE(2, tr2);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t acc_col = buf * p.MT * p.Nstride;
+            // work items (mt, cc) are dealt round-robin to the warps sharing a quadrant
+            const int nitems = p.MT * ncc;
+            for (int item = half; item < nitems; item += NSHARE) {
+                const int mt = item / ncc, cc = item - mt * ncc;
+                const int row = mt * 128 + q * 32 + lane;
+                int bb, l;
+                if (p.packed) { const int f = row / p.S; bb = b0 + f; l = row - f * p.S; if (f >= p.FR) l = p.L; }
+                else { bb = b0; l = l0 + row; }
+                const bool valid = (bb < p.B) && (l < p.L);
                 uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * p.Nstride + cc * 32), v);
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc_col + (uint32_t)(mt * p.Nstride + cc * 32), v);
                 if (!valid) continue;
                 const int colbase = cc * 32;
                 float f[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float2 s = (colbase + j < Nthis) ? ss[colbase + j] : make_float2(0.f, 0.f);
-                    f[j] = lrelu(fmaf(__uint_as_float(v[j]), s.x, s.y));
+                for (int j = 0; j < 32; j += 2) {
+                    // (scale, shift) pairs of two adjacent columns in one 16-byte shared load
+                    const float4 s2 = (colbase + j < Nthis) ? *reinterpret_cast<const float4 *>(&ss[n0 + colbase + j])
+                                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+                    f[j] = lrelu(fmaf(__uint_as_float(v[j]), s2.x, s2.y));
+                    f[j + 1] = lrelu(fmaf(__uint_as_float(v[j + 1]), s2.z, s2.w));
                 }
                 if (p.out != nullptr) {
                     __nv_bfloat16 *orow = p.out + ((size_t)bb * p.L + l) * p.Cout + n0 + colbase;
@@ -372,13 +487,106 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 if (p.head) {
                     // cat([o, input], 1) -> Conv1d(C+1 -> 1, k=1) -> Tanh   (model/unet_basic.py:98-99)
-                    float acc = __ldg(p.head_b);
+                    const float *hw = reinterpret_cast<const float *>(base_ptr + sm.ss) + 2 * p.Npad;   // [C+1] weights, bias
+                    float acc = hw[p.Cout + 1];
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
-                        if (j < p.Cout) acc = fmaf(__ldg(p.head_w + j), f[j], acc);
-                    acc = fmaf(__ldg(p.head_w + p.Cout), __ldg(p.x + (size_t)bb * p.T + l), acc);
-                    p.y[(size_t)bb * p.T + l] = tanhf(acc);
+                        if (j < p.Cout) acc = fmaf(hw[j], f[j], acc);
+                    acc = fmaf(hw[p.Cout], xin[mt & 3], acc);
+                    p.y[(size_t)bb * p.T + l] = tanh_fast(acc);
                 }
+            }
+            // accumulator buffer drained: hand it back to the MMA warp
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty + 8 * buf);
+        }
+    } else if (UPCAT) {
+        // ======================= upsample producers (decoder) =======================
+        const int pt = (warp - 2 - kEpilogueWarps) * 32 + lane;
+        int sa = 0, pa = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            int b0, l0, n0;
+            tile_coords(tile, b0, l0, n0);
+            for (int c = 0; c < p.nchunks; ++c) {
+                mbar_wait(a_empty + 8 * sa, pa ^ 1);
+                if (c < p.nchunks0) {
+                    const int nvec = chunk_k16(p, c) * 2;                    // 16-byte vectors per row
+                    uint8_t *dst = base_ptr + sm.a + sa * p.a_stage_bytes;
+                    if (!p.packed) {
+                        // a thread owns (16 consecutive output rows) x (one 16-byte channel vector): the 10 previous-level
+                        // rows they interpolate between are loaded once, all loads in flight together. Row l of the
+                        // upsampled signal lies between prev rows (l-1)>>1 and that + 1 (src = l*(Lin-1)/(2Lin-1)).
+                        const int nruns = (p.rows_used + 15) >> 4;
+                        for (int itx = pt; itx < nruns * nvec; itx += NPROD) {
+                            const int run = itx / nvec, vec = itx - run * nvec;
+                            const int ch = c * 64 + vec * 8;
+                            const int lstart = l0 - PAD + 16 * run;            // even
+                            const int ms = lstart >> 1;
+                            const bool chok = ch < p.Cin0;
+                            uint4 xr[10];
+                            const __nv_bfloat16 *pb = p.prev + (size_t)b0 * p.Lin * p.Cin0 + ch;
+#pragma unroll
+                            for (int qq = 0; qq < 10; ++qq) {
+                                int m = ms - 1 + qq;
+                                m = m < 0 ? 0 : (m > p.Lin - 1 ? p.Lin - 1 : m);
+                                xr[qq] = chok ? __ldg(reinterpret_cast<const uint4 *>(pb + (size_t)m * p.Cin0)) : make_uint4(0u, 0u, 0u, 0u);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                const int row = 16 * run + j;
+                                if (row >= p.rows_used) break;
+                                const int l = lstart + j;
+                                uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                                if (chok && l >= 0 && l < p.L) {
+                                    const int qa = (j >> 1) + (j & 1);
+                                    // out = a + lam1 * (b - a) in packed bf16 (HFMA2): 3 ops per pair instead of 9
+                                    const float lam1 = p.up_scale * (float)l - (float)(ms - 1 + qa);
+                                    const __nv_bfloat162 lam = __float2bfloat162_rn(lam1);
+                                    const __nv_bfloat162 *a2 = reinterpret_cast<const __nv_bfloat162 *>(&xr[qa]);
+                                    const __nv_bfloat162 *b2 = reinterpret_cast<const __nv_bfloat162 *>(&xr[qa + 1]);
+                                    __nv_bfloat162 r2[4];
+#pragma unroll
+                                    for (int q4 = 0; q4 < 4; ++q4) r2[q4] = __hfma2(lam, __hsub2(b2[q4], a2[q4]), a2[q4]);
+                                    o = *reinterpret_cast<const uint4 *>(r2);
+                                }
+                                *reinterpret_cast<uint4 *>(dst + row * 128 + ((vec ^ (row & 7)) << 4)) = o;
+                            }
+                        }
+                    } else {
+                        const int items = p.rows_used * nvec;
+                        for (int itx = pt; itx < items; itx += NPROD) {
+                            const int row = itx / nvec, vec = itx - row * nvec;
+                            const int f = row / p.S;
+                            const int bb = b0 + f, l = row - f * p.S - PAD;
+                            const int ch = c * 64 + vec * 8;
+                            uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                            if (bb < p.B && l >= 0 && l < p.L && ch < p.Cin0) {
+                                // F.interpolate(scale_factor=2, mode="linear", align_corners=True): ATen index math in fp32
+                                const float s = p.up_scale * (float)l;
+                                const int i0 = (int)s;
+                                const int i1 = i0 + (i0 < p.Lin - 1 ? 1 : 0);
+                                const float lam1 = s - (float)i0, lam0 = 1.f - lam1;
+                                const uint4 u0 = __ldg(reinterpret_cast<const uint4 *>(p.prev + ((size_t)bb * p.Lin + i0) * p.Cin0 + ch));
+                                const uint4 u1 = __ldg(reinterpret_cast<const uint4 *>(p.prev + ((size_t)bb * p.Lin + i1) * p.Cin0 + ch));
+                                const uint32_t a0[4] = {u0.x, u0.y, u0.z, u0.w}, a1[4] = {u1.x, u1.y, u1.z, u1.w};
+                                uint32_t r[4];
+#pragma unroll
+                                for (int q4 = 0; q4 < 4; ++q4) {
+                                    const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&a0[q4]));
+                                    const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&a1[q4]));
+                                    r[q4] = pack_bf16(lam0 * f0.x + lam1 * f1.x, lam0 * f0.y + lam1 * f1.y);
+                                }
+                                o = make_uint4(r[0], r[1], r[2], r[3]);
+                            }
+                            *reinterpret_cast<uint4 *>(dst + row * 128 + ((vec ^ (row & 7)) << 4)) = o;
+                        }
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor core reads
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(a_full + 8 * sa);
+                if (++sa == p.na) { sa = 0; pa ^= 1; }
             }
         }
     }
@@ -497,6 +705,7 @@ struct TcPlanLevel {
     TcParams p;
     CUtensorMap tmA, tmW;
     dim3 grid;
+    int threads;
     size_t smem;
     bool upcat;
 };
@@ -513,6 +722,9 @@ struct TcState {
     EncodeTiledFn encode = nullptr;
     bool store_last = false;           // WUNET_TC_STORE_LAST=1: also materialise the last decoder block (tests)
     bool attr_set = false;
+    int num_sms = 148;
+    long long *trace = nullptr;        // development: WUNET_TC_TRACE builds + WUNET_TC_TRACE_LEVEL=<block>
+    int trace_level = -1;
     // plan cache, keyed on (workspace pointer, B, T)
     const void *plan_ws = nullptr;
     int plan_B = 0, plan_T = 0;
@@ -562,6 +774,13 @@ int tc_set_weights(TcState **pst, int n, int ci, const TcBlockSrc *blocks, int n
         st->encode = reinterpret_cast<EncodeTiledFn>(fn);
         const char *e = getenv("WUNET_TC_STORE_LAST");
         st->store_last = e && e[0] == '1';
+#ifdef WUNET_TC_TRACE
+        if (const char *tl = getenv("WUNET_TC_TRACE_LEVEL")) {
+            st->trace_level = atoi(tl);
+            cudaMalloc(&st->trace, 3 * 512 * sizeof(long long));
+            cudaMemset(st->trace, 0, 3 * 512 * sizeof(long long));
+        }
+#endif
         *pst = st;
     }
     st->out_w = out_w; st->out_b = out_b;
@@ -630,20 +849,15 @@ static int build_plan(TcState *st, const float *x, float *y, int B, int T, void 
         p.nchunks0 = (lv.cin0 + 63) / 64;
         p.nchunks = p.nchunks0 + (lv.cin1 + 63) / 64;
         p.Npad = lv.Npad;
-        const int nsplit = lv.Npad > 256 ? 2 : 1;
-        p.Nh = nsplit == 1 ? lv.Npad : round_up(lv.Npad / 2, 16);
-        p.Nstride = round_up(p.Nh, 32);
-        int mtcap = 512 / p.Nstride;
-        if (mtcap > 4) mtcap = 4;
-        if (mtcap == 3) mtcap = 2;
-        p.b_stage_bytes = (uint32_t)round_up(p.Nh * 128, 1024);
-        for (int MT = mtcap; MT >= 1; MT >>= 1) {
+        // ---- tiling ---------------------------------------------------------------------------------
+        const bool packed = L < 128;
+        auto geometry = [&](int MT, int nsplit) {
+            p.nsplit = nsplit;
+            p.Nh = nsplit == 1 ? lv.Npad : round_up((lv.Npad + nsplit - 1) / nsplit, 16);
+            p.Nstride = round_up(p.Nh, 32);
             p.MT = MT;
-            if (L >= 128) {
+            if (!packed) {
                 p.packed = 0;
-                int mt_l = 1;
-                while (mt_l * 2 <= MT && L >= 128 * mt_l * 2) mt_l *= 2;
-                p.MT = MT = mt_l;
                 p.tiles_per_frame = (L + 128 * MT - 1) / (128 * MT);
                 const int rows = 128 * MT + KS - 1;
                 p.nops = (rows + 255) / 256;
@@ -652,33 +866,72 @@ static int build_plan(TcState *st, const float *x, float *y, int B, int T, void 
                 p.rows_used = rows;
                 p.a_stage_bytes = (uint32_t)round_up(p.nops * p.R1 * 128, 1024);
                 p.a_tx_bytes = p.nops * p.R1 * 128;
-                P.grid = dim3((unsigned)(B * p.tiles_per_frame), (unsigned)nsplit, 1);
+                p.m_tiles = B * p.tiles_per_frame;
             } else {
                 p.packed = 1;
                 p.S = L + KS - 1;
-                // smallest MT whose frame capacity covers the batch, else the largest allowed
                 int FR = (128 * MT - L) / p.S + 1;
-                while (MT > 1 && (128 * (MT / 2) - L) / p.S + 1 >= B) { MT /= 2; FR = (128 * MT - L) / p.S + 1; }
                 if (FR > B) FR = B;
                 if (FR > 256) FR = 256;
-                p.MT = MT; p.FR = FR;
+                p.FR = FR;
                 p.tiles_per_frame = 0;
                 p.nops = 1; p.R1 = p.S;
                 p.rows_used = FR * p.S;
                 const int rows_alloc = round_up(std::max(FR * p.S, 128 * MT + KS - 1), 8);
                 p.a_stage_bytes = (uint32_t)round_up(rows_alloc * 128, 1024);
                 p.a_tx_bytes = FR * p.S * 128;
-                P.grid = dim3((unsigned)((B + FR - 1) / FR), (unsigned)nsplit, 1);
+                p.m_tiles = (B + FR - 1) / FR;
             }
-            int nb = ((int)kSmemLimit - 2048 - 2 * (int)p.a_stage_bytes - p.Nh * 8 - 256) / (int)p.b_stage_bytes;
-            if (nb > kMaxBStages) nb = kMaxBStages;
-            p.nb = nb;
-            if (nb >= 2) break;
-            if (MT == 1) return tc_fail("level %d does not fit in shared memory", i);
+            p.nacc = (2 * MT * p.Nstride <= 512) ? 2 : 1;
+            uint32_t cols = 32;
+            while ((int)cols < p.nacc * MT * p.Nstride) cols <<= 1;
+            p.tmem_cols = cols;
+        };
+        const int base_split = lv.Npad > 256 ? 2 : 1;
+        if (!packed) {
+            const int ns32 = round_up(base_split == 1 ? lv.Npad : round_up((lv.Npad + 1) / 2, 16), 32);
+            int MT;
+            if (ns32 <= 64) MT = 4;            // 2 x 4 x 64 TMEM columns: double-buffered accumulators
+            else if (ns32 <= 96) MT = 2;       // 2 x 2 x 96
+            else if (ns32 <= 128) MT = 4;      // single buffer, weights shared by 4 sub-tiles
+            else MT = 2;
+            while (MT > 1 && 128 * MT > L) MT >>= 1;
+            geometry(MT, base_split);
+        } else {
+            // bottom of the U: few tiles, long K loops -> spread over the SMs with small tiles and column splits
+            int MT = 2, ns = base_split;
+            geometry(MT, ns);
+            if (p.m_tiles * ns < st->num_sms) { MT = 1; geometry(MT, ns); }
+            while (p.m_tiles * ns * 2 <= st->num_sms + st->num_sms / 4 && ns < 4 && lv.Npad / (ns * 2) >= 48) { ns *= 2; geometry(MT, ns); }
         }
-        uint32_t cols = 32;
-        while ((int)cols < p.MT * p.Nstride) cols <<= 1;
-        p.tmem_cols = cols;
+        p.na = 2;
+        {
+            // weight stages hold `tg` consecutive taps (one TMA box, one barrier handshake per stage)
+            const int budget = (int)kSmemLimit - 2048 - p.Npad * 8 - 512;
+            int best_tg = 0;
+            for (int tg : {5, 3, 1}) {
+                if (KS % tg != 0) continue;
+                const int stage = round_up(p.Nh * 128 * tg, 1024);
+                const int want_stages = (tg == 1) ? 4 : 3;
+                if (2 * (int)p.a_stage_bytes + want_stages * stage <= budget) { best_tg = tg; break; }
+            }
+            if (best_tg == 0) best_tg = 1;
+            p.tg = best_tg;
+            p.ngroups = (KS + p.tg - 1) / p.tg;
+            p.b_stage_bytes = (uint32_t)round_up(p.Nh * 128 * p.tg, 1024);
+            int nb = (budget - p.na * (int)p.a_stage_bytes) / (int)p.b_stage_bytes;
+            if (nb < 2) { p.na = 1; nb = (budget - (int)p.a_stage_bytes) / (int)p.b_stage_bytes; }
+            if (nb > kMaxBStages) nb = kMaxBStages;
+            if (nb < 2) return tc_fail("level %d does not fit in shared memory", i);
+            p.nb = nb;
+        }
+        {
+            const int threads = dec ? kThreadsDec : kThreadsEnc;
+            const int per_sm = std::max(1, std::min({(int)(kSmemLimit / smem_total(p)), (int)(512 / p.tmem_cols), 2048 / threads}));
+            const int total_tiles = p.m_tiles * p.nsplit;
+            P.grid = dim3((unsigned)std::min(total_tiles, st->num_sms * per_sm), 1, 1);
+            P.threads = threads;
+        }
         P.smem = smem_total(p);
         if (P.smem > (size_t)kSmemLimit) return tc_fail("level %d: smem %zu too large", i, P.smem);
 
@@ -687,6 +940,7 @@ static int build_plan(TcState *st, const float *x, float *y, int B, int T, void 
         p.out = (last && !st->store_last) ? nullptr : lvl(i);
         p.head = last ? 1 : 0;
         p.x = x; p.y = y; p.head_w = st->out_w; p.head_b = st->out_b;
+        p.trace = (st->trace && st->trace_level == i) ? st->trace : nullptr;
         if (last && lv.cout > 32) return tc_fail("fused head needs channels_interval <= 32");
         // operand maps
         if (!dec) {
@@ -704,8 +958,16 @@ static int build_plan(TcState *st, const float *x, float *y, int B, int T, void 
             p.up_scale = (L > 1) ? (float)(p.Lin - 1) / (float)(L - 1) : 0.f;
         }
         if (make_map(st, &P.tmW, lv.wp, lv.Ktot, lv.Npad, lv.k, (uint64_t)lv.Ktot * 2, (uint64_t)lv.Npad * lv.Ktot * 2, 64,
-                     (uint32_t)p.Nh, 1))
+                     (uint32_t)p.Nh, (uint32_t)p.tg))
             return -1;
+    }
+    if (getenv("WUNET_TC_DEBUG")) {
+        for (int i = 1; i < 2 * n + 1; ++i) {
+            const TcParams &p = pl.lv[i].p;
+            fprintf(stderr, "[wunet tc] blk %2d L=%5d Cin=%3d+%3d Cout=%3d Nh=%3d x%d MT=%d nacc=%d packed=%d FR=%d na=%d nb=%d tg=%d smem=%zu tmem=%u tiles=%d grid=%u\n",
+                    i, p.L, p.Cin0, p.Cin1, p.Cout, p.Nh, p.nsplit, p.MT, p.nacc, p.packed, p.FR, p.na, p.nb, p.tg, pl.lv[i].smem, p.tmem_cols,
+                    p.m_tiles * p.nsplit, pl.lv[i].grid.x);
+        }
     }
     st->plan_ws = ws; st->plan_B = B; st->plan_T = T; st->plan_x = x; st->plan_y = y;
     return 0;
@@ -720,6 +982,9 @@ int tc_forward(TcState *st, const float *x, float *y, int B, int T, void *ws, cu
     if (!st->attr_set) {
         cudaFuncSetAttribute(conv_tc_kernel<15, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         cudaFuncSetAttribute(conv_tc_kernel<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+        int dev = 0, sms = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
+            st->num_sms = sms;
         st->attr_set = true;
     }
     if (st->plan_ws != ws || st->plan_B != B || st->plan_T != T || st->plan_x != x || st->plan_y != y)
@@ -741,8 +1006,8 @@ int tc_forward(TcState *st, const float *x, float *y, int B, int T, void *ws, cu
     }
     for (int i = 1; i < 2 * n + 1; ++i) {
         TcPlanLevel &P = pl.lv[i];
-        if (P.upcat) conv_tc_kernel<5, true><<<P.grid, kThreads, P.smem, stream>>>(P.tmA, P.tmW, P.p);
-        else conv_tc_kernel<15, false><<<P.grid, kThreads, P.smem, stream>>>(P.tmA, P.tmW, P.p);
+        if (P.upcat) conv_tc_kernel<5, true><<<P.grid, P.threads, P.smem, stream>>>(P.tmA, P.tmW, P.p);
+        else conv_tc_kernel<15, false><<<P.grid, P.threads, P.smem, stream>>>(P.tmA, P.tmW, P.p);
         const cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return tc_fail("conv_tc level %d launch failed: %s", i, cudaGetErrorString(e));
         ++nl;
@@ -773,6 +1038,18 @@ int tc_read_level(TcState *st, int block, const void *ws, int B, int T, float *o
 void tc_destroy(TcState *st)
 {
     if (!st) return;
+    if (st->trace) {
+        std::vector<long long> h(3 * 512);
+        cudaDeviceSynchronize();
+        cudaMemcpy(h.data(), st->trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        long long t0 = h[512];
+        for (int r = 0; r < 3; ++r) {
+            fprintf(stderr, "[trace role %d]", r);
+            for (int i = 0; i < 140 && h[r * 512 + i]; ++i) fprintf(stderr, " %lld", h[r * 512 + i] - t0);
+            fprintf(stderr, "\n");
+        }
+        cudaFree(st->trace);
+    }
     for (auto &lv : st->levels) { cudaFree(lv.wp); cudaFree(lv.ss); }
     delete st;
 }
