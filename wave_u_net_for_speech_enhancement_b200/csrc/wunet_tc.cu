@@ -52,7 +52,7 @@ int tc_fail(const char *fmt, ...)
 
 constexpr int kEpiWarpsEnc = 8;                   // encoder kernels: two epilogue warps per TMEM lane quadrant
 constexpr int kEpiWarpsDec = 4;                   // decoder kernels: one per quadrant ...
-constexpr int kProducerWarps = 8;                 // ... plus eight upsample-producer warps
+constexpr int kProducerWarps = 9;                 // ... plus nine upsample-producer warps (one item per thread at MT=4)
 constexpr int kThreadsEnc = 64 + 32 * kEpiWarpsEnc;                    // TMA, MMA, epilogue warps
 constexpr int kThreadsDec = 64 + 32 * (kEpiWarpsDec + kProducerWarps);
 constexpr int kMaxBStages = 8;
@@ -144,16 +144,27 @@ __device__ __forceinline__ void umma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, u
         ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate) : "memory");
 }
 // all MMAs of one tap: MT sub-tiles x NK K-steps. a_lo/b_lo are descriptor low words (16-byte units).
-template <int NK>
-__device__ __forceinline__ void issue_tap(uint32_t d_col, int MT, uint32_t nstride, uint32_t a_lo, uint32_t b_lo, uint32_t hi,
+template <int NK, int MT>
+__device__ __forceinline__ void issue_tap(uint32_t d_col, uint32_t nstride, uint32_t a_lo, uint32_t b_lo, uint32_t hi,
                                           uint32_t idesc, uint32_t acc_first)
 {
+#pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
         for (int kk = 0; kk < NK; ++kk)
-            umma_bf16_lohi(d_col, a_lo + 2 * kk, b_lo + 2 * kk, hi, idesc, kk == 0 ? acc_first : 1u);
-        d_col += nstride;
-        a_lo += 128 * 8;                          // next 128-row sub-tile: 128 rows x 128 B = 1024 sixteen-byte units
+            umma_bf16_lohi(d_col + mt * nstride, a_lo + mt * (128 * 8) + 2 * kk, b_lo + 2 * kk, hi, idesc,
+                           kk == 0 ? acc_first : 1u);   // next 128-row sub-tile: +128 rows x 128 B = 1024 sixteen-byte units
+    }
+}
+template <int MT>
+__device__ __forceinline__ void issue_tap_nk(int nk, uint32_t d_col, uint32_t nstride, uint32_t a_lo, uint32_t b_lo, uint32_t hi,
+                                             uint32_t idesc, uint32_t acc_first)
+{
+    switch (nk) {
+        case 4: issue_tap<4, MT>(d_col, nstride, a_lo, b_lo, hi, idesc, acc_first); break;
+        case 3: issue_tap<3, MT>(d_col, nstride, a_lo, b_lo, hi, idesc, acc_first); break;
+        case 2: issue_tap<2, MT>(d_col, nstride, a_lo, b_lo, hi, idesc, acc_first); break;
+        default: issue_tap<1, MT>(d_col, nstride, a_lo, b_lo, hi, idesc, acc_first); break;
     }
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
@@ -195,6 +206,7 @@ struct TcParams {
     int B, L, Cout, T;
     int Cin0, Cin1;            // K segments: ENC: Cin0 = Cin, Cin1 = 0; DEC: Cin0 = upsampled prev, Cin1 = skip
     int nchunks0, nchunks;     // 64-channel chunks in segment 0 / in total
+    unsigned char chunk_map[16]; // K-loop order: bit 7 = chunk of the upsampled segment, bits 0-6 = chunk index inside its segment
     // N tiling
     int Npad, Nh, Nstride;     // padded Cout, columns per CTA, TMEM column stride between sub-tile accumulators
     // M tiling
@@ -236,13 +248,21 @@ __host__ __device__ inline SmemMap smem_map(const TcParams &p)
     m.bars = (m.bars + 15) & ~15u;
     return m;
 }
-inline size_t smem_total(const TcParams &p) { return smem_map(p).bars + 8 * (4 + 2 * kMaxBStages + 4) + 16 + 1024; }
+inline size_t smem_total(const TcParams &p) { return smem_map(p).bars + 8 * (8 + 2 * kMaxBStages + 4) + 16 + 1024; }
 
-__device__ __forceinline__ int chunk_k16(const TcParams &p, int c)
+// K-loop position c -> (segment, chunk index inside the segment, K16 steps, 64-wide slot in the packed weights)
+struct ChunkInfo { bool up; int idx, nk, kslot; };
+template <bool UPCAT>
+__device__ __forceinline__ ChunkInfo chunk_info(const TcParams &p, int c)
 {
-    const int seg_c = (c < p.nchunks0) ? p.Cin0 - 64 * c : p.Cin1 - 64 * (c - p.nchunks0);
-    const int ch = seg_c < 64 ? seg_c : 64;
-    return (ch + 15) >> 4;
+    ChunkInfo ci;
+    const int m = p.chunk_map[c];
+    ci.up = UPCAT && (m & 0x80);
+    ci.idx = m & 0x7f;
+    const int seg_c = (ci.up || !UPCAT) ? p.Cin0 - 64 * ci.idx : p.Cin1 - 64 * ci.idx;
+    ci.nk = ((seg_c < 64 ? seg_c : 64) + 15) >> 4;
+    ci.kslot = (ci.up || !UPCAT) ? ci.idx : p.nchunks0 + ci.idx;
+    return ci;
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -260,11 +280,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint8_t *base_ptr = smem_raw + (base - smem_u32(smem_raw));
     const SmemMap sm = smem_map(p);
     const uint32_t bars = base + sm.bars;
-    // barrier slots (8 B each): a_full[2] a_empty[2] b_full[8] b_empty[8] acc_full[2] acc_empty[2] | tmem slot
-    const uint32_t a_full = bars, a_empty = bars + 16, b_full = bars + 32, b_empty = bars + 32 + 8 * kMaxBStages;
-    const uint32_t acc_full = bars + 32 + 16 * kMaxBStages, acc_empty = acc_full + 16;
+    // barrier slots (8 B each): a_full[4] a_empty[4] b_full[8] b_empty[8] acc_full[2] acc_empty[2] | tmem slot
+    const uint32_t a_full = bars, a_empty = bars + 32, b_full = bars + 64, b_empty = bars + 64 + 8 * kMaxBStages;
+    const uint32_t acc_full = bars + 64 + 16 * kMaxBStages, acc_empty = acc_full + 16;
     const uint32_t tmem_slot = acc_empty + 16;
-    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(base_ptr + sm.bars + 32 + 16 * kMaxBStages + 32);
+    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(base_ptr + sm.bars + 64 + 16 * kMaxBStages + 32);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = p.m_tiles * p.nsplit;
@@ -272,9 +292,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < 4; ++s) {
             mbar_init(a_full + 8 * s, UPCAT ? 1 + kProducerWarps : 1);
             mbar_init(a_empty + 8 * s, 1);
+        }
+        for (int s = 0; s < 2; ++s) {
             mbar_init(acc_full + 8 * s, 1);
             mbar_init(acc_empty + 8 * s, kEpilogueWarps);
         }
@@ -320,12 +342,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (!blocking && !mbar_test(a_empty + 8 * sa, pa ^ 1)) return false;
                 int b0, l0, n0;
                 tile_coords(a_tile, b0, l0, n0);
-                const bool from_tma = !UPCAT || a_c >= p.nchunks0;
+                const ChunkInfo aci = chunk_info<UPCAT>(p, a_c);
+                const bool from_tma = !aci.up;
                 TRACE(0, tr0);
                 mbar_wait(a_empty + 8 * sa, pa ^ 1);
                 TRACE(0, tr0);
                 if (from_tma) {
-                    const int cc = UPCAT ? a_c - p.nchunks0 : a_c;
+                    const int cc = aci.idx;
                     const int lcoord = p.packed ? -PAD : l0 - PAD;
                     mbar_expect_tx(a_full + 8 * sa, p.a_tx_bytes);
                     for (int op = 0; op < p.nops; ++op)
@@ -338,7 +361,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (++a_c == p.nchunks) { a_c = 0; a_tile += gridDim.x; }
                 return true;
             };
-            issue_a(true);
+            for (int pre = 0; pre < p.na - 1; ++pre) issue_a(true);          // A tiles run na-1 chunks ahead of the weights
+            if (p.na == 1) issue_a(true);
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 int b0, l0, n0;
                 tile_coords(tile, b0, l0, n0);
@@ -346,12 +370,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     // the weight groups of this chunk go out as soon as their ring slots free up; the A tile of the NEXT
                     // chunk is slipped in between them the moment its stage is released (it never blocks the weights)
                     bool a_done = false;
+                    const int kslot = chunk_info<UPCAT>(p, c).kslot;
                     for (int g = 0; g < p.ngroups; ++g) {
                         if (!a_done) a_done = issue_a(false);
                         mbar_wait(b_empty + 8 * sb, pb ^ 1);
                         TRACE(0, tr0);
                         mbar_expect_tx(b_full + 8 * sb, p.Nh * 128 * p.tg);          // taps past KS are zero-filled by TMA
-                        tma_load_3d(base + sm.b + sb * p.b_stage_bytes, &tmW, b_full + 8 * sb, c * 64, n0, g * p.tg);
+                        tma_load_3d(base + sm.b + sb * p.b_stage_bytes, &tmW, b_full + 8 * sb, kslot * 64, n0, g * p.tg);
                         if (++sb == p.nb) { sb = 0; pb ^= 1; }
                     }
                     if (!a_done) issue_a(true);
@@ -379,7 +404,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t acc_col = tmem_base + buf * p.MT * p.Nstride;
                 for (int c = 0; c < p.nchunks; ++c) {
-                    const int nk = chunk_k16(p, c);
+                    const int nk = chunk_info<UPCAT>(p, c).nk;
                     mbar_wait(a_full + 8 * sa, pa);
                     if (lane == 0) TRACE(1, tr1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -399,12 +424,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             const uint32_t b_step = tile_bytes >> 4;
                             for (int t = g * p.tg; t < t_end; ++t) {
                                 const uint32_t accf = (c | t) ? 1u : 0u;
-                                switch (nk) {
-                                    case 4: issue_tap<4>(acc_col, p.MT, p.Nstride, a_lo, b_lo, hi, idesc, accf); break;
-                                    case 3: issue_tap<3>(acc_col, p.MT, p.Nstride, a_lo, b_lo, hi, idesc, accf); break;
-                                    case 2: issue_tap<2>(acc_col, p.MT, p.Nstride, a_lo, b_lo, hi, idesc, accf); break;
-                                    default: issue_tap<1>(acc_col, p.MT, p.Nstride, a_lo, b_lo, hi, idesc, accf); break;
-                                }
+                                if (p.MT == 4) issue_tap_nk<4>(nk, acc_col, p.Nstride, a_lo, b_lo, hi, idesc, accf);
+                                else if (p.MT == 2) issue_tap_nk<2>(nk, acc_col, p.Nstride, a_lo, b_lo, hi, idesc, accf);
+                                else issue_tap_nk<1>(nk, acc_col, p.Nstride, a_lo, b_lo, hi, idesc, accf);
                                 a_lo += 8;
                                 b_lo += b_step;
                             }
@@ -438,24 +460,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t use = (p.nacc == 2) ? (uint32_t)(it >> 1) : (uint32_t)it;
             if (warp == 2 && lane == 0) TRACE(2, tr2);
             // fused head: fetch the raw-input samples of this thread's rows before waiting for the accumulators
-            float xin[4] = {0.f, 0.f, 0.f, 0.f};
-            if (p.head) {
-#pragma unroll
-                for (int mt = 0; mt < 4; ++mt) {
-                    if (mt < p.MT) {
-                        const int l = l0 + mt * 128 + q * 32 + lane;
-                        if (b0 < p.B && l < p.L) xin[mt] = __ldg(p.x + (size_t)b0 * p.T + l);
-                    }
-                }
+            float xin0 = 0.f, xin1 = 0.f, xin2 = 0.f, xin3 = 0.f;     // scalars (not an array): they must stay in registers
+            if (p.head && b0 < p.B) {
+                const float *xp = p.x + (size_t)b0 * p.T + l0 + q * 32 + lane;
+                const int lb = l0 + q * 32 + lane;
+                if (lb < p.L) xin0 = __ldg(xp);
+                if (p.MT > 1 && lb + 128 < p.L) xin1 = __ldg(xp + 128);
+                if (p.MT > 2 && lb + 256 < p.L) xin2 = __ldg(xp + 256);
+                if (p.MT > 3 && lb + 384 < p.L) xin3 = __ldg(xp + 384);
             }
             mbar_wait(acc_full + 8 * buf, use & 1);
             if (warp == 2 && lane == 0) TRACE(2, tr2);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t acc_col = buf * p.MT * p.Nstride;
             // work items (mt, cc) are dealt round-robin to the warps sharing a quadrant
-            const int nitems = p.MT * ncc;
-            for (int item = half; item < nitems; item += NSHARE) {
-                const int mt = item / ncc, cc = item - mt * ncc;
+            int turn = 0;
+            for (int mt = 0; mt < p.MT; ++mt)
+            for (int cc = 0; cc < ncc; ++cc) {
+                if (NSHARE > 1) { const bool mine = (turn == half); turn = (turn + 1 == NSHARE) ? 0 : turn + 1; if (!mine) continue; }
                 const int row = mt * 128 + q * 32 + lane;
                 int bb, l;
                 if (p.packed) { const int f = row / p.S; bb = b0 + f; l = row - f * p.S; if (f >= p.FR) l = p.L; }
@@ -492,7 +514,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
                         if (j < p.Cout) acc = fmaf(hw[j], f[j], acc);
-                    acc = fmaf(hw[p.Cout], xin[mt & 3], acc);
+                    acc = fmaf(hw[p.Cout], mt == 0 ? xin0 : (mt == 1 ? xin1 : (mt == 2 ? xin2 : xin3)), acc);
                     p.y[(size_t)bb * p.T + l] = tanh_fast(acc);
                 }
             }
@@ -503,66 +525,116 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else if (UPCAT) {
         // ======================= upsample producers (decoder) =======================
+        // F.interpolate(scale_factor=2, mode="linear", align_corners=True) of the previous block's output, written straight
+        // into the swizzled operand tile. A thread owns (16 consecutive output rows) x (one 16-byte channel vector): the 10
+        // previous-level rows they interpolate between (row l lies between prev rows (l-1)>>1 and that + 1, since
+        // src = l*(Lin-1)/(2Lin-1)) are fetched into registers one work unit AHEAD, so their DRAM latency overlaps the wait
+        // for the shared-memory stage.
         const int pt = (warp - 2 - kEpilogueWarps) * 32 + lane;
         int sa = 0, pa = 0;
+        uint4 xr[10];
+        bool pref = false;
+        const int nruns = (p.rows_used + 15) >> 4;
+        auto unit_fast = [&](int c) { const ChunkInfo u = chunk_info<UPCAT>(p, c); return !p.packed && u.up && nruns * u.nk * 2 <= NPROD; };
+        auto fetch = [&](int ub0, int ul0, int c) {
+            const ChunkInfo u = chunk_info<UPCAT>(p, c);
+            const int nvec = u.nk * 2;
+            if (pt >= nruns * nvec) return;
+            const int run = pt / nvec, vec = pt - run * nvec;
+            const int ch = u.idx * 64 + vec * 8;
+            const int ms = (ul0 - PAD + 16 * run) >> 1;
+            const bool chok = ch < p.Cin0 && ub0 < p.B;
+            const __nv_bfloat16 *pb = p.prev + (size_t)ub0 * p.Lin * p.Cin0 + ch;
+#pragma unroll
+            for (int qq = 0; qq < 10; ++qq) {
+                int m = ms - 1 + qq;
+                m = m < 0 ? 0 : (m > p.Lin - 1 ? p.Lin - 1 : m);
+                xr[qq] = chok ? __ldg(reinterpret_cast<const uint4 *>(pb + (size_t)m * p.Cin0)) : make_uint4(0u, 0u, 0u, 0u);
+            }
+        };
+        // interpolate + store the 16 rows of one item from the register window
+        auto emit = [&](uint8_t *dst, int l0, int c, int item, const uint4 (&w)[10]) {
+            const ChunkInfo u = chunk_info<UPCAT>(p, c);
+            const int nvec = u.nk * 2;
+            const int run = item / nvec, vec = item - run * nvec;
+            const int ch = u.idx * 64 + vec * 8;
+            const int lstart = l0 - PAD + 16 * run;                            // even
+            const int ms = lstart >> 1;
+            const bool chok = ch < p.Cin0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int row = 16 * run + j;
+                if (row >= p.rows_used) break;
+                const int l = lstart + j;
+                uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                if (chok && l >= 0 && l < p.L) {
+                    const int qa = (j >> 1) + (j & 1);
+                    // out = a + lam1 * (b - a) in packed bf16 (HFMA2)
+                    const float lam1 = p.up_scale * (float)l - (float)(ms - 1 + qa);
+                    const __nv_bfloat162 lam = __float2bfloat162_rn(lam1);
+                    const __nv_bfloat162 *a2 = reinterpret_cast<const __nv_bfloat162 *>(&w[qa]);
+                    const __nv_bfloat162 *b2 = reinterpret_cast<const __nv_bfloat162 *>(&w[qa + 1]);
+                    __nv_bfloat162 r2[4];
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) r2[q4] = __hfma2(lam, __hsub2(b2[q4], a2[q4]), a2[q4]);
+                    o = *reinterpret_cast<const uint4 *>(r2);
+                }
+                *reinterpret_cast<uint4 *>(dst + row * 128 + ((vec ^ (row & 7)) << 4)) = o;
+            }
+        };
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             int b0, l0, n0;
             tile_coords(tile, b0, l0, n0);
             for (int c = 0; c < p.nchunks; ++c) {
+                const bool fast = unit_fast(c);
+                if (fast && !pref) fetch(b0, l0, c);
                 mbar_wait(a_empty + 8 * sa, pa ^ 1);
-                if (c < p.nchunks0) {
-                    const int nvec = chunk_k16(p, c) * 2;                    // 16-byte vectors per row
+                const ChunkInfo cu = chunk_info<UPCAT>(p, c);
+                if (cu.up) {
+                    const int nvec = cu.nk * 2;                              // 16-byte vectors per row
                     uint8_t *dst = base_ptr + sm.a + sa * p.a_stage_bytes;
-                    if (!p.packed) {
-                        // a thread owns (16 consecutive output rows) x (one 16-byte channel vector): the 10 previous-level
-                        // rows they interpolate between are loaded once, all loads in flight together. Row l of the
-                        // upsampled signal lies between prev rows (l-1)>>1 and that + 1 (src = l*(Lin-1)/(2Lin-1)).
-                        const int nruns = (p.rows_used + 15) >> 4;
+                    if (fast) {
+                        if (pt < nruns * nvec) emit(dst, l0, c, pt, xr);
+                        pref = false;
+                        // next upsampled unit of this CTA: next chunk of this tile, or chunk 0 of the next tile
+                        int nt = tile, nc = c + 1;
+                        for (int hop = 0; hop < p.nchunks; ++hop) {               // next upsampled chunk in K-loop order
+                            if (nc >= p.nchunks) { nc = 0; nt += gridDim.x; }
+                            if (chunk_info<UPCAT>(p, nc).up) break;
+                            ++nc;
+                        }
+                        if (nt < total_tiles && unit_fast(nc)) {
+                            int nb0, nl0, nn0;
+                            tile_coords(nt, nb0, nl0, nn0);
+                            fetch(nb0, nl0, nc);
+                            pref = true;
+                        }
+                    } else if (!p.packed) {
                         for (int itx = pt; itx < nruns * nvec; itx += NPROD) {
+                            uint4 w[10];
                             const int run = itx / nvec, vec = itx - run * nvec;
-                            const int ch = c * 64 + vec * 8;
-                            const int lstart = l0 - PAD + 16 * run;            // even
-                            const int ms = lstart >> 1;
+                            const int ch = cu.idx * 64 + vec * 8;
+                            const int ms = (l0 - PAD + 16 * run) >> 1;
                             const bool chok = ch < p.Cin0;
-                            uint4 xr[10];
                             const __nv_bfloat16 *pb = p.prev + (size_t)b0 * p.Lin * p.Cin0 + ch;
 #pragma unroll
                             for (int qq = 0; qq < 10; ++qq) {
                                 int m = ms - 1 + qq;
                                 m = m < 0 ? 0 : (m > p.Lin - 1 ? p.Lin - 1 : m);
-                                xr[qq] = chok ? __ldg(reinterpret_cast<const uint4 *>(pb + (size_t)m * p.Cin0)) : make_uint4(0u, 0u, 0u, 0u);
+                                w[qq] = chok ? __ldg(reinterpret_cast<const uint4 *>(pb + (size_t)m * p.Cin0)) : make_uint4(0u, 0u, 0u, 0u);
                             }
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                const int row = 16 * run + j;
-                                if (row >= p.rows_used) break;
-                                const int l = lstart + j;
-                                uint4 o = make_uint4(0u, 0u, 0u, 0u);
-                                if (chok && l >= 0 && l < p.L) {
-                                    const int qa = (j >> 1) + (j & 1);
-                                    // out = a + lam1 * (b - a) in packed bf16 (HFMA2): 3 ops per pair instead of 9
-                                    const float lam1 = p.up_scale * (float)l - (float)(ms - 1 + qa);
-                                    const __nv_bfloat162 lam = __float2bfloat162_rn(lam1);
-                                    const __nv_bfloat162 *a2 = reinterpret_cast<const __nv_bfloat162 *>(&xr[qa]);
-                                    const __nv_bfloat162 *b2 = reinterpret_cast<const __nv_bfloat162 *>(&xr[qa + 1]);
-                                    __nv_bfloat162 r2[4];
-#pragma unroll
-                                    for (int q4 = 0; q4 < 4; ++q4) r2[q4] = __hfma2(lam, __hsub2(b2[q4], a2[q4]), a2[q4]);
-                                    o = *reinterpret_cast<const uint4 *>(r2);
-                                }
-                                *reinterpret_cast<uint4 *>(dst + row * 128 + ((vec ^ (row & 7)) << 4)) = o;
-                            }
+                            emit(dst, l0, c, itx, w);
                         }
                     } else {
+                        // frames shorter than a tile (packed): generic per-(row, vector) path, ATen index math in fp32
                         const int items = p.rows_used * nvec;
                         for (int itx = pt; itx < items; itx += NPROD) {
                             const int row = itx / nvec, vec = itx - row * nvec;
                             const int f = row / p.S;
                             const int bb = b0 + f, l = row - f * p.S - PAD;
-                            const int ch = c * 64 + vec * 8;
+                            const int ch = cu.idx * 64 + vec * 8;
                             uint4 o = make_uint4(0u, 0u, 0u, 0u);
                             if (bb < p.B && l >= 0 && l < p.L && ch < p.Cin0) {
-                                // F.interpolate(scale_factor=2, mode="linear", align_corners=True): ATen index math in fp32
                                 const float s = p.up_scale * (float)l;
                                 const int i0 = (int)s;
                                 const int i1 = i0 + (i0 < p.Lin - 1 ? 1 : 0);
@@ -849,6 +921,19 @@ static int build_plan(TcState *st, const float *x, float *y, int B, int T, void 
         p.nchunks0 = (lv.cin0 + 63) / 64;
         p.nchunks = p.nchunks0 + (lv.cin1 + 63) / 64;
         p.Npad = lv.Npad;
+        {
+            // K-loop order. Encoders: natural. Decoders: full upsampled chunks, then the skip chunks (TMA), then the partial
+            // upsampled chunk: a TMA chunk is never preceded by a short chunk, so its load latency hides behind MMAs.
+            int k = 0;
+            if (!dec) { for (int c = 0; c < p.nchunks; ++c) p.chunk_map[k++] = (unsigned char)c; }
+            else {
+                const int nfull0 = lv.cin0 / 64, n1 = p.nchunks - p.nchunks0;
+                for (int c = 0; c < nfull0; ++c) p.chunk_map[k++] = (unsigned char)(0x80 | c);
+                for (int c = 0; c < n1; ++c) p.chunk_map[k++] = (unsigned char)c;
+                if (nfull0 < p.nchunks0) p.chunk_map[k++] = (unsigned char)(0x80 | nfull0);
+            }
+            if (p.nchunks > 16) return tc_fail("too many K chunks");
+        }
         // ---- tiling ---------------------------------------------------------------------------------
         const bool packed = L < 128;
         auto geometry = [&](int MT, int nsplit) {
@@ -904,26 +989,29 @@ static int build_plan(TcState *st, const float *x, float *y, int B, int T, void 
             if (p.m_tiles * ns < st->num_sms) { MT = 1; geometry(MT, ns); }
             while (p.m_tiles * ns * 2 <= st->num_sms + st->num_sms / 4 && ns < 4 && lv.Npad / (ns * 2) >= 48) { ns *= 2; geometry(MT, ns); }
         }
-        p.na = 2;
         {
-            // weight stages hold `tg` consecutive taps (one TMA box, one barrier handshake per stage)
+            // A ring depth: decoders whose K chunks are short (5 taps, few K-steps) need the TMA/producers to run two chunks
+            // ahead; everything else double-buffers. Weight stages hold `tg` consecutive taps (one TMA box, one handshake).
             const int budget = (int)kSmemLimit - 2048 - p.Npad * 8 - 512;
-            int best_tg = 0;
-            for (int tg : {5, 3, 1}) {
-                if (KS % tg != 0) continue;
-                const int stage = round_up(p.Nh * 128 * tg, 1024);
-                const int want_stages = (tg == 1) ? 4 : 3;
-                if (2 * (int)p.a_stage_bytes + want_stages * stage <= budget) { best_tg = tg; break; }
+            const int na_want = (dec && !packed && p.nchunks >= 3 && p.MT <= 2) ? 3 : 2;
+            bool ok = false;
+            for (int na = na_want; na >= 1 && !ok; --na) {
+                for (int tg : {5, 3, 1}) {
+                    if (KS % tg != 0) continue;
+                    const int stage = round_up(p.Nh * 128 * tg, 1024);
+                    const int min_stages = (tg == 1) ? 4 : 2;
+                    if (na * (int)p.a_stage_bytes + min_stages * stage > budget) continue;
+                    p.na = na; p.tg = tg;
+                    p.ngroups = (KS + tg - 1) / tg;
+                    p.b_stage_bytes = (uint32_t)stage;
+                    int nb = (budget - na * (int)p.a_stage_bytes) / stage;
+                    if (nb > kMaxBStages) nb = kMaxBStages;
+                    p.nb = nb;
+                    ok = true;
+                    break;
+                }
             }
-            if (best_tg == 0) best_tg = 1;
-            p.tg = best_tg;
-            p.ngroups = (KS + p.tg - 1) / p.tg;
-            p.b_stage_bytes = (uint32_t)round_up(p.Nh * 128 * p.tg, 1024);
-            int nb = (budget - p.na * (int)p.a_stage_bytes) / (int)p.b_stage_bytes;
-            if (nb < 2) { p.na = 1; nb = (budget - (int)p.a_stage_bytes) / (int)p.b_stage_bytes; }
-            if (nb > kMaxBStages) nb = kMaxBStages;
-            if (nb < 2) return tc_fail("level %d does not fit in shared memory", i);
-            p.nb = nb;
+            if (!ok) return tc_fail("level %d does not fit in shared memory", i);
         }
         {
             const int threads = dec ? kThreadsDec : kThreadsEnc;
