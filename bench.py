@@ -251,8 +251,19 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms_total = e0.elapsed_time(e1)
+    # the timed region is tens of milliseconds; nvidia-smi samples every 100 ms. Keep issuing the identical step (untimed)
+    # for ~1.2 s so that the clock / throttle record is taken under the same load.
+    t_load = time.perf_counter()
+    extra = 0
+    while time.perf_counter() - t_load < 1.2:
+        for i in range(args.steps):
+            step(i)
+        torch.cuda.synchronize()
+        extra += args.steps
     barrier()
     clocks = sampler.stop() if sampler else None
+    if clocks is not None:
+        clocks["note"] = f"sampled every 100 ms over the timed steps plus {extra} identical untimed steps"
     t = torch.tensor([ms_total], device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -292,7 +303,20 @@ def main():
     else:
         roof = {"bound": "tensor", "achieved": d["tflops"], "peak": peaks["tensor_tflops"], "unit": "TFLOP/s",
                 "frac": round(d["tflops"] / peaks["tensor_tflops"], 4)}
-    roof.update({"kernel": dname, "kernel_ms": d["ms"], "traffic": None, "peak_source": peaks["source"],
+    traffic = None
+    try:
+        import csv, glob
+        cands = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_conv_tc_*summary.csv")))
+        if cands and precision == "bf16" and B == 256:
+            rows = [r for r in csv.reader(open(cands[-1])) if r and not r[0].startswith("#")]
+            hdr = rows[0]
+            for r in rows[1:]:
+                if r[0] == dname.split("+")[0]:
+                    traffic = (float(r[hdr.index("dram_rd_MB")]) + float(r[hdr.index("dram_wr_MB")])) * 1e6
+    except Exception:
+        traffic = None
+    roof.update({"kernel": dname, "kernel_ms": d["ms"], "traffic": traffic, "algorithmic_bytes": dbytes,
+                 "algorithmic_flops": dflops, "peak_source": peaks["source"],
                  "net_frac": round(sum(l["roof_ms"] for l in levels) / sum(l["ms"] for l in levels), 4),
                  "sum_levels_ms": round(float(sum(blk_ms)), 4)})
 
