@@ -1,6 +1,7 @@
 // tools/umma_rate.cu — development probe: cycles per tcgen05.mma (M=128, K=16, bf16) versus N and operand layout.
 // Question: for small N, is the MMA rate bounded by the shared-memory read of the 128-row A slice, and does a
 // layout whose K16 slice is compact (32B swizzle / interleaved) lift that bound?
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <cstdio>
@@ -23,16 +24,24 @@ __device__ __forceinline__ bool elect_one() {
 }
 // mode 0: SW128 (row 128 B, K slice kk at +32kk)          mode 1: SW64 (row 64 B; two sub-tiles of K=32)
 // mode 2: SW32  (row 32 B; four sub-tiles of K=16)         mode 3: INTERLEAVE (plane per 16 B chunk)
-extern "C" __global__ void __launch_bounds__(128) rate_kernel(long long *out, int mode, int N, int nmma, int ROWS)
+extern "C" __global__ void __launch_bounds__(128) rate_kernel(const __grid_constant__ CUtensorMap tmap, long long *out, int mode, int N, int nmma, int ROWS, int tma_boxes, int ld_traffic)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     __shared__ uint64_t bar;
+    __shared__ uint64_t tbar;
+    __shared__ volatile int stop_flag;
     __shared__ uint32_t tmem_slot;
     const int warp = threadIdx.x >> 5;
     const uint32_t a_bytes = (uint32_t)ROWS * 128, b_bytes = 256 * 128;
-    for (uint32_t i = threadIdx.x; i < (a_bytes + b_bytes) / 4; i += 128) ((uint32_t *)smem)[i] = 0x3c003c00u + (i & 0xff);
-    if (threadIdx.x == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    for (uint32_t i = threadIdx.x; i < (a_bytes + b_bytes) / 4; i += 128) {
+        uint32_t h = (i + blockIdx.x * 7919u) * 2654435761u; h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+        // random bf16 pairs in (-2,2): sign + exponent 126..128 + random mantissa
+        const uint32_t r = (h & 0x807F807Fu) | 0x3F003F00u;
+        ((uint32_t *)smem)[i] = (ld_traffic & 2) ? r : 0x3c003c00u + (i & 0xff);
+    }
+    if (threadIdx.x == 0) stop_flag = 0;
+    if (threadIdx.x == 0) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar))); asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&tbar))); }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     if (warp == 0) {
@@ -45,6 +54,36 @@ extern "C" __global__ void __launch_bounds__(128) rate_kernel(long long *out, in
     const uint32_t tmem = tmem_slot;
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const uint32_t sA = smem_u32(smem), sB = sA + a_bytes;
+    if (warp == 2 && tma_boxes > 0 && (threadIdx.x & 31) == 0) {
+        // concurrent TMA stream: boxes of 176 rows x 64 channels into the region after the B tile
+        const uint32_t dst = sB + 256 * 128;
+        uint32_t ph = 0;
+        for (int i = 0; i < tma_boxes && !stop_flag; ++i) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&tbar)), "r"(176 * 128) : "memory");
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(smem_u32(&tbar)), "r"(0), "r"((i * 176) % 8000), "r"(i & 1) : "memory");
+            uint32_t ok;
+            do {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(&tbar)), "r"(ph) : "memory");
+            } while (!ok);
+            ph ^= 1;
+        }
+    }
+    if ((warp == 0 || warp == 3) && ld_traffic) {
+        uint32_t v[32]; uint32_t sink = 0;
+        while (!stop_flag) {
+            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + 384;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                  "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+                  "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+                  "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]) : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            sink += v[0] ^ v[31];
+        }
+        if (sink == 0x12345678u) out[1] = 0;
+    }
     if (warp == 1 && mode == 4) {
         // optimized issue: hi word constant, lo word = base + small immediates, 4 K-steps unrolled
         const uint32_t hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
@@ -52,17 +91,21 @@ extern "C" __global__ void __launch_bounds__(128) rate_kernel(long long *out, in
         long long t0 = clock64();
         if (elect_one()) {
             uint32_t acc = 0;
-            for (int i = 0; i < nmma / 8; ++i) {
+#ifndef P_MT
+#define P_MT 2
+#define P_NK 4
+#define P_NSTRIDE 256
+#endif
+            for (int i = 0; i < nmma / (P_MT * P_NK); ++i) {
                 const int tap = i % 15;
 #pragma unroll
-                for (int mt = 0; mt < 2; ++mt) {
+                for (int mt = 0; mt < P_MT; ++mt) {
                     const uint32_t a_lo = a_lo0 + (uint32_t)(mt * 128 + tap) * 8;
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
+                    for (int kk = 0; kk < P_NK; ++kk) {
                         asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
                                      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
-                                     ::"r"(tmem + mt * 256), "r"(a_lo + 2 * kk), "r"(hi), "r"(b_lo0 + 2 * kk), "r"(hi), "r"(idesc), "r"(acc) : "memory");
-                        acc = 1;
+                                     ::"r"(tmem + mt * P_NSTRIDE), "r"(a_lo + 2 * kk), "r"(hi), "r"(b_lo0 + 2 * kk), "r"(hi), "r"(idesc), "r"(kk == 0 ? (i > 0 ? 1u : 0u) : 1u) : "memory");
                     }
                 }
             }
@@ -75,7 +118,7 @@ extern "C" __global__ void __launch_bounds__(128) rate_kernel(long long *out, in
             asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(&bar)), "r"(0) : "memory");
         } while (!ok);
         long long t2 = clock64();
-        if ((threadIdx.x & 31) == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+        if ((threadIdx.x & 31) == 0) { out[0] = t1 - t0; out[1] = t2 - t0; stop_flag = 1; }
     } else if (warp == 1) {
         long long t0 = clock64();
         if (elect_one()) {
@@ -116,19 +159,36 @@ extern "C" __global__ void __launch_bounds__(128) rate_kernel(long long *out, in
 int main() {
     long long *d; CK(cudaMalloc(&d, 16));
     const int ROWS = 288;
-    const int smem = ROWS * 128 + 256 * 128 + 2048;
+    const int smem = ROWS * 128 + 256 * 128 + 176 * 128 + 2048;
     CK(cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    const char *names[5] = {"SW128", "SW64", "SW32", "INTERLEAVE", "SW128-fastissue"};
-    for (int mode = 4; mode < 5; ++mode)
-        for (int N : {16, 32, 48, 64, 96, 128, 192, 256}) {
-            long long h[2];
-            for (int rep = 0; rep < 2; ++rep) {
-                rate_kernel<<<1, 128, smem>>>(d, mode, N, 480, ROWS);
-                cudaError_t e = cudaDeviceSynchronize();
-                if (e != cudaSuccess) { printf("%s N=%d: CUDA error %s\n", names[mode], N, cudaGetErrorString(e)); return 2; }
-                CK(cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost));
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void *fn = nullptr; cudaDriverEntryPointQueryResult qres;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    __nv_bfloat16 *gx; CK(cudaMalloc(&gx, (size_t)2 * 16384 * 64 * 2)); CK(cudaMemset(gx, 0, (size_t)2 * 16384 * 64 * 2));
+    CUtensorMap maps[3];
+    const int Cs[3] = {24, 64, 24};
+    const int strideMul[3] = {2, 2, 1};          // decimated (row stride 2C) / plain
+    for (int k = 0; k < 3; ++k) {
+        cuuint64_t gdim[3] = {(cuuint64_t)Cs[k], 8192, 2};
+        cuuint64_t gstr[2] = {(cuuint64_t)Cs[k] * 2 * strideMul[k], (cuuint64_t)8192 * Cs[k] * 2 * strideMul[k]};
+        cuuint32_t box[3] = {64, 176, 1}; cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = ((EncodeFn)fn)(&maps[k], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, gx, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { printf("encode failed %d\n", (int)r); return 3; }
+    }
+    for (int grid : {1, 148})
+        for (int rnd : {0, 2})
+            for (int N : {32, 48, 96, 128}) {
+                long long h[2];
+                for (int rep = 0; rep < 3; ++rep) {
+                    rate_kernel<<<grid, 128, smem>>>(maps[0], d, 4, N, 1920, ROWS, 0, rnd);
+                    cudaError_t e = cudaDeviceSynchronize();
+                    if (e != cudaSuccess) { printf("N=%d: CUDA error %s\n", N, cudaGetErrorString(e)); return 2; }
+                    CK(cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost));
+                }
+                printf("grid=%3d data=%-8s N=%3d  %6.1f cyc/MMA\n", grid, rnd ? "random" : "constant", N, h[1] / 1920.0);
             }
-            printf("%-10s N=%3d  issue %6.1f cyc/MMA   complete %6.1f cyc/MMA   (ideal N/2 = %d)\n", names[mode], N, h[0] / 480.0, h[1] / 480.0, N / 2);
-        }
     return 0;
 }

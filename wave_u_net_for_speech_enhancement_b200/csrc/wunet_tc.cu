@@ -218,6 +218,9 @@ struct TcParams {
     int nb;                    // B ring depth
     int na;                    // A stages (1 or 2)
     int tg, ngroups;           // taps per weight stage, stages per chunk (= ceil(KS / tg))
+    int n_epi;                 // epilogue warps of this kernel flavour (slab count for bulk stores)
+    int bulk_store;            // 1: epilogue stages 32-row slabs in smem and writes them with cp.async.bulk (contiguous NLC rows)
+    int resident;              // 1: all weight tiles of the block stay in shared memory for the CTA's lifetime (no ring)
     uint32_t tmem_cols;
     // operands
     const __nv_bfloat16 *prev; // DEC: previous block output [B][L/2][Cin0]
@@ -236,7 +239,7 @@ struct TcParams {
 
 // smem carve-up (offsets from the 1024-aligned base): A stages | B stages | ss | barriers
 struct SmemMap {
-    uint32_t a, b, ss, bars;
+    uint32_t a, b, ss, stg, bars;
 };
 __host__ __device__ inline SmemMap smem_map(const TcParams &p)
 {
@@ -244,7 +247,8 @@ __host__ __device__ inline SmemMap smem_map(const TcParams &p)
     m.a = 0;
     m.b = p.na * p.a_stage_bytes;
     m.ss = m.b + p.nb * p.b_stage_bytes;
-    m.bars = m.ss + (uint32_t)p.Npad * 8 + 64 * 4;   // + head weights (<= 33) and bias
+    m.stg = (m.ss + (uint32_t)p.Npad * 8 + 64 * 4 + 127) & ~127u;   // after scale/shift + head weights
+    m.bars = m.stg + (p.bulk_store ? (uint32_t)(p.n_epi * 32 * p.Cout * 2) : 0u);   // one 32-row slab per epilogue warp
     m.bars = (m.bars + 15) & ~15u;
     return m;
 }
@@ -287,6 +291,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(base_ptr + sm.bars + 64 + 16 * kMaxBStages + 32);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp roles. The scheduler of an SM sub-partition favours the highest warp id among eligible warps, so the two
+    // single-lane service warps (TMA, MMA issue) sit at the top: the MMA issuer must never queue behind epilogue math.
+    constexpr int kFirstProducer = kEpilogueWarps;
+    constexpr int kTmaWarp = kEpilogueWarps + (UPCAT ? kProducerWarps : 0);
+    constexpr int kMmaWarp = kTmaWarp + 1;
     const int total_tiles = p.m_tiles * p.nsplit;
 
     if (threadIdx.x == 0) {
@@ -300,10 +309,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_init(acc_full + 8 * s, 1);
             mbar_init(acc_empty + 8 * s, kEpilogueWarps);
         }
-        for (int s = 0; s < p.nb; ++s) { mbar_init(b_full + 8 * s, 1); mbar_init(b_empty + 8 * s, 1); }
+        for (int s = 0; s < min(p.nb, kMaxBStages); ++s) { mbar_init(b_full + 8 * s, 1); mbar_init(b_empty + 8 * s, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {
+    if (warp == kMmaWarp) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -329,7 +338,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         else { b0 = mi / p.tiles_per_frame; l0 = (mi - b0 * p.tiles_per_frame) * 128 * p.MT; }
     };
 
-    if (warp == 0) {
+    if (warp == kTmaWarp) {
         // ======================= TMA producer =======================
         if (lane == 0) {
             int sa = 0, pa = 0, sb = 0, pb = 0;
@@ -361,6 +370,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (++a_c == p.nchunks) { a_c = 0; a_tile += gridDim.x; }
                 return true;
             };
+            if (p.resident) {
+                // the whole packed weight set of this block (nchunks x KS tiles of [Nh x 64]) is loaded once per CTA
+                mbar_expect_tx(b_full, (uint32_t)p.nchunks * p.ngroups * p.tg * p.Nh * 128);
+                for (int c = 0; c < p.nchunks; ++c) {
+                    const int kslot = chunk_info<UPCAT>(p, c).kslot;
+                    for (int g = 0; g < p.ngroups; ++g)
+                        tma_load_3d(base + sm.b + (uint32_t)(c * p.ngroups + g) * p.b_stage_bytes, &tmW, b_full, kslot * 64, 0, g * p.tg);
+                }
+            }
             for (int pre = 0; pre < p.na - 1; ++pre) issue_a(true);          // A tiles run na-1 chunks ahead of the weights
             if (p.na == 1) issue_a(true);
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -371,7 +389,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     // chunk is slipped in between them the moment its stage is released (it never blocks the weights)
                     bool a_done = false;
                     const int kslot = chunk_info<UPCAT>(p, c).kslot;
-                    for (int g = 0; g < p.ngroups; ++g) {
+                    for (int g = 0; g < (p.resident ? 0 : p.ngroups); ++g) {
                         if (!a_done) a_done = issue_a(false);
                         mbar_wait(b_empty + 8 * sb, pb ^ 1);
                         TRACE(0, tr0);
@@ -383,13 +401,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == kMmaWarp) {
         // ======================= MMA issuer =======================
         // The whole warp runs the (uniform) control flow; one elected lane issues tcgen05.mma / commit.
         {
             int sa = 0, pa = 0, sb = 0, pb = 0, it = 0;
             int tr1 = 0; (void)tr1;
+            int tr3 = 0; (void)tr3;
             const uint32_t tile_bytes = (uint32_t)p.Nh * 128;
+            if (p.resident) { mbar_wait(b_full, 0); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
                 int b0, l0, n0;
                 tile_coords(tile, b0, l0, n0);
@@ -410,10 +430,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a_base = base + sm.a + sa * p.a_stage_bytes;
                     for (int g = 0; g < p.ngroups; ++g) {
-                        mbar_wait(b_full + 8 * sb, pb);
-                        if (lane == 0) TRACE(1, tr1);
-                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const uint32_t b_base = base + sm.b + sb * p.b_stage_bytes;
+                        uint32_t b_base;
+                        if (p.resident) {
+                            b_base = base + sm.b + (uint32_t)(c * p.ngroups + g) * p.b_stage_bytes;
+                        } else {
+                            mbar_wait(b_full + 8 * sb, pb);
+                            if (lane == 0) TRACE(1, tr1);
+                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                            b_base = base + sm.b + sb * p.b_stage_bytes;
+                        }
                         const int t_end = min(KS, (g + 1) * p.tg);
                         if (elect_one()) {
                             // descriptor words: hi = SBO(1024 B) | version 1 | SWIZZLE_128B, lo = (addr >> 4) | LBO(1)
@@ -423,6 +448,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             a_lo += (uint32_t)(g * p.tg) * 8;                      // tap shift: +128 B per tap
                             const uint32_t b_step = tile_bytes >> 4;
                             for (int t = g * p.tg; t < t_end; ++t) {
+                                TRACE(3, tr3);
                                 const uint32_t accf = (c | t) ? 1u : 0u;
                                 if (p.MT == 4) issue_tap_nk<4>(nk, acc_col, p.Nstride, a_lo, b_lo, hi, idesc, accf);
                                 else if (p.MT == 2) issue_tap_nk<2>(nk, acc_col, p.Nstride, a_lo, b_lo, hi, idesc, accf);
@@ -430,7 +456,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 a_lo += 8;
                                 b_lo += b_step;
                             }
-                            umma_commit(b_empty + 8 * sb);
+                            if (!p.resident) umma_commit(b_empty + 8 * sb);
                         }
                         __syncwarp();
                         if (++sb == p.nb) { sb = 0; pb ^= 1; }
@@ -443,10 +469,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 __syncwarp();
             }
         }
-    } else if (warp < 2 + kEpilogueWarps) {
+    } else if (warp < kEpilogueWarps) {
         // ======================= epilogue warps (TMEM lane quadrant = warp % 4; two warps share a quadrant) ==========
         const int q = warp & 3;
-        const int half = (warp - 2) >> 2;                 // 0 .. kEpilogueWarps/4 - 1
+        const int half = warp >> 2;                       // 0 .. kEpilogueWarps/4 - 1
         constexpr int NSHARE = kEpilogueWarps / 4;        // warps sharing a quadrant
         const float2 *ss = reinterpret_cast<const float2 *>(base_ptr + sm.ss);
         int it = 0;
@@ -458,7 +484,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int ncc = (Nthis + 31) >> 5;
             const int buf = (p.nacc == 2) ? (it & 1) : 0;
             const uint32_t use = (p.nacc == 2) ? (uint32_t)(it >> 1) : (uint32_t)it;
-            if (warp == 2 && lane == 0) TRACE(2, tr2);
+            if (warp == 0 && lane == 0) TRACE(2, tr2);
             // fused head: fetch the raw-input samples of this thread's rows before waiting for the accumulators
             float xin0 = 0.f, xin1 = 0.f, xin2 = 0.f, xin3 = 0.f;     // scalars (not an array): they must stay in registers
             if (p.head && b0 < p.B) {
@@ -470,10 +496,50 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (p.MT > 3 && lb + 384 < p.L) xin3 = __ldg(xp + 384);
             }
             mbar_wait(acc_full + 8 * buf, use & 1);
-            if (warp == 2 && lane == 0) TRACE(2, tr2);
+            if (warp == 0 && lane == 0) TRACE(2, tr2);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t acc_col = buf * p.MT * p.Nstride;
             // work items (mt, cc) are dealt round-robin to the warps sharing a quadrant
+            if (p.bulk_store) {
+                // rows of this warp's quadrant are staged in its shared-memory slab (the [32 rows x Cout] block is one contiguous
+                // range of the channels-last output) and written with a single bulk async copy: scattered 16-byte row stores
+                // would occupy the L1/shared-memory pipe for 32 wavefronts each and starve the MMA operand reads.
+                uint8_t *slab = base_ptr + sm.stg + (uint32_t)warp * (32u * p.Cout * 2u);
+                for (int mt = half; mt < p.MT; mt += NSHARE) {
+                    for (int cc = 0; cc < ncc; ++cc) {
+                        uint32_t v[32];
+                        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc_col + (uint32_t)(mt * p.Nstride + cc * 32), v);
+                        if (cc == 0) {                                      // slab free again? (previous bulk copy has read it)
+                            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                            __syncwarp();
+                        }
+                        const int colbase = cc * 32;
+                        uint8_t *srow = slab + (uint32_t)lane * (p.Cout * 2u) + colbase * 2;
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            if (colbase + g * 8 < p.Cout) {
+                                float f[8];
+#pragma unroll
+                                for (int j = 0; j < 8; j += 2) {
+                                    const float4 s2 = *reinterpret_cast<const float4 *>(&ss[colbase + g * 8 + j]);
+                                    f[j] = lrelu(fmaf(__uint_as_float(v[g * 8 + j]), s2.x, s2.y));
+                                    f[j + 1] = lrelu(fmaf(__uint_as_float(v[g * 8 + j + 1]), s2.z, s2.w));
+                                }
+                                *reinterpret_cast<uint4 *>(srow + g * 16) =
+                                    make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+                            }
+                        }
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        const __nv_bfloat16 *gdst = p.out + ((size_t)b0 * p.L + l0 + mt * 128 + q * 32) * p.Cout;
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                     ::"l"(gdst), "r"(smem_u32(slab)), "r"(32u * p.Cout * 2u) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                }
+            } else {
             int turn = 0;
             for (int mt = 0; mt < p.MT; ++mt)
             for (int cc = 0; cc < ncc; ++cc) {
@@ -518,11 +584,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     p.y[(size_t)bb * p.T + l] = tanh_fast(acc);
                 }
             }
+            }
             // accumulator buffer drained: hand it back to the MMA warp
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty + 8 * buf);
         }
+        if (p.bulk_store && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     } else if (UPCAT) {
         // ======================= upsample producers (decoder) =======================
         // F.interpolate(scale_factor=2, mode="linear", align_corners=True) of the previous block's output, written straight
@@ -530,7 +598,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // previous-level rows they interpolate between (row l lies between prev rows (l-1)>>1 and that + 1, since
         // src = l*(Lin-1)/(2Lin-1)) are fetched into registers one work unit AHEAD, so their DRAM latency overlaps the wait
         // for the shared-memory stage.
-        const int pt = (warp - 2 - kEpilogueWarps) * 32 + lane;
+        const int pt = (warp - kFirstProducer) * 32 + lane;
         int sa = 0, pa = 0;
         uint4 xr[10];
         bool pref = false;
@@ -664,7 +732,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols));
+    if (warp == kMmaWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols));
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -849,8 +917,8 @@ int tc_set_weights(TcState **pst, int n, int ci, const TcBlockSrc *blocks, int n
 #ifdef WUNET_TC_TRACE
         if (const char *tl = getenv("WUNET_TC_TRACE_LEVEL")) {
             st->trace_level = atoi(tl);
-            cudaMalloc(&st->trace, 3 * 512 * sizeof(long long));
-            cudaMemset(st->trace, 0, 3 * 512 * sizeof(long long));
+            cudaMalloc(&st->trace, 4 * 512 * sizeof(long long));
+            cudaMemset(st->trace, 0, 4 * 512 * sizeof(long long));
         }
 #endif
         *pst = st;
@@ -989,7 +1057,30 @@ static int build_plan(TcState *st, const float *x, float *y, int B, int T, void 
             if (p.m_tiles * ns < st->num_sms) { MT = 1; geometry(MT, ns); }
             while (p.m_tiles * ns * 2 <= st->num_sms + st->num_sms / 4 && ns < 4 && lv.Npad / (ns * 2) >= 48) { ns *= 2; geometry(MT, ns); }
         }
-        {
+        // epilogue store mode (needs complete tiles of complete rows per warp)
+        p.bulk_store = 0;
+        p.n_epi = dec ? kEpiWarpsDec : kEpiWarpsEnc;
+        p.resident = 0;
+        if (!packed && base_split == 1) {
+            // weights-resident mode: if the block's packed weights fit in shared memory next to the input ring, the persistent
+            // CTA loads them once instead of re-streaming them from L2 for every tile (the L2->SM stream, not HBM and not the
+            // tensor pipe, is what bounds the shallow blocks otherwise).
+            const int budget = (int)kSmemLimit - 2048 - p.Npad * 8 - 512;
+            const int mt_pref = p.MT;
+            for (int MT = mt_pref; MT >= std::max(1, mt_pref / (dec ? 1 : 2)) && !p.resident; MT >>= 1) {
+                geometry(MT, 1);
+                const int stage = round_up(p.Nh * 128 * 5, 1024);
+                const int wbytes = p.nchunks * (KS / 5) * stage;
+                const int na = (dec && p.nchunks >= 3) ? 3 : 2;
+                if (na * (int)p.a_stage_bytes + wbytes <= budget) {
+                    p.resident = 1; p.na = na; p.tg = 5; p.ngroups = KS / 5;
+                    p.b_stage_bytes = (uint32_t)stage;
+                    p.nb = p.nchunks * p.ngroups;
+                }
+            }
+            if (!p.resident) geometry(mt_pref, 1);
+        }
+        if (!p.resident) {
             // A ring depth: decoders whose K chunks are short (5 taps, few K-steps) need the TMA/producers to run two chunks
             // ahead; everything else double-buffers. Weight stages hold `tg` consecutive taps (one TMA box, one handshake).
             const int budget = (int)kSmemLimit - 2048 - p.Npad * 8 - 512;
@@ -999,7 +1090,7 @@ static int build_plan(TcState *st, const float *x, float *y, int B, int T, void 
                 for (int tg : {5, 3, 1}) {
                     if (KS % tg != 0) continue;
                     const int stage = round_up(p.Nh * 128 * tg, 1024);
-                    const int min_stages = (tg == 1) ? 4 : 2;
+                    const int min_stages = (tg == 1) ? 4 : 3;
                     if (na * (int)p.a_stage_bytes + min_stages * stage > budget) continue;
                     p.na = na; p.tg = tg;
                     p.ngroups = (KS + tg - 1) / tg;
@@ -1012,6 +1103,13 @@ static int build_plan(TcState *st, const float *x, float *y, int B, int T, void 
                 }
             }
             if (!ok) return tc_fail("level %d does not fit in shared memory", i);
+        }
+        if (!packed && base_split == 1 && i != 2 * n && (L % (128 * p.MT) == 0) && p.MT >= (dec ? 1 : 2)) {
+            // staged bulk stores if the slabs fit without giving up ring depth / residency / tile size
+            const int need = p.n_epi * 32 * lv.cout * 2 + 256;
+            const int min_nb = p.resident ? p.nb : (p.tg == 1 ? 4 : 3);
+            while ((int)smem_total(p) + need > (int)kSmemLimit && !p.resident && p.nb > min_nb) --p.nb;
+            if ((int)smem_total(p) + need <= (int)kSmemLimit) p.bulk_store = 1;
         }
         {
             const int threads = dec ? kThreadsDec : kThreadsEnc;
@@ -1052,8 +1150,8 @@ static int build_plan(TcState *st, const float *x, float *y, int B, int T, void 
     if (getenv("WUNET_TC_DEBUG")) {
         for (int i = 1; i < 2 * n + 1; ++i) {
             const TcParams &p = pl.lv[i].p;
-            fprintf(stderr, "[wunet tc] blk %2d L=%5d Cin=%3d+%3d Cout=%3d Nh=%3d x%d MT=%d nacc=%d packed=%d FR=%d na=%d nb=%d tg=%d smem=%zu tmem=%u tiles=%d grid=%u\n",
-                    i, p.L, p.Cin0, p.Cin1, p.Cout, p.Nh, p.nsplit, p.MT, p.nacc, p.packed, p.FR, p.na, p.nb, p.tg, pl.lv[i].smem, p.tmem_cols,
+            fprintf(stderr, "[wunet tc] blk %2d L=%5d Cin=%3d+%3d Cout=%3d Nh=%3d x%d MT=%d nacc=%d packed=%d FR=%d res=%d bulk=%d na=%d nb=%d tg=%d smem=%zu tmem=%u tiles=%d grid=%u\n",
+                    i, p.L, p.Cin0, p.Cin1, p.Cout, p.Nh, p.nsplit, p.MT, p.nacc, p.packed, p.FR, p.resident, p.bulk_store, p.na, p.nb, p.tg, pl.lv[i].smem, p.tmem_cols,
                     p.m_tiles * p.nsplit, pl.lv[i].grid.x);
         }
     }
@@ -1127,11 +1225,11 @@ void tc_destroy(TcState *st)
 {
     if (!st) return;
     if (st->trace) {
-        std::vector<long long> h(3 * 512);
+        std::vector<long long> h(4 * 512);
         cudaDeviceSynchronize();
         cudaMemcpy(h.data(), st->trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
         long long t0 = h[512];
-        for (int r = 0; r < 3; ++r) {
+        for (int r = 0; r < 4; ++r) {
             fprintf(stderr, "[trace role %d]", r);
             for (int i = 0; i < 140 && h[r * 512 + i]; ++i) fprintf(stderr, " %lld", h[r * 512 + i] - t0);
             fprintf(stderr, "\n");
