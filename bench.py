@@ -166,6 +166,14 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # libraries (NCCL's version banner, ...) write to fd 1; keep the real stdout for the ONE JSON line only
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+    def emit(obj):
+        real_stdout.write(json.dumps(obj) + "\n")
+        real_stdout.flush()
 
     # --------------------------------------------------------------------------------------------
     # reference arm: the reference's CPU implementation of the path, on the host cores (rank 0 only)
@@ -183,7 +191,7 @@ def main():
                 "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": r["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return
 
     # --------------------------------------------------------------------------------------------
@@ -365,7 +373,7 @@ def main():
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
