@@ -290,6 +290,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t tmem_slot = acc_empty + 16;
     volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(base_ptr + sm.bars + 64 + 16 * kMaxBStages + 32);
 
+    // Programmatic dependent launch: let the next block's kernel be scheduled as our CTAs retire, so its prologue (barrier
+    // init, TMEM allocation, descriptor prefetch, resident weight preload) overlaps this kernel's tail.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // warp roles. The scheduler of an SM sub-partition favours the highest warp id among eligible warps, so the two
     // single-lane service warps (TMA, MMA issue) sit at the top: the MMA issuer must never queue behind epilogue math.
@@ -329,6 +332,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot_ptr;
+    const bool pdl_early_weights = p.resident != 0;      // weights do not depend on the previous kernel's output
+    if (!(warp == kTmaWarp && pdl_early_weights)) asm volatile("griddepcontrol.wait;" ::: "memory");
 
     // tile -> (frame / first row, column half)
     auto tile_coords = [&](int tile, int &b0, int &l0, int &n0) {
@@ -378,6 +383,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int g = 0; g < p.ngroups; ++g)
                         tma_load_3d(base + sm.b + (uint32_t)(c * p.ngroups + g) * p.b_stage_bytes, &tmW, b_full, kslot * 64, 0, g * p.tg);
                 }
+                asm volatile("griddepcontrol.wait;" ::: "memory");        // activations of the previous block from here on
             }
             for (int pre = 0; pre < p.na - 1; ++pre) issue_a(true);          // A tiles run na-1 chunks ahead of the weights
             if (p.na == 1) issue_a(true);
@@ -738,34 +744,42 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // -------------------------------------------------------------------------------------------------
 // enc0: Conv1d(1 -> C, k=15) + BN + LeakyReLU on CUDA cores (Cin = 1: K = 15, HBM-bound), fp32 in, bf16 NLC out
 // -------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) enc0_kernel(const float *__restrict__ x, const float *__restrict__ w /*[C][1][15]*/,
-                                                   const float *__restrict__ scale, const float *__restrict__ shift,
-                                                   __nv_bfloat16 *__restrict__ out, int B, int T, int C)
+__global__ void __launch_bounds__(256, 3) enc0_kernel(const float *__restrict__ x, const float *__restrict__ w /*[C][1][15]*/,
+                                                      const float *__restrict__ scale, const float *__restrict__ shift,
+                                                      __nv_bfloat16 *__restrict__ out, int B, int T, int C)
 {
-    constexpr int KS = 15, PAD = 7, PPT = 4;                  // positions per thread
+    // A block owns 1024 consecutive positions of one frame; a thread owns 4 consecutive positions and sweeps the channels
+    // 8 at a time (32 accumulators, 15 taps: 480 FFMA per 2x15 broadcast LDS.128 of weights). The bf16 rows are staged in
+    // shared memory ([1024][C] is one contiguous range of the channels-last output) and leave with ONE bulk async copy.
+    constexpr int KS = 15, PAD = 7, TILE = 1024;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     extern __shared__ uint8_t smem_raw[];
     float *ws = reinterpret_cast<float *>(smem_raw);          // [15][C]
     float *sc = ws + KS * C, *sh = sc + C;
-    float *xs = sh + C;                                       // [256*PPT + 14]
+    float *xs = sh + C + ((4 - ((KS * C + 2 * C) & 3)) & 3);  // keep xs 16-byte aligned
+    uint8_t *stage = reinterpret_cast<uint8_t *>(xs + TILE + 16);   // [TILE][C] bf16, 16-byte aligned
     const int b = blockIdx.y;
-    const int l0 = blockIdx.x * (256 * PPT);
+    const int l0 = blockIdx.x * TILE;
     for (int i = threadIdx.x; i < KS * C; i += 256) { const int k = i / C, c = i - k * C; ws[i] = w[c * KS + k]; }
     for (int i = threadIdx.x; i < C; i += 256) { sc[i] = scale[i]; sh[i] = shift[i]; }
-    for (int i = threadIdx.x; i < 256 * PPT + KS - 1; i += 256) {
-        const int l = l0 - PAD + i;
+    // the previous forward's last kernel may still be reading this workspace: wait before the first dependent access
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    for (int i = threadIdx.x; i < TILE + 16; i += 256) {
+        const int l = l0 - PAD + i - 1;                       // xs[i] = x[l0 - 8 + i] so that a thread's window starts 16-byte aligned
         xs[i] = (l >= 0 && l < T) ? x[(size_t)b * T + l] : 0.f;
     }
     __syncthreads();
-    // thread handles positions threadIdx.x + 256*j (coalesced-ish stores of C*2 bytes per position)
-    float xv[PPT][KS];
+    // window: positions 4*tid .. 4*tid+3 need x[l-7 .. l+3+7] = xs[4*tid + 1 .. 4*tid + 18]; load xs[4*tid .. 4*tid+19]
+    float xw[20];
 #pragma unroll
-    for (int j = 0; j < PPT; ++j)
-#pragma unroll
-        for (int k = 0; k < KS; ++k) xv[j][k] = xs[threadIdx.x + 256 * j + k];
+    for (int q = 0; q < 5; ++q) {
+        const float4 v = *reinterpret_cast<const float4 *>(&xs[4 * threadIdx.x + 4 * q]);
+        xw[4 * q] = v.x; xw[4 * q + 1] = v.y; xw[4 * q + 2] = v.z; xw[4 * q + 3] = v.w;
+    }
     for (int c0 = 0; c0 < C; c0 += 8) {
-        float acc[PPT][8];
+        float acc[4][8];
 #pragma unroll
-        for (int j = 0; j < PPT; ++j)
+        for (int j = 0; j < 4; ++j)
 #pragma unroll
             for (int m = 0; m < 8; ++m) acc[j][m] = 0.f;
 #pragma unroll
@@ -774,21 +788,27 @@ __global__ void __launch_bounds__(256) enc0_kernel(const float *__restrict__ x, 
             const float4 w1 = *reinterpret_cast<const float4 *>(&ws[k * C + c0 + 4]);
             const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-            for (int j = 0; j < PPT; ++j)
+            for (int j = 0; j < 4; ++j)
 #pragma unroll
-                for (int m = 0; m < 8; ++m) acc[j][m] = fmaf(wv[m], xv[j][k], acc[j][m]);
+                for (int m = 0; m < 8; ++m) acc[j][m] = fmaf(wv[m], xw[j + k + 1], acc[j][m]);
         }
 #pragma unroll
-        for (int j = 0; j < PPT; ++j) {
-            const int l = l0 + threadIdx.x + 256 * j;
-            if (l < T) {
-                float f[8];
+        for (int j = 0; j < 4; ++j) {
+            float f[8];
 #pragma unroll
-                for (int m = 0; m < 8; ++m) f[m] = lrelu(fmaf(acc[j][m], sc[c0 + m], sh[c0 + m]));
-                const uint4 o = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
-                *reinterpret_cast<uint4 *>(out + ((size_t)b * T + l) * C + c0) = o;
-            }
+            for (int m = 0; m < 8; ++m) f[m] = lrelu(fmaf(acc[j][m], sc[c0 + m], sh[c0 + m]));
+            *reinterpret_cast<uint4 *>(stage + (size_t)(4 * threadIdx.x + j) * (C * 2) + c0 * 2) =
+                make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
         }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int rows = min(TILE, T - l0);
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                     ::"l"(out + ((size_t)b * T + l0) * C), "r"(smem_u32(stage)), "r"((uint32_t)(rows * C * 2)) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
 }
 
@@ -862,6 +882,7 @@ struct TcState {
     EncodeTiledFn encode = nullptr;
     bool store_last = false;           // WUNET_TC_STORE_LAST=1: also materialise the last decoder block (tests)
     bool attr_set = false;
+    bool pdl = false;                  // programmatic dependent launch between the blocks (WUNET_TC_PDL=1); measured slower, off
     int num_sms = 148;
     long long *trace = nullptr;        // development: WUNET_TC_TRACE builds + WUNET_TC_TRACE_LEVEL=<block>
     int trace_level = -1;
@@ -914,6 +935,8 @@ int tc_set_weights(TcState **pst, int n, int ci, const TcBlockSrc *blocks, int n
         st->encode = reinterpret_cast<EncodeTiledFn>(fn);
         const char *e = getenv("WUNET_TC_STORE_LAST");
         st->store_last = e && e[0] == '1';
+        const char *pe = getenv("WUNET_TC_PDL");
+        st->pdl = pe && pe[0] == '1';
 #ifdef WUNET_TC_TRACE
         if (const char *tl = getenv("WUNET_TC_TRACE_LEVEL")) {
             st->trace_level = atoi(tl);
@@ -1090,7 +1113,7 @@ static int build_plan(TcState *st, const float *x, float *y, int B, int T, void 
                 for (int tg : {5, 3, 1}) {
                     if (KS % tg != 0) continue;
                     const int stage = round_up(p.Nh * 128 * tg, 1024);
-                    const int min_stages = (tg == 1) ? 4 : 3;
+                    const int min_stages = (tg == 1) ? 4 : 2;   // fewer, fatter weight stages beat a deeper ring (measured)
                     if (na * (int)p.a_stage_bytes + min_stages * stage > budget) continue;
                     p.na = na; p.tg = tg;
                     p.ngroups = (KS + tg - 1) / tg;
@@ -1168,6 +1191,7 @@ int tc_forward(TcState *st, const float *x, float *y, int B, int T, void *ws, cu
     if (!st->attr_set) {
         cudaFuncSetAttribute(conv_tc_kernel<15, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         cudaFuncSetAttribute(conv_tc_kernel<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+        cudaFuncSetAttribute(enc0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
         int dev = 0, sms = 0;
         if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
             st->num_sms = sms;
@@ -1182,18 +1206,29 @@ int tc_forward(TcState *st, const float *x, float *y, int B, int T, void *ws, cu
     {   // enc0
         const TcLevel &lv = st->levels[0];
         const int C = lv.cout;
-        const size_t smem = (size_t)(15 * C + 2 * C + 256 * 4 + 14) * sizeof(float);
+        const size_t smem = (size_t)(15 * C + 2 * C + 4 + 1024 + 16) * sizeof(float) + (size_t)1024 * C * 2 + 16;
         dim3 grid((unsigned)((T + 1023) / 1024), (unsigned)B, 1);
-        enc0_kernel<<<grid, 256, smem, stream>>>(x, lv.w_src, lv.scale, lv.shift, reinterpret_cast<__nv_bfloat16 *>(base + pl.off[0]),
-                                                 B, T, C);
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = grid; cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = st->pdl ? 1 : 0;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, enc0_kernel, x, lv.w_src, lv.scale, lv.shift, reinterpret_cast<__nv_bfloat16 *>(base + pl.off[0]), B, T, C);
         if (cudaGetLastError() != cudaSuccess) return tc_fail("enc0 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         ++nl;
         if (ev) cudaEventRecord(ev[1], stream);
     }
     for (int i = 1; i < 2 * n + 1; ++i) {
         TcPlanLevel &P = pl.lv[i];
-        if (P.upcat) conv_tc_kernel<5, true><<<P.grid, P.threads, P.smem, stream>>>(P.tmA, P.tmW, P.p);
-        else conv_tc_kernel<15, false><<<P.grid, P.threads, P.smem, stream>>>(P.tmA, P.tmW, P.p);
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = P.grid; cfg.blockDim = dim3(P.threads); cfg.dynamicSmemBytes = P.smem; cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = st->pdl ? 1 : 0;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        if (P.upcat) cudaLaunchKernelEx(&cfg, conv_tc_kernel<5, true>, P.tmA, P.tmW, P.p);
+        else cudaLaunchKernelEx(&cfg, conv_tc_kernel<15, false>, P.tmA, P.tmW, P.p);
         const cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return tc_fail("conv_tc level %d launch failed: %s", i, cudaGetErrorString(e));
         ++nl;
