@@ -247,8 +247,8 @@ __host__ __device__ inline SmemMap smem_map(const TcParams &p)
     m.a = 0;
     m.b = p.na * p.a_stage_bytes;
     m.ss = m.b + p.nb * p.b_stage_bytes;
-    m.stg = (m.ss + (uint32_t)p.Npad * 8 + 64 * 4 + 127) & ~127u;   // after scale/shift + head weights
-    m.bars = m.stg + (p.bulk_store ? (uint32_t)(p.n_epi * 32 * p.Cout * 2) : 0u);   // one 32-row slab per epilogue warp
+    m.stg = (m.ss + (uint32_t)p.Npad * 8 + 64 * 4 + 1023) & ~1023u;   // after scale/shift + head weights
+    m.bars = m.stg + (p.bulk_store ? (uint32_t)(p.n_epi * 2048) : 0u);   // one [32 rows x 32 ch] bf16 slab per epilogue warp
     m.bars = (m.bars + 15) & ~15u;
     return m;
 }
@@ -274,7 +274,8 @@ __device__ __forceinline__ ChunkInfo chunk_info(const TcParams &p, int c)
 // -------------------------------------------------------------------------------------------------
 template <int KS, bool UPCAT>
 __global__ void __launch_bounds__(UPCAT ? kThreadsDec : kThreadsEnc, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TcParams p)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+               const __grid_constant__ CUtensorMap tmO, const TcParams p)
 {
     constexpr int PAD = (KS - 1) / 2;
     constexpr int NPROD = kProducerWarps * 32;
@@ -304,6 +305,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
+        if (p.bulk_store) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmO)) : "memory");
         for (int s = 0; s < 4; ++s) {
             mbar_init(a_full + 8 * s, UPCAT ? 1 + kProducerWarps : 1);
             mbar_init(a_empty + 8 * s, 1);
@@ -507,41 +509,42 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t acc_col = buf * p.MT * p.Nstride;
             // work items (mt, cc) are dealt round-robin to the warps sharing a quadrant
             if (p.bulk_store) {
-                // rows of this warp's quadrant are staged in its shared-memory slab (the [32 rows x Cout] block is one contiguous
-                // range of the channels-last output) and written with a single bulk async copy: scattered 16-byte row stores
-                // would occupy the L1/shared-memory pipe for 32 wavefronts each and starve the MMA operand reads.
-                uint8_t *slab = base_ptr + sm.stg + (uint32_t)warp * (32u * p.Cout * 2u);
-                for (int mt = half; mt < p.MT; mt += NSHARE) {
-                    for (int cc = 0; cc < ncc; ++cc) {
-                        uint32_t v[32];
-                        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc_col + (uint32_t)(mt * p.Nstride + cc * 32), v);
-                        if (cc == 0) {                                      // slab free again? (previous bulk copy has read it)
-                            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                            __syncwarp();
-                        }
-                        const int colbase = cc * 32;
-                        uint8_t *srow = slab + (uint32_t)lane * (p.Cout * 2u) + colbase * 2;
+                // Every [32 rows x 32 channels] chunk is staged in this warp's 2 KB slab (64-byte rows, SWIZZLE_64B so the
+                // 16-byte row writes are bank-conflict free) and leaves through one 2-D TMA store. Direct 16-byte row stores
+                // would cost 32 L1 wavefronts per instruction on the pipe the MMA operand reads share.
+                uint8_t *slab = base_ptr + sm.stg + (uint32_t)warp * 2048u;
+                const uint32_t slab_s = smem_u32(slab);
+                uint8_t *srow = slab + lane * 64;
+                const int sw = (lane >> 1) & 3;
+                int turn = 0;
+                for (int mt = 0; mt < p.MT; ++mt)
+                for (int cc = 0; cc < ncc; ++cc) {
+                    if (NSHARE > 1) { const bool mine = (turn == half); turn = (turn + 1 == NSHARE) ? 0 : turn + 1; if (!mine) continue; }
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc_col + (uint32_t)(mt * p.Nstride + cc * 32), v);
+                    const int colbase = cc * 32;
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // slab free again?
+                    __syncwarp();
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            if (colbase + g * 8 < p.Cout) {
-                                float f[8];
+                    for (int g = 0; g < 4; ++g) {
+                        if (colbase + g * 8 < p.Cout) {
+                            float f[8];
 #pragma unroll
-                                for (int j = 0; j < 8; j += 2) {
-                                    const float4 s2 = *reinterpret_cast<const float4 *>(&ss[colbase + g * 8 + j]);
-                                    f[j] = lrelu(fmaf(__uint_as_float(v[g * 8 + j]), s2.x, s2.y));
-                                    f[j + 1] = lrelu(fmaf(__uint_as_float(v[g * 8 + j + 1]), s2.z, s2.w));
-                                }
-                                *reinterpret_cast<uint4 *>(srow + g * 16) =
-                                    make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+                            for (int j = 0; j < 8; j += 2) {
+                                const float4 s2 = *reinterpret_cast<const float4 *>(&ss[colbase + g * 8 + j]);
+                                f[j] = lrelu(fmaf(__uint_as_float(v[g * 8 + j]), s2.x, s2.y));
+                                f[j + 1] = lrelu(fmaf(__uint_as_float(v[g * 8 + j + 1]), s2.z, s2.w));
                             }
+                            *reinterpret_cast<uint4 *>(srow + ((g ^ sw) << 4)) =
+                                make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
                         }
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) {
-                        const __nv_bfloat16 *gdst = p.out + ((size_t)b0 * p.L + l0 + mt * 128 + q * 32) * p.Cout;
-                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                                     ::"l"(gdst), "r"(smem_u32(slab)), "r"(32u * p.Cout * 2u) : "memory");
+                        const int grow = b0 * p.L + l0 + mt * 128 + q * 32;       // row of the [B*L][Cout] view
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                     ::"l"(reinterpret_cast<uint64_t>(&tmO)), "r"(slab_s), "r"(colbase), "r"(grow) : "memory");
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                 }
@@ -863,7 +866,7 @@ struct TcLevel {
 
 struct TcPlanLevel {
     TcParams p;
-    CUtensorMap tmA, tmW;
+    CUtensorMap tmA, tmW, tmO;
     dim3 grid;
     int threads;
     size_t smem;
@@ -969,6 +972,19 @@ int tc_set_weights(TcState **pst, int n, int ci, const TcBlockSrc *blocks, int n
                                                                           lv.ss, lv.cout, lv.cin0, lv.cin1, lv.k, lv.Npad, lv.Ktot);
         if (cudaGetLastError() != cudaSuccess) return tc_fail("pack_tc_kernel launch failed");
     }
+    return 0;
+}
+
+static int make_map_out(TcState *st, CUtensorMap *m, const void *base, uint64_t cout, uint64_t rows)
+{
+    cuuint64_t gdim[2] = {cout, rows};
+    cuuint64_t gstr[1] = {cout * 2};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    const CUresult r = st->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), gdim, gstr, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return tc_fail("cuTensorMapEncodeTiled(out) failed (%d)", (int)r);
     return 0;
 }
 
@@ -1127,10 +1143,10 @@ static int build_plan(TcState *st, const float *x, float *y, int B, int T, void 
             }
             if (!ok) return tc_fail("level %d does not fit in shared memory", i);
         }
-        if (!packed && base_split == 1 && i != 2 * n && (L % (128 * p.MT) == 0) && p.MT >= (dec ? 1 : 2)) {
-            // staged bulk stores if the slabs fit without giving up ring depth / residency / tile size
-            const int need = p.n_epi * 32 * lv.cout * 2 + 256;
-            const int min_nb = p.resident ? p.nb : (p.tg == 1 ? 4 : 3);
+        if (!packed && base_split == 1 && i != 2 * n && (L % (128 * p.MT) == 0) && (long long)B * L < (1LL << 31)) {
+            // TMA-store epilogue if the slabs fit without giving up ring depth / residency / tile size
+            const int need = p.n_epi * 2048 + 1024;
+            const int min_nb = p.resident ? p.nb : (p.tg == 1 ? 4 : 2);
             while ((int)smem_total(p) + need > (int)kSmemLimit && !p.resident && p.nb > min_nb) --p.nb;
             if ((int)smem_total(p) + need <= (int)kSmemLimit) p.bulk_store = 1;
         }
@@ -1166,6 +1182,8 @@ static int build_plan(TcState *st, const float *x, float *y, int B, int T, void 
             p.Lin = L / 2;
             p.up_scale = (L > 1) ? (float)(p.Lin - 1) / (float)(L - 1) : 0.f;
         }
+        if (p.out != nullptr) { if (make_map_out(st, &P.tmO, p.out, (uint64_t)lv.cout, (uint64_t)B * L)) return -1; }
+        else P.tmO = P.tmA;
         if (make_map(st, &P.tmW, lv.wp, lv.Ktot, lv.Npad, lv.k, (uint64_t)lv.Ktot * 2, (uint64_t)lv.Npad * lv.Ktot * 2, 64,
                      (uint32_t)p.Nh, (uint32_t)p.tg))
             return -1;
@@ -1227,8 +1245,8 @@ int tc_forward(TcState *st, const float *x, float *y, int B, int T, void *ws, cu
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = st->pdl ? 1 : 0;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        if (P.upcat) cudaLaunchKernelEx(&cfg, conv_tc_kernel<5, true>, P.tmA, P.tmW, P.p);
-        else cudaLaunchKernelEx(&cfg, conv_tc_kernel<15, false>, P.tmA, P.tmW, P.p);
+        if (P.upcat) cudaLaunchKernelEx(&cfg, conv_tc_kernel<5, true>, P.tmA, P.tmW, P.tmO, P.p);
+        else cudaLaunchKernelEx(&cfg, conv_tc_kernel<15, false>, P.tmA, P.tmW, P.tmO, P.p);
         const cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return tc_fail("conv_tc level %d launch failed: %s", i, cudaGetErrorString(e));
         ++nl;
