@@ -321,6 +321,15 @@ int wunet_forward_host(wunet_ctx *c, const float *x_host, float *y_host, int B, 
         CUDA_TRY(cudaMalloc(&c->hws, need));
         c->hws_cap = need;
     }
+    if (precision == WUNET_PREC_BF16) {
+        // chunked pipeline: H2D, first/last kernels and D2H overlap per batch chunk (see tc_forward_host)
+        if (!c->have_weights) return fail(WUNET_ESTATE, "wunet_forward_host called before wunet_set_weights");
+        int launches = 0;
+        if (tc_forward_host(c->tc, x_host, y_host, c->hx, c->hy, B, T, c->hws, c->hstream, &launches) != 0)
+            return fail(WUNET_ECUDA, "tcgen05 host pipeline failed: %s", tc_error());
+        c->last_launches = launches;
+        return WUNET_OK;
+    }
     CUDA_TRY(cudaMemcpyAsync(c->hx, x_host, nbytes, cudaMemcpyHostToDevice, c->hstream));
     rc = wunet_forward(c, c->hx, c->hy, B, T, precision, c->hws, c->hws_cap, c->hstream);
     if (rc != WUNET_OK) return rc;

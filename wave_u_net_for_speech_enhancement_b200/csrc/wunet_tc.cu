@@ -212,6 +212,7 @@ struct TcParams {
     // M tiling
     int MT, packed, S, FR, tiles_per_frame;
     int m_tiles, nsplit, nacc; // M tiles in the problem, N halves, accumulator buffers in TMEM
+    int tile_begin, tile_end;  // tiles [begin, end) handled by this launch (sub-ranges = batch chunks of the host pipeline)
     int nops, R1, a_tx_bytes;  // TMA ops per A chunk, rows advanced per op, bytes per chunk
     int rows_used;             // smem rows the producers must fill (upsample path)
     uint32_t a_stage_bytes, b_stage_bytes;
@@ -300,7 +301,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int kFirstProducer = kEpilogueWarps;
     constexpr int kTmaWarp = kEpilogueWarps + (UPCAT ? kProducerWarps : 0);
     constexpr int kMmaWarp = kTmaWarp + 1;
-    const int total_tiles = p.m_tiles * p.nsplit;
+    const int total_tiles = p.tile_end;
+    const int first_tile = p.tile_begin + (int)blockIdx.x;
 
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
@@ -351,7 +353,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int sa = 0, pa = 0, sb = 0, pb = 0;
             int tr0 = 0; (void)tr0;
             // A tiles are issued one chunk ahead of the weight stream (across tile boundaries)
-            int a_tile = blockIdx.x, a_c = 0;
+            int a_tile = first_tile, a_c = 0;
             // returns false if the stage is still in use and blocking == false
             auto issue_a = [&](bool blocking) -> bool {
                 if (a_tile >= total_tiles) return true;
@@ -389,7 +391,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             for (int pre = 0; pre < p.na - 1; ++pre) issue_a(true);          // A tiles run na-1 chunks ahead of the weights
             if (p.na == 1) issue_a(true);
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int tile = first_tile; tile < total_tiles; tile += gridDim.x) {
                 int b0, l0, n0;
                 tile_coords(tile, b0, l0, n0);
                 for (int c = 0; c < p.nchunks; ++c) {
@@ -418,7 +420,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int tr3 = 0; (void)tr3;
             const uint32_t tile_bytes = (uint32_t)p.Nh * 128;
             if (p.resident) { mbar_wait(b_full, 0); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            for (int tile = first_tile; tile < total_tiles; tile += gridDim.x, ++it) {
                 int b0, l0, n0;
                 tile_coords(tile, b0, l0, n0);
                 const int Nthis = min(p.Nh, p.Npad - n0);
@@ -485,7 +487,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const float2 *ss = reinterpret_cast<const float2 *>(base_ptr + sm.ss);
         int it = 0;
         int tr2 = 0; (void)tr2;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        for (int tile = first_tile; tile < total_tiles; tile += gridDim.x, ++it) {
             int b0, l0, n0;
             tile_coords(tile, b0, l0, n0);
             const int Nthis = min(p.Nh, p.Npad - n0);
@@ -659,7 +661,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 *reinterpret_cast<uint4 *>(dst + row * 128 + ((vec ^ (row & 7)) << 4)) = o;
             }
         };
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int tile = first_tile; tile < total_tiles; tile += gridDim.x) {
             int b0, l0, n0;
             tile_coords(tile, b0, l0, n0);
             for (int c = 0; c < p.nchunks; ++c) {
@@ -869,6 +871,7 @@ struct TcPlanLevel {
     CUtensorMap tmA, tmW, tmO;
     dim3 grid;
     int threads;
+    int per_sm;
     size_t smem;
     bool upcat;
 };
@@ -887,6 +890,8 @@ struct TcState {
     bool attr_set = false;
     bool pdl = false;                  // programmatic dependent launch between the blocks (WUNET_TC_PDL=1); measured slower, off
     int num_sms = 148;
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;     // host pipeline: H2D / D2H streams
+    cudaEvent_t ev_in[8] = {}, ev_out[8] = {};
     long long *trace = nullptr;        // development: WUNET_TC_TRACE builds + WUNET_TC_TRACE_LEVEL=<block>
     int trace_level = -1;
     // plan cache, keyed on (workspace pointer, B, T)
@@ -1154,6 +1159,8 @@ static int build_plan(TcState *st, const float *x, float *y, int B, int T, void 
             const int threads = dec ? kThreadsDec : kThreadsEnc;
             const int per_sm = std::max(1, std::min({(int)(kSmemLimit / smem_total(p)), (int)(512 / p.tmem_cols), 2048 / threads}));
             const int total_tiles = p.m_tiles * p.nsplit;
+            p.tile_begin = 0; p.tile_end = total_tiles;
+            P.per_sm = per_sm;
             P.grid = dim3((unsigned)std::min(total_tiles, st->num_sms * per_sm), 1, 1);
             P.threads = threads;
         }
@@ -1200,11 +1207,10 @@ static int build_plan(TcState *st, const float *x, float *y, int B, int T, void 
     return 0;
 }
 
-int tc_forward(TcState *st, const float *x, float *y, int B, int T, void *ws, cudaStream_t stream, int *launches,
-               cudaEvent_t *ev)
+static int tc_prepare(TcState *st, const float *x, float *y, int B, int T, void *ws)
 {
     if (!st) return tc_fail("tensor-core state missing");
-    const int n = st->n, ci = st->ci;
+    const int ci = st->ci;
     if (ci % 8 != 0 || ci > 32) return tc_fail("bf16 tcgen05 path needs channels_interval %% 8 == 0 and <= 32 (got %d)", ci);
     if (!st->attr_set) {
         cudaFuncSetAttribute(conv_tc_kernel<15, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
@@ -1217,42 +1223,116 @@ int tc_forward(TcState *st, const float *x, float *y, int B, int T, void *ws, cu
     }
     if (st->plan_ws != ws || st->plan_B != B || st->plan_T != T || st->plan_x != x || st->plan_y != y)
         if (build_plan(st, x, y, B, T, ws)) return -1;
-    TcPlan &pl = st->plan;
-    char *base = static_cast<char *>(ws);
+    return 0;
+}
+
+// enc0 over frames [f0, f0 + nf)
+static int launch_enc0(TcState *st, const float *x, int f0, int nf, int T, void *ws, cudaStream_t stream)
+{
+    const TcLevel &lv = st->levels[0];
+    const int C = lv.cout;
+    const size_t smem = (size_t)(15 * C + 2 * C + 4 + 1024 + 16) * sizeof(float) + (size_t)1024 * C * 2 + 16;
+    dim3 grid((unsigned)((T + 1023) / 1024), (unsigned)nf, 1);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = st->pdl ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    __nv_bfloat16 *out0 = reinterpret_cast<__nv_bfloat16 *>(static_cast<char *>(ws) + st->plan.off[0]);
+    cudaLaunchKernelEx(&cfg, enc0_kernel, x + (size_t)f0 * T, lv.w_src, lv.scale, lv.shift, out0 + (size_t)f0 * T * C, nf, T, C);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return tc_fail("enc0 launch failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+// conv block i over the tile range [t0, t1) (t1 < 0: all tiles)
+static int launch_block(TcState *st, int i, int t0, int t1, cudaStream_t stream)
+{
+    TcPlanLevel &P = st->plan.lv[i];
+    TcParams p = P.p;
+    if (t1 >= 0) { p.tile_begin = t0; p.tile_end = t1; }
+    const int ntiles = p.tile_end - p.tile_begin;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)std::min(ntiles, st->num_sms * P.per_sm), 1, 1);
+    cfg.blockDim = dim3(P.threads); cfg.dynamicSmemBytes = P.smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = st->pdl ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (P.upcat) cudaLaunchKernelEx(&cfg, conv_tc_kernel<5, true>, P.tmA, P.tmW, P.tmO, p);
+    else cudaLaunchKernelEx(&cfg, conv_tc_kernel<15, false>, P.tmA, P.tmW, P.tmO, p);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return tc_fail("conv_tc level %d launch failed: %s", i, cudaGetErrorString(e));
+    return 0;
+}
+
+int tc_forward(TcState *st, const float *x, float *y, int B, int T, void *ws, cudaStream_t stream, int *launches,
+               cudaEvent_t *ev)
+{
+    if (tc_prepare(st, x, y, B, T, ws)) return -1;
+    const int n = st->n;
     int nl = 0;
     if (ev) cudaEventRecord(ev[0], stream);
-    {   // enc0
-        const TcLevel &lv = st->levels[0];
-        const int C = lv.cout;
-        const size_t smem = (size_t)(15 * C + 2 * C + 4 + 1024 + 16) * sizeof(float) + (size_t)1024 * C * 2 + 16;
-        dim3 grid((unsigned)((T + 1023) / 1024), (unsigned)B, 1);
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = grid; cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = st->pdl ? 1 : 0;
-        cfg.attrs = attr; cfg.numAttrs = 1;
-        cudaLaunchKernelEx(&cfg, enc0_kernel, x, lv.w_src, lv.scale, lv.shift, reinterpret_cast<__nv_bfloat16 *>(base + pl.off[0]), B, T, C);
-        if (cudaGetLastError() != cudaSuccess) return tc_fail("enc0 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-        ++nl;
-        if (ev) cudaEventRecord(ev[1], stream);
-    }
+    if (launch_enc0(st, x, 0, B, T, ws, stream)) return -1;
+    ++nl;
+    if (ev) cudaEventRecord(ev[1], stream);
     for (int i = 1; i < 2 * n + 1; ++i) {
-        TcPlanLevel &P = pl.lv[i];
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = P.grid; cfg.blockDim = dim3(P.threads); cfg.dynamicSmemBytes = P.smem; cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = st->pdl ? 1 : 0;
-        cfg.attrs = attr; cfg.numAttrs = 1;
-        if (P.upcat) cudaLaunchKernelEx(&cfg, conv_tc_kernel<5, true>, P.tmA, P.tmW, P.tmO, P.p);
-        else cudaLaunchKernelEx(&cfg, conv_tc_kernel<15, false>, P.tmA, P.tmW, P.tmO, P.p);
-        const cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) return tc_fail("conv_tc level %d launch failed: %s", i, cudaGetErrorString(e));
+        if (launch_block(st, i, 0, -1, stream)) return -1;
         ++nl;
         if (ev) cudaEventRecord(ev[i + 1], stream);
     }
     if (ev) cudaEventRecord(ev[2 * n + 2], stream);     // head is fused: zero-length segment
+    if (launches) *launches = nl;
+    return 0;
+}
+
+// Host-buffer pipeline (enhancement.py:64-66 form): the first kernel (enc0) and the last (decoder + fused head) run per
+// batch chunk, so the H2D copy of chunk c+1 overlaps enc0 of chunk c and the D2H copy of chunk c overlaps the head of c+1.
+int tc_forward_host(TcState *st, const float *x_host, float *y_host, float *x_dev, float *y_dev, int B, int T, void *ws,
+                    cudaStream_t stream, int *launches)
+{
+    if (tc_prepare(st, x_dev, y_dev, B, T, ws)) return -1;
+    const int n = st->n;
+    const TcParams &pl = st->plan.lv[2 * n].p;
+    int nc = 1;
+    if (!pl.packed && pl.nsplit == 1) { if (B % 4 == 0 && B >= 32) nc = 4; else if (B % 2 == 0 && B >= 8) nc = 2; }
+    if (!st->copy_in) {
+        if (cudaStreamCreateWithFlags(&st->copy_in, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&st->copy_out, cudaStreamNonBlocking) != cudaSuccess)
+            return tc_fail("cudaStreamCreate failed");
+        for (int i = 0; i < 8; ++i) {
+            cudaEventCreateWithFlags(&st->ev_in[i], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&st->ev_out[i], cudaEventDisableTiming);
+        }
+    }
+    const int bc = B / nc;
+    const size_t chunk = (size_t)bc * T;
+    int nl = 0;
+    // the compute stream may still own x_dev/y_dev from an earlier call: order the copies after it
+    cudaEventRecord(st->ev_out[7], stream);
+    cudaStreamWaitEvent(st->copy_in, st->ev_out[7], 0);
+    for (int c = 0; c < nc; ++c) {
+        cudaMemcpyAsync(x_dev + c * chunk, x_host + c * chunk, chunk * sizeof(float), cudaMemcpyHostToDevice, st->copy_in);
+        cudaEventRecord(st->ev_in[c], st->copy_in);
+        cudaStreamWaitEvent(stream, st->ev_in[c], 0);
+        if (launch_enc0(st, x_dev, c * bc, bc, T, ws, stream)) return -1;
+        ++nl;
+    }
+    for (int i = 1; i < 2 * n; ++i) {
+        if (launch_block(st, i, 0, -1, stream)) return -1;
+        ++nl;
+    }
+    const int tiles_per_chunk = (pl.m_tiles * pl.nsplit) / nc;      // non-packed: m_tiles = B * tiles_per_frame
+    for (int c = 0; c < nc; ++c) {
+        if (nc == 1) { if (launch_block(st, 2 * n, 0, -1, stream)) return -1; }
+        else if (launch_block(st, 2 * n, c * tiles_per_chunk, (c + 1) * tiles_per_chunk, stream)) return -1;
+        ++nl;
+        cudaEventRecord(st->ev_out[c], stream);
+        cudaStreamWaitEvent(st->copy_out, st->ev_out[c], 0);
+        cudaMemcpyAsync(y_host + c * chunk, y_dev + c * chunk, chunk * sizeof(float), cudaMemcpyDeviceToHost, st->copy_out);
+    }
+    if (cudaStreamSynchronize(st->copy_out) != cudaSuccess) return tc_fail("host pipeline failed: %s", cudaGetErrorString(cudaGetLastError()));
     if (launches) *launches = nl;
     return 0;
 }
@@ -1277,6 +1357,10 @@ int tc_read_level(TcState *st, int block, const void *ws, int B, int T, float *o
 void tc_destroy(TcState *st)
 {
     if (!st) return;
+    if (st->copy_in) {
+        cudaStreamDestroy(st->copy_in); cudaStreamDestroy(st->copy_out);
+        for (int i = 0; i < 8; ++i) { cudaEventDestroy(st->ev_in[i]); cudaEventDestroy(st->ev_out[i]); }
+    }
     if (st->trace) {
         std::vector<long long> h(4 * 512);
         cudaDeviceSynchronize();

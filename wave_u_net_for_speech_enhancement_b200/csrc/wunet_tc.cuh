@@ -23,6 +23,9 @@ size_t tc_workspace_bytes(int n_layers, int ci, int B, int T);
 // events: null, or 2n+3 events: [0] before the first kernel, [i+1] after block i, [2n+2] after the head
 int tc_forward(TcState *st, const float *x, float *y, int B, int T, void *ws, cudaStream_t stream, int *launches,
                cudaEvent_t *events);
+// host-buffer form: x_host/y_host (pinned for full rate), x_dev/y_dev = device staging buffers of B*T floats
+int tc_forward_host(TcState *st, const float *x_host, float *y_host, float *x_dev, float *y_dev, int B, int T, void *ws,
+                    cudaStream_t stream, int *launches);
 int tc_read_level(TcState *st, int block, const void *ws, int B, int T, float *out_ncl, cudaStream_t stream);
 void tc_destroy(TcState *st);
 
