@@ -328,21 +328,33 @@ def main():
                  "net_frac": round(sum(l["roof_ms"] for l in levels) / sum(l["ms"] for l in levels), 4),
                  "sum_levels_ms": round(float(sum(blk_ms)), 4)})
 
-    # ---- end to end: public API with HOST buffers (pinned), H2D + kernels + D2H inside the timed region ----
-    xh = [torch.from_numpy(wo.make_input(B, T, seed=99 + i)).pin_memory() for i in range(2)]
-    yh = torch.empty_like(xh[0]).pin_memory()
+    # ---- end to end: public API with HOST buffers (pinned); every step copies ITS inputs H2D and ITS result D2H inside
+    # the timed region. (a) streaming API Model.forward_host_stream: two batches in flight, so the copies of step k+1 / k-1
+    # overlap the kernels of step k (the way enhancement.py's many chunks are served); (b) one synchronous forward_host per step.
+    NH = 4
+    xh = [torch.from_numpy(wo.make_input(B, T, seed=99 + i)).pin_memory() for i in range(NH)]
+    yh = [torch.empty_like(xh[0]).pin_memory() for _ in range(NH)]
     for i in range(2):
-        model.forward_host(xh[i % 2], out=yh)
+        model.forward_host(xh[i % NH], out=yh[i % NH])
+    for _ in model.forward_host_stream([xh[i % NH] for i in range(3)], [yh[i % NH] for i in range(3)]):
+        pass
+    barrier()
+    t0 = time.perf_counter()
+    for _ in model.forward_host_stream((xh[i % NH] for i in range(args.steps)), (yh[i % NH] for i in range(args.steps))):
+        pass
+    torch.cuda.synchronize()
+    dt_stream = time.perf_counter() - t0
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
-        model.forward_host(xh[i % 2], out=yh)
+        model.forward_host(xh[i % NH], out=yh[i % NH])
     torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    t = torch.tensor([dt], device=dev)
+    dt_sync = time.perf_counter() - t0
+    t = torch.tensor([dt_stream, dt_sync], device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_val = B * world * args.steps / float(t.item())
+    e2e_val = B * world * args.steps / float(t[0].item())
+    e2e_sync = B * world * args.steps / float(t[1].item())
     nbytes = B * T * 4
 
     if rank != 0:
@@ -366,7 +378,9 @@ def main():
                          f"{sum(b for _n, _f, b in tab) / 2**30:.2f} GiB >> 126 MB L2"},
         "clocks": clocks,
         "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
-                "api": "Model.forward_host -> wunet_forward_host (pinned host buffers)"},
+                "api": "Model.forward_host_stream -> wunet_stream_submit/wait: pinned host buffers in and out every step, "
+                       "two batches in flight",
+                "sync_value": e2e_sync, "sync_api": "Model.forward_host -> wunet_forward_host (one blocking call per step)"},
         "gpu_launches": launches_per_step * args.steps,
         "roofline": roof,
         "levels": levels,

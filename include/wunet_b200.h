@@ -96,6 +96,17 @@ int wunet_forward(wunet_ctx *ctx, const float *x_dev, float *y_dev, int B, int T
 int wunet_forward_host(wunet_ctx *ctx, const float *x_host, float *y_host, int B, int T, int precision);
 
 /*
+ * Streaming form of the same operator for MANY batches — what enhancement.py:49-74 / trainer/trainer.py:58-79 do when they
+ * push every 16384-sample chunk of every clip through the model. wunet_stream_submit() enqueues batch k and returns at once:
+ * the H2D copy (copy stream, one of two device slots), the kernels (compute stream) and the D2H copy (second copy stream)
+ * of consecutive batches overlap. wunet_stream_wait(ticket) blocks until that batch's y_host is complete. At most two
+ * batches are in flight: submitting a third waits for the first. Host buffers should be pinned and must stay valid until
+ * the ticket has been waited for.
+ */
+int wunet_stream_submit(wunet_ctx *ctx, const float *x_host, float *y_host, int B, int T, int precision, int *ticket);
+int wunet_stream_wait(wunet_ctx *ctx, int ticket);
+
+/*
  * Test/diagnostic hook: copy the full-resolution output of block `block` from the workspace of the
  * LAST wunet_forward() call (same ctx, same workspace, B, T, precision) to out_dev as fp32
  * [B,Cout,L] (the reference's NCL layout) — what a forward hook on encoder[i] / middle /

@@ -41,6 +41,8 @@ def load() -> ctypes.CDLL:
     lib.wunet_workspace_bytes.restype = cs
     lib.wunet_forward.argtypes = [vp, vp, vp, ci, ci, ci, vp, cs, vp]
     lib.wunet_forward_host.argtypes = [vp, vp, vp, ci, ci, ci]
+    lib.wunet_stream_submit.argtypes = [vp, vp, vp, ci, ci, ci, ctypes.POINTER(ci)]
+    lib.wunet_stream_wait.argtypes = [vp, ci]
     lib.wunet_read_level.argtypes = [vp, ci, vp, ci, ci, ci, vp, vp]
     lib.wunet_last_launch_count.argtypes = [vp]
     lib.wunet_profile_enable.argtypes = [vp, ci]
@@ -56,6 +58,6 @@ def check(rc: int) -> None:
 
 EXPORTED_SYMBOLS = [
     "wunet_version", "wunet_last_error", "wunet_create", "wunet_destroy", "wunet_num_blocks", "wunet_block_shape",
-    "wunet_set_weights", "wunet_workspace_bytes", "wunet_forward", "wunet_forward_host", "wunet_read_level",
+    "wunet_set_weights", "wunet_workspace_bytes", "wunet_forward", "wunet_forward_host", "wunet_stream_submit", "wunet_stream_wait", "wunet_read_level",
     "wunet_last_launch_count", "wunet_profile_enable", "wunet_profile_read",
 ]

@@ -57,6 +57,13 @@ struct wunet_ctx {
     size_t hx_cap = 0;
     void *hws = nullptr;
     size_t hws_cap = 0;
+    // streaming (double-buffered) host pipeline
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    float *sx[2] = {nullptr, nullptr}, *sy[2] = {nullptr, nullptr};
+    size_t s_cap = 0;
+    cudaEvent_t e_in[2] = {}, e_comp[2] = {}, e_done[2] = {};
+    bool slot_busy[2] = {false, false};
+    int next_ticket = 0;
 };
 
 namespace {
@@ -204,6 +211,10 @@ void wunet_destroy(wunet_ctx *c)
     for (auto e : c->ev) cudaEventDestroy(e);
     if (c->hstream) cudaStreamDestroy(c->hstream);
     cudaFree(c->hx); cudaFree(c->hy); cudaFree(c->hws);
+    if (c->s_in) {
+        cudaStreamDestroy(c->s_in); cudaStreamDestroy(c->s_out);
+        for (int i = 0; i < 2; ++i) { cudaEventDestroy(c->e_in[i]); cudaEventDestroy(c->e_comp[i]); cudaEventDestroy(c->e_done[i]); cudaFree(c->sx[i]); cudaFree(c->sy[i]); }
+    }
     cudaSetDevice(prev);
     delete c;
 }
@@ -335,6 +346,73 @@ int wunet_forward_host(wunet_ctx *c, const float *x_host, float *y_host, int B, 
     if (rc != WUNET_OK) return rc;
     CUDA_TRY(cudaMemcpyAsync(y_host, c->hy, nbytes, cudaMemcpyDeviceToHost, c->hstream));
     CUDA_TRY(cudaStreamSynchronize(c->hstream));
+    return WUNET_OK;
+}
+
+int wunet_stream_submit(wunet_ctx *c, const float *x_host, float *y_host, int B, int T, int precision, int *ticket)
+{
+    int rc = check_shape(c, B, T);
+    if (rc != WUNET_OK) return rc;
+    if (!x_host || !y_host || !ticket) return fail(WUNET_EINVAL, "null argument");
+    if (!c->have_weights) return fail(WUNET_ESTATE, "wunet_stream_submit called before wunet_set_weights");
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (!c->hstream) CUDA_TRY(cudaStreamCreateWithFlags(&c->hstream, cudaStreamNonBlocking));
+    if (!c->s_in) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CUDA_TRY(cudaEventCreateWithFlags(&c->e_in[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&c->e_comp[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&c->e_done[i], cudaEventDisableTiming));
+        }
+    }
+    const size_t nbytes = (size_t)B * T * sizeof(float);
+    const int k = c->next_ticket;
+    const int slot = k & 1;
+    if (c->slot_busy[slot]) { CUDA_TRY(cudaEventSynchronize(c->e_done[slot])); c->slot_busy[slot] = false; }
+    if (c->s_cap < nbytes) {
+        for (int i = 0; i < 2; ++i) {
+            if (c->slot_busy[i]) { CUDA_TRY(cudaEventSynchronize(c->e_done[i])); c->slot_busy[i] = false; }
+            cudaFree(c->sx[i]); cudaFree(c->sy[i]); c->sx[i] = c->sy[i] = nullptr;
+        }
+        c->s_cap = 0;
+        for (int i = 0; i < 2; ++i) { CUDA_TRY(cudaMalloc(&c->sx[i], nbytes)); CUDA_TRY(cudaMalloc(&c->sy[i], nbytes)); }
+        c->s_cap = nbytes;
+    }
+    const size_t need = wunet_workspace_bytes(c, B, T, precision);
+    if (need == 0) return WUNET_EINVAL;
+    if (c->hws_cap < need) {
+        CUDA_TRY(cudaStreamSynchronize(c->hstream));
+        cudaFree(c->hws);
+        c->hws = nullptr; c->hws_cap = 0;
+        CUDA_TRY(cudaMalloc(&c->hws, need));
+        c->hws_cap = need;
+    }
+    // slot reuse: x_dev[slot] was last read by the forward of ticket k-2 (e_comp), y_dev[slot] by its D2H (e_done, waited above)
+    if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(c->s_in, c->e_comp[slot], 0));
+    CUDA_TRY(cudaMemcpyAsync(c->sx[slot], x_host, nbytes, cudaMemcpyHostToDevice, c->s_in));
+    CUDA_TRY(cudaEventRecord(c->e_in[slot], c->s_in));
+    CUDA_TRY(cudaStreamWaitEvent(c->hstream, c->e_in[slot], 0));
+    rc = wunet_forward(c, c->sx[slot], c->sy[slot], B, T, precision, c->hws, c->hws_cap, c->hstream);
+    if (rc != WUNET_OK) return rc;
+    CUDA_TRY(cudaEventRecord(c->e_comp[slot], c->hstream));
+    CUDA_TRY(cudaStreamWaitEvent(c->s_out, c->e_comp[slot], 0));
+    CUDA_TRY(cudaMemcpyAsync(y_host, c->sy[slot], nbytes, cudaMemcpyDeviceToHost, c->s_out));
+    CUDA_TRY(cudaEventRecord(c->e_done[slot], c->s_out));
+    c->slot_busy[slot] = true;
+    *ticket = k;
+    c->next_ticket = k + 1;
+    return WUNET_OK;
+}
+
+int wunet_stream_wait(wunet_ctx *c, int ticket)
+{
+    if (!c) return fail(WUNET_EINVAL, "null context");
+    if (ticket < 0 || ticket >= c->next_ticket) return fail(WUNET_EINVAL, "unknown ticket %d", ticket);
+    if (ticket < c->next_ticket - 2) return WUNET_OK;            // older tickets were completed when their slot was reused
+    const int slot = ticket & 1;
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (c->slot_busy[slot]) { CUDA_TRY(cudaEventSynchronize(c->e_done[slot])); c->slot_busy[slot] = false; }
     return WUNET_OK;
 }
 

@@ -1221,8 +1221,9 @@ static int tc_prepare(TcState *st, const float *x, float *y, int B, int T, void 
             st->num_sms = sms;
         st->attr_set = true;
     }
-    if (st->plan_ws != ws || st->plan_B != B || st->plan_T != T || st->plan_x != x || st->plan_y != y)
-        if (build_plan(st, x, y, B, T, ws)) return -1;
+    (void)x; (void)y;
+    if (st->plan_ws != ws || st->plan_B != B || st->plan_T != T)
+        if (build_plan(st, nullptr, nullptr, B, T, ws)) return -1;
     return 0;
 }
 
@@ -1247,10 +1248,11 @@ static int launch_enc0(TcState *st, const float *x, int f0, int nf, int T, void 
 }
 
 // conv block i over the tile range [t0, t1) (t1 < 0: all tiles)
-static int launch_block(TcState *st, int i, int t0, int t1, cudaStream_t stream)
+static int launch_block(TcState *st, int i, int t0, int t1, cudaStream_t stream, const float *x = nullptr, float *y = nullptr)
 {
     TcPlanLevel &P = st->plan.lv[i];
     TcParams p = P.p;
+    p.x = x; p.y = y;                                    // only the fused head (last block) reads x / writes y
     if (t1 >= 0) { p.tile_begin = t0; p.tile_end = t1; }
     const int ntiles = p.tile_end - p.tile_begin;
     cudaLaunchConfig_t cfg{};
@@ -1278,7 +1280,7 @@ int tc_forward(TcState *st, const float *x, float *y, int B, int T, void *ws, cu
     ++nl;
     if (ev) cudaEventRecord(ev[1], stream);
     for (int i = 1; i < 2 * n + 1; ++i) {
-        if (launch_block(st, i, 0, -1, stream)) return -1;
+        if (launch_block(st, i, 0, -1, stream, x, y)) return -1;
         ++nl;
         if (ev) cudaEventRecord(ev[i + 1], stream);
     }
@@ -1325,8 +1327,8 @@ int tc_forward_host(TcState *st, const float *x_host, float *y_host, float *x_de
     }
     const int tiles_per_chunk = (pl.m_tiles * pl.nsplit) / nc;      // non-packed: m_tiles = B * tiles_per_frame
     for (int c = 0; c < nc; ++c) {
-        if (nc == 1) { if (launch_block(st, 2 * n, 0, -1, stream)) return -1; }
-        else if (launch_block(st, 2 * n, c * tiles_per_chunk, (c + 1) * tiles_per_chunk, stream)) return -1;
+        if (nc == 1) { if (launch_block(st, 2 * n, 0, -1, stream, x_dev, y_dev)) return -1; }
+        else if (launch_block(st, 2 * n, c * tiles_per_chunk, (c + 1) * tiles_per_chunk, stream, x_dev, y_dev)) return -1;
         ++nl;
         cudaEventRecord(st->ev_out[c], stream);
         cudaStreamWaitEvent(st->copy_out, st->ev_out[c], 0);

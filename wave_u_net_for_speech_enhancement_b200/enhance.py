@@ -1,0 +1,77 @@
+"""
+Chunk batching for inference: the reference's ``enhancement.py:49-74`` (and the validation loop,
+``trainer/trainer.py:58-79``) zero-pads every clip to a multiple of ``sample_length``, splits it into 16384-sample chunks
+and pushes them through the model ONE chunk at a time with a device→host sync each. Chunks are independent in eval mode,
+so this module stacks the chunks of many clips on the batch axis and streams the batches through
+``Model.forward_host_stream`` (H2D copy / kernels / D2H copy of consecutive batches overlap), then re-assembles and trims
+every clip exactly like the reference loop does (``enhancement.py:68-71``).
+"""
+from __future__ import annotations
+
+from typing import Callable, Iterable, List, Sequence, Tuple
+
+import numpy as np
+import torch
+
+
+def frame_clips(waveforms: Sequence[np.ndarray], sample_length: int = 16384, pin: bool = True
+                ) -> Tuple[torch.Tensor, List[Tuple[int, int, int]]]:
+    """Zero-pad each 1-D waveform to a multiple of ``sample_length`` (enhancement.py:57-59) and split it into chunks
+    (enhancement.py:62). Returns the stacked chunks ``[N,1,sample_length]`` (float32, pinned if requested) and, per clip,
+    ``(first_frame, n_frames, original_length)``."""
+    index, total = [], 0
+    for w in waveforms:
+        n = int(np.asarray(w).shape[-1])
+        if np.asarray(w).ndim != 1:
+            raise ValueError("waveforms must be 1-D")
+        nf = max(1, -(-n // sample_length))
+        index.append((total, nf, n))
+        total += nf
+    frames = torch.zeros(total, 1, sample_length, dtype=torch.float32)
+    if pin and torch.cuda.is_available():
+        frames = frames.pin_memory()
+    flat = frames.view(total, sample_length)
+    for (f0, nf, n), w in zip(index, waveforms):
+        dst = flat[f0:f0 + nf].reshape(-1)
+        dst[:n] = torch.from_numpy(np.ascontiguousarray(w, dtype=np.float32))
+    return frames, index
+
+
+def unframe_clips(frames: torch.Tensor, index: List[Tuple[int, int, int]]) -> List[np.ndarray]:
+    """Concatenate each clip's chunks and drop the padding (enhancement.py:68-71)."""
+    flat = frames.view(frames.shape[0], frames.shape[-1])
+    return [flat[f0:f0 + nf].reshape(-1)[:n].numpy().copy() for (f0, nf, n) in index]
+
+
+def enhance_waveforms(model, waveforms: Sequence[np.ndarray], sample_length: int = 16384, batch_frames: int = 256,
+                      stream_fn: Callable[[Iterable[torch.Tensor], Iterable[torch.Tensor]], Iterable[torch.Tensor]] = None
+                      ) -> List[np.ndarray]:
+    """Enhance a list of 1-D float32 waveforms; returns the enhanced waveforms (same lengths).
+
+    ``model`` is a ``wave_u_net_for_speech_enhancement_b200.Model`` on a CUDA device in eval mode. ``stream_fn`` (tests
+    only) replaces ``model.forward_host_stream``."""
+    frames, index = frame_clips(waveforms, sample_length)
+    total = frames.shape[0]
+    out = torch.empty_like(frames)
+    if frames.is_pinned():
+        out = out.pin_memory()
+    B = min(batch_frames, total)
+    nfull, rem = divmod(total, B)
+    batches = [frames[i * B:(i + 1) * B] for i in range(nfull)]
+    outs = [out[i * B:(i + 1) * B] for i in range(nfull)]
+    tail_in = tail_out = None
+    if rem:
+        # keep the batch size constant (one plan / workspace): the last batch is filled up with silent frames
+        tail_in = torch.zeros(B, 1, sample_length, dtype=torch.float32)
+        tail_out = torch.empty_like(tail_in)
+        if frames.is_pinned():
+            tail_in, tail_out = tail_in.pin_memory(), tail_out.pin_memory()
+        tail_in[:rem] = frames[nfull * B:]
+        batches.append(tail_in)
+        outs.append(tail_out)
+    fn = stream_fn if stream_fn is not None else model.forward_host_stream
+    for _ in fn(batches, outs):
+        pass
+    if rem:
+        out[nfull * B:] = tail_out[:rem]
+    return unframe_clips(out, index)

@@ -248,6 +248,44 @@ class Model(nn.Module):
         return out
 
     @torch.no_grad()
+    def forward_host_stream(self, batches, outs=None):
+        """Streaming form of :meth:`forward_host` for many host batches (every chunk of every clip, enhancement.py:49-74):
+        yields one output tensor per input batch, in order; H2D copy, kernels and D2H copy of consecutive batches overlap
+        (two batches in flight). ``batches``: iterable of pinned ``[B,1,T]`` float32 host tensors that must stay alive until
+        their result has been yielded; ``outs``: optional iterable of pinned output tensors."""
+        if self.training:
+            raise NotImplementedError("forward_host_stream is eval-only")
+        device = self.out[0].weight.device
+        if device.type != "cuda":
+            raise RuntimeError("no CPU fallback: move the model to a CUDA device first")
+        lib = _lib.load()
+        prec = _lib.PRECISIONS[self.precision]
+        outs_it = iter(outs) if outs is not None else None
+        pending = []                                   # (ticket, x, out)
+        with torch.cuda.device(device):
+            ctx = self._context(device)
+            self._sync_weights(ctx, device)
+            torch.cuda.current_stream(device).synchronize()        # packing ran on torch's stream
+            for x in batches:
+                self._check_input(x)
+                if x.is_cuda:
+                    raise RuntimeError("forward_host_stream takes host tensors")
+                x = x.contiguous()
+                out = next(outs_it) if outs_it is not None else torch.empty_like(x, pin_memory=x.is_pinned())
+                B, _, T = x.shape
+                ticket = ctypes.c_int(0)
+                _lib.check(lib.wunet_stream_submit(ctx, x.data_ptr(), out.data_ptr(), B, T, prec, ctypes.byref(ticket)))
+                pending.append((ticket.value, x, out))
+                if len(pending) == 2:
+                    t, _x, o = pending.pop(0)
+                    _lib.check(lib.wunet_stream_wait(ctx, t))
+                    yield o
+            while pending:
+                t, _x, o = pending.pop(0)
+                _lib.check(lib.wunet_stream_wait(ctx, t))
+                yield o
+
+    @torch.no_grad()
     def read_level(self, block: int, B: int, T: int) -> torch.Tensor:
         """Diagnostic: full-resolution output of block ``block`` (0..2n: encoder i / middle / decoder j)
         of the LAST native forward with this (B, T), as fp32 [B, Cout, L] — what a forward hook on the
