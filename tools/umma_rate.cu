@@ -24,7 +24,7 @@ __device__ __forceinline__ bool elect_one() {
 }
 // mode 0: SW128 (row 128 B, K slice kk at +32kk)          mode 1: SW64 (row 64 B; two sub-tiles of K=32)
 // mode 2: SW32  (row 32 B; four sub-tiles of K=16)         mode 3: INTERLEAVE (plane per 16 B chunk)
-extern "C" __global__ void __launch_bounds__(128) rate_kernel(const __grid_constant__ CUtensorMap tmap, long long *out, int mode, int N, int nmma, int ROWS, int tma_boxes, int ld_traffic)
+extern "C" __global__ void __launch_bounds__(256) rate_kernel(const __grid_constant__ CUtensorMap tmap, long long *out, int mode, int N, int nmma, int ROWS, int tma_boxes, int ld_traffic, int warp_mask)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -34,7 +34,7 @@ extern "C" __global__ void __launch_bounds__(128) rate_kernel(const __grid_const
     __shared__ uint32_t tmem_slot;
     const int warp = threadIdx.x >> 5;
     const uint32_t a_bytes = (uint32_t)ROWS * 128, b_bytes = 256 * 128;
-    for (uint32_t i = threadIdx.x; i < (a_bytes + b_bytes) / 4; i += 128) {
+    for (uint32_t i = threadIdx.x; i < (a_bytes + b_bytes) / 4; i += 256) {
         uint32_t h = (i + blockIdx.x * 7919u) * 2654435761u; h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
         // random bf16 pairs in (-2,2): sign + exponent 126..128 + random mantissa
         const uint32_t r = (h & 0x807F807Fu) | 0x3F003F00u;
@@ -69,7 +69,38 @@ extern "C" __global__ void __launch_bounds__(128) rate_kernel(const __grid_const
             ph ^= 1;
         }
     }
-    if ((warp == 0 || warp == 3) && ld_traffic) {
+    const bool traffic_warp = warp != 1 && ((warp_mask >> warp) & 1);
+    if (traffic_warp && (ld_traffic & 16)) {
+        // ALU-heavy epilogue-like loop (FMA + selects + packs), no memory
+        float a = threadIdx.x * 0.001f, b2 = 1.0001f, c2 = 0.5f; uint32_t acc = 0;
+        while (!stop_flag) {
+#pragma unroll
+            for (int g = 0; g < 64; ++g) { a = fmaf(a, b2, c2); a = a >= 0.f ? a : 0.1f * a; acc += __float_as_uint(a) >> 16; }
+        }
+        if (acc == 0x12345u) out[1] = 0;
+    }
+    if (traffic_warp && (ld_traffic & 4)) {
+        // epilogue-like scattered 16-byte stores: lane r writes row r (96 B pitch), 6 chunks per row
+        uint4 val = make_uint4(threadIdx.x, 1, 2, 3);
+        char *gb = reinterpret_cast<char *>(out) + 4096 + (size_t)(blockIdx.x * 4 + warp) * (1 << 20);
+        uint32_t it = 0;
+        while (!stop_flag) {
+            char *rowp = gb + ((it & 255) * 32 + (threadIdx.x & 31)) * 96;
+#pragma unroll
+            for (int g = 0; g < 6; ++g) *reinterpret_cast<uint4 *>(rowp + g * 16) = val;
+            ++it;
+        }
+    }
+    if (traffic_warp && (ld_traffic & 8)) {
+        float acc = 0.f; uint32_t it = 0;
+        while (!stop_flag) {
+#pragma unroll
+            for (int g = 0; g < 16; ++g) { float4 v; asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(smem) + (((it + g) & 63) * 16))); acc += v.x + v.w; }
+            ++it;
+        }
+        if (acc == 1.2345f) out[1] = 0;
+    }
+    if ((warp == 0 || warp == 3) && (ld_traffic & 1)) {
         uint32_t v[32]; uint32_t sink = 0;
         while (!stop_flag) {
             const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + 384;
@@ -157,7 +188,7 @@ extern "C" __global__ void __launch_bounds__(128) rate_kernel(const __grid_const
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 int main() {
-    long long *d; CK(cudaMalloc(&d, 16));
+    long long *d; CK(cudaMalloc(&d, (size_t)8 << 20));
     const int ROWS = 288;
     const int smem = ROWS * 128 + 256 * 128 + 176 * 128 + 2048;
     CK(cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -178,17 +209,26 @@ int main() {
                                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { printf("encode failed %d\n", (int)r); return 3; }
     }
-    for (int grid : {1, 148})
-        for (int rnd : {0, 2})
-            for (int N : {32, 48, 96, 128}) {
-                long long h[2];
-                for (int rep = 0; rep < 3; ++rep) {
-                    rate_kernel<<<grid, 128, smem>>>(maps[0], d, 4, N, 1920, ROWS, 0, rnd);
-                    cudaError_t e = cudaDeviceSynchronize();
-                    if (e != cudaSuccess) { printf("N=%d: CUDA error %s\n", N, cudaGetErrorString(e)); return 2; }
-                    CK(cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost));
-                }
-                printf("grid=%3d data=%-8s N=%3d  %6.1f cyc/MMA\n", grid, rnd ? "random" : "constant", N, h[1] / 1920.0);
+    struct Cfg { const char *name; int flags; int mask; } cfgs[] = {
+        {"quiet", 0, 0},
+        {"ALU loop on warps 0,2,3 (other SMSPs)", 16, 0b00001101},
+        {"ALU loop on warp 5 (same SMSP)", 16, 0b00100000},
+        {"ALU loop on warps 5,9->(5 only;8 warps)", 16, 0b00100000},
+        {"ALU loop on warps 4-7 (one per SMSP)", 16, 0b11110000},
+        {"LDS loop on warp 5 (same SMSP)", 8, 0b00100000},
+        {"STG loop on warp 5 (same SMSP)", 4, 0b00100000},
+        {"ALU+LDS+STG on warps 4-7", 28, 0b11110000},
+    };
+    for (auto &c : cfgs)
+        for (int N : {32, 48, 128}) {
+            long long h[2];
+            for (int rep = 0; rep < 2; ++rep) {
+                rate_kernel<<<1, 256, smem>>>(maps[0], d, 4, N, 1920, ROWS, 0, c.flags, c.mask);
+                cudaError_t e = cudaDeviceSynchronize();
+                if (e != cudaSuccess) { printf("N=%d: CUDA error %s\n", N, cudaGetErrorString(e)); return 2; }
+                CK(cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost));
             }
+            printf("%-42s N=%3d  %6.1f cyc/MMA\n", c.name, N, h[1] / 1920.0);
+        }
     return 0;
 }

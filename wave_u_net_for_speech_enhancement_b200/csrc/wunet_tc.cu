@@ -144,28 +144,29 @@ __device__ __forceinline__ void umma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, u
         ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate) : "memory");
 }
 // all MMAs of one tap: MT sub-tiles x NK K-steps. a_lo/b_lo are descriptor low words (16-byte units).
-template <int NK, int MT>
-__device__ __forceinline__ void issue_tap(uint32_t d_col, uint32_t nstride, uint32_t a_lo, uint32_t b_lo, uint32_t hi,
-                                          uint32_t idesc, uint32_t acc_first)
+// all MMAs of one tap: MT sub-tiles x nk K-steps. a_lo / b_lo are descriptor low words (16-byte units). Deliberately a
+// small rolled loop: the kernel's instruction footprint must stay cache-resident next to the epilogue / producer code.
+__device__ __forceinline__ void issue_tap(uint32_t d_col, int MT, uint32_t nstride, int nk, uint32_t a_lo, uint32_t b_lo,
+                                          uint32_t hi, uint32_t idesc, uint32_t acc_first)
 {
-#pragma unroll
+#pragma unroll 1
     for (int mt = 0; mt < MT; ++mt) {
-#pragma unroll
-        for (int kk = 0; kk < NK; ++kk)
-            umma_bf16_lohi(d_col + mt * nstride, a_lo + mt * (128 * 8) + 2 * kk, b_lo + 2 * kk, hi, idesc,
-                           kk == 0 ? acc_first : 1u);   // next 128-row sub-tile: +128 rows x 128 B = 1024 sixteen-byte units
+        umma_bf16_lohi(d_col, a_lo, b_lo, hi, idesc, acc_first);
+        if (nk > 1) umma_bf16_lohi(d_col, a_lo + 2, b_lo + 2, hi, idesc, 1u);
+        if (nk > 2) umma_bf16_lohi(d_col, a_lo + 4, b_lo + 4, hi, idesc, 1u);
+        if (nk > 3) umma_bf16_lohi(d_col, a_lo + 6, b_lo + 6, hi, idesc, 1u);
+        d_col += nstride;
+        a_lo += 128 * 8;                          // next 128-row sub-tile: 128 rows x 128 B = 1024 sixteen-byte units
     }
 }
-template <int MT>
-__device__ __forceinline__ void issue_tap_nk(int nk, uint32_t d_col, uint32_t nstride, uint32_t a_lo, uint32_t b_lo, uint32_t hi,
-                                             uint32_t idesc, uint32_t acc_first)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16])
 {
-    switch (nk) {
-        case 4: issue_tap<4, MT>(d_col, nstride, a_lo, b_lo, hi, idesc, acc_first); break;
-        case 3: issue_tap<3, MT>(d_col, nstride, a_lo, b_lo, hi, idesc, acc_first); break;
-        case 2: issue_tap<2, MT>(d_col, nstride, a_lo, b_lo, hi, idesc, acc_first); break;
-        default: issue_tap<1, MT>(d_col, nstride, a_lo, b_lo, hi, idesc, acc_first); break;
-    }
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
 {
@@ -457,12 +458,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             uint32_t b_lo = ((b_base >> 4) & 0x3FFFu) | (1u << 16);
                             a_lo += (uint32_t)(g * p.tg) * 8;                      // tap shift: +128 B per tap
                             const uint32_t b_step = tile_bytes >> 4;
+#pragma unroll 1
                             for (int t = g * p.tg; t < t_end; ++t) {
                                 TRACE(3, tr3);
                                 const uint32_t accf = (c | t) ? 1u : 0u;
-                                if (p.MT == 4) issue_tap_nk<4>(nk, acc_col, p.Nstride, a_lo, b_lo, hi, idesc, accf);
-                                else if (p.MT == 2) issue_tap_nk<2>(nk, acc_col, p.Nstride, a_lo, b_lo, hi, idesc, accf);
-                                else issue_tap_nk<1>(nk, acc_col, p.Nstride, a_lo, b_lo, hi, idesc, accf);
+                                issue_tap(acc_col, p.MT, p.Nstride, nk, a_lo, b_lo, hi, idesc, accf);
                                 a_lo += 8;
                                 b_lo += b_step;
                             }
@@ -509,92 +509,78 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (warp == 0 && lane == 0) TRACE(2, tr2);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t acc_col = buf * p.MT * p.Nstride;
-            // work items (mt, cc) are dealt round-robin to the warps sharing a quadrant
-            if (p.bulk_store) {
-                // Every [32 rows x 32 channels] chunk is staged in this warp's 2 KB slab (64-byte rows, SWIZZLE_64B so the
-                // 16-byte row writes are bank-conflict free) and leaves through one 2-D TMA store. Direct 16-byte row stores
-                // would cost 32 L1 wavefronts per instruction on the pipe the MMA operand reads share.
-                uint8_t *slab = base_ptr + sm.stg + (uint32_t)warp * 2048u;
-                const uint32_t slab_s = smem_u32(slab);
-                uint8_t *srow = slab + lane * 64;
-                const int sw = (lane >> 1) & 3;
-                int turn = 0;
-                for (int mt = 0; mt < p.MT; ++mt)
-                for (int cc = 0; cc < ncc; ++cc) {
-                    if (NSHARE > 1) { const bool mine = (turn == half); turn = (turn + 1 == NSHARE) ? 0 : turn + 1; if (!mine) continue; }
-                    uint32_t v[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc_col + (uint32_t)(mt * p.Nstride + cc * 32), v);
-                    const int colbase = cc * 32;
-                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // slab free again?
-                    __syncwarp();
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        if (colbase + g * 8 < p.Cout) {
-                            float f[8];
-#pragma unroll
-                            for (int j = 0; j < 8; j += 2) {
-                                const float4 s2 = *reinterpret_cast<const float4 *>(&ss[colbase + g * 8 + j]);
-                                f[j] = lrelu(fmaf(__uint_as_float(v[g * 8 + j]), s2.x, s2.y));
-                                f[j + 1] = lrelu(fmaf(__uint_as_float(v[g * 8 + j + 1]), s2.z, s2.w));
-                            }
-                            *reinterpret_cast<uint4 *>(srow + ((g ^ sw) << 4)) =
-                                make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
-                        }
-                    }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) {
-                        const int grow = b0 * p.L + l0 + mt * 128 + q * 32;       // row of the [B*L][Cout] view
-                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                                     ::"l"(reinterpret_cast<uint64_t>(&tmO)), "r"(slab_s), "r"(colbase), "r"(grow) : "memory");
-                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    }
-                }
-            } else {
+            // Work items (mt, 32-column chunk) are dealt round-robin to the warps sharing a quadrant. One rolled code path
+            // serves the three store flavours (TMA-store slab, direct row stores, fused head): 16 accumulator columns are
+            // read per tcgen05.ld, converted 8 at a time.
+            uint8_t *slab = base_ptr + sm.stg + (uint32_t)warp * 2048u;
+            const uint32_t slab_s = smem_u32(slab);
+            uint8_t *srow = slab + lane * 64;
+            const int sw = (lane >> 1) & 3;
+            const float *hw = reinterpret_cast<const float *>(base_ptr + sm.ss) + 2 * p.Npad;   // head: [C+1] weights, bias
             int turn = 0;
-            for (int mt = 0; mt < p.MT; ++mt)
-            for (int cc = 0; cc < ncc; ++cc) {
-                if (NSHARE > 1) { const bool mine = (turn == half); turn = (turn + 1 == NSHARE) ? 0 : turn + 1; if (!mine) continue; }
+#pragma unroll 1
+            for (int mt = 0; mt < p.MT; ++mt) {
                 const int row = mt * 128 + q * 32 + lane;
                 int bb, l;
                 if (p.packed) { const int f = row / p.S; bb = b0 + f; l = row - f * p.S; if (f >= p.FR) l = p.L; }
                 else { bb = b0; l = l0 + row; }
                 const bool valid = (bb < p.B) && (l < p.L);
-                uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc_col + (uint32_t)(mt * p.Nstride + cc * 32), v);
-                if (!valid) continue;
-                const int colbase = cc * 32;
-                float f[32];
+                float hacc = p.head ? hw[p.Cout + 1] : 0.f;
+#pragma unroll 1
+                for (int cc = 0; cc < ncc; ++cc) {
+                    if (NSHARE > 1) { const bool mine = (turn == half); turn = (turn + 1 == NSHARE) ? 0 : turn + 1; if (!mine) continue; }
+                    const int colbase = cc * 32;
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc_col + (uint32_t)(mt * p.Nstride + colbase);
+#pragma unroll 1
+                    for (int h16 = 0; h16 < 2; ++h16) {
+                        if (colbase + 16 * h16 >= Nthis) break;
+                        uint32_t v[16];
+                        tmem_ld16(taddr + 16 * h16, v);
+                        if (p.bulk_store && h16 == 0) {                   // slab free again? (previous TMA store has read it)
+                            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                            __syncwarp();
+                        }
 #pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                    // (scale, shift) pairs of two adjacent columns in one 16-byte shared load
-                    const float4 s2 = (colbase + j < Nthis) ? *reinterpret_cast<const float4 *>(&ss[n0 + colbase + j])
-                                                            : make_float4(0.f, 0.f, 0.f, 0.f);
-                    f[j] = lrelu(fmaf(__uint_as_float(v[j]), s2.x, s2.y));
-                    f[j + 1] = lrelu(fmaf(__uint_as_float(v[j + 1]), s2.z, s2.w));
-                }
-                if (p.out != nullptr) {
-                    __nv_bfloat16 *orow = p.out + ((size_t)bb * p.L + l) * p.Cout + n0 + colbase;
+                        for (int g8 = 0; g8 < 2; ++g8) {
+                            const int col = colbase + 16 * h16 + 8 * g8;       // column inside this CTA's N range
+                            float f[8];
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        if (colbase + g * 8 < Nthis && n0 + colbase + g * 8 < p.Cout) {
-                            const uint4 o = make_uint4(pack_bf16(f[g * 8 + 0], f[g * 8 + 1]), pack_bf16(f[g * 8 + 2], f[g * 8 + 3]),
-                                                       pack_bf16(f[g * 8 + 4], f[g * 8 + 5]), pack_bf16(f[g * 8 + 6], f[g * 8 + 7]));
-                            *reinterpret_cast<uint4 *>(orow + g * 8) = o;
+                            for (int j = 0; j < 8; j += 2) {
+                                const float4 s2 = (col + j < Nthis) ? *reinterpret_cast<const float4 *>(&ss[n0 + col + j])
+                                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+                                f[j] = lrelu(fmaf(__uint_as_float(v[8 * g8 + j]), s2.x, s2.y));
+                                f[j + 1] = lrelu(fmaf(__uint_as_float(v[8 * g8 + j + 1]), s2.z, s2.w));
+                            }
+                            const uint4 o = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+                            const bool col_ok = col < Nthis && n0 + col < p.Cout;
+                            if (p.bulk_store) {
+                                if (col_ok) *reinterpret_cast<uint4 *>(srow + (((2 * h16 + g8) ^ sw) << 4)) = o;
+                            } else if (p.out != nullptr && valid && col_ok) {
+                                *reinterpret_cast<uint4 *>(p.out + ((size_t)bb * p.L + l) * p.Cout + n0 + col) = o;
+                            }
+                            if (p.head) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j)
+                                    if (col + j < p.Cout) hacc = fmaf(hw[col + j], f[j], hacc);
+                            }
+                        }
+                    }
+                    if (p.bulk_store) {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) {
+                            const int grow = b0 * p.L + l0 + mt * 128 + q * 32;       // row of the [B*L][Cout] view
+                            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                         ::"l"(reinterpret_cast<uint64_t>(&tmO)), "r"(slab_s), "r"(colbase), "r"(grow) : "memory");
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                         }
                     }
                 }
-                if (p.head) {
-                    // cat([o, input], 1) -> Conv1d(C+1 -> 1, k=1) -> Tanh   (model/unet_basic.py:98-99)
-                    const float *hw = reinterpret_cast<const float *>(base_ptr + sm.ss) + 2 * p.Npad;   // [C+1] weights, bias
-                    float acc = hw[p.Cout + 1];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (j < p.Cout) acc = fmaf(hw[j], f[j], acc);
-                    acc = fmaf(hw[p.Cout], mt == 0 ? xin0 : (mt == 1 ? xin1 : (mt == 2 ? xin2 : xin3)), acc);
-                    p.y[(size_t)bb * p.T + l] = tanh_fast(acc);
+                if (p.head && valid) {
+                    // cat([o, input], 1) -> Conv1d(C+1 -> 1, k=1) -> Tanh   (model/unet_basic.py:98-99); Cout <= 32: one chunk
+                    hacc = fmaf(hw[p.Cout], mt == 0 ? xin0 : (mt == 1 ? xin1 : (mt == 2 ? xin2 : xin3)), hacc);
+                    p.y[(size_t)bb * p.T + l] = tanh_fast(hacc);
                 }
-            }
             }
             // accumulator buffer drained: hand it back to the MMA warp
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -614,12 +600,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint4 xr[10];
         bool pref = false;
         const int nruns = (p.rows_used + 15) >> 4;
-        auto unit_fast = [&](int c) { const ChunkInfo u = chunk_info<UPCAT>(p, c); return !p.packed && u.up && nruns * u.nk * 2 <= NPROD; };
-        auto fetch = [&](int ub0, int ul0, int c) {
+        // a chunk whose first-round items can be prefetched into the register window one work unit ahead
+        auto unit_fast = [&](int c) { return !p.packed && chunk_info<UPCAT>(p, c).up; };
+        // loads of item `item` of unit (frame ub0, first row ul0, K-loop position c) into the window
+        auto fetch = [&](int ub0, int ul0, int c, int item) {
             const ChunkInfo u = chunk_info<UPCAT>(p, c);
             const int nvec = u.nk * 2;
-            if (pt >= nruns * nvec) return;
-            const int run = pt / nvec, vec = pt - run * nvec;
+            if (item >= nruns * nvec) return;
+            const int run = item / nvec, vec = item - run * nvec;
             const int ch = u.idx * 64 + vec * 8;
             const int ms = (ul0 - PAD + 16 * run) >> 1;
             const bool chok = ch < p.Cin0 && ub0 < p.B;
@@ -666,18 +654,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tile_coords(tile, b0, l0, n0);
             for (int c = 0; c < p.nchunks; ++c) {
                 const bool fast = unit_fast(c);
-                if (fast && !pref) fetch(b0, l0, c);
+                if (fast && !pref) fetch(b0, l0, c, pt);
                 mbar_wait(a_empty + 8 * sa, pa ^ 1);
                 const ChunkInfo cu = chunk_info<UPCAT>(p, c);
                 if (cu.up) {
                     const int nvec = cu.nk * 2;                              // 16-byte vectors per row
                     uint8_t *dst = base_ptr + sm.a + sa * p.a_stage_bytes;
                     if (fast) {
-                        if (pt < nruns * nvec) emit(dst, l0, c, pt, xr);
+                        const int nitems = nruns * nvec;
+#pragma unroll 1
+                        for (int itx = pt; itx < nitems; itx += NPROD) {
+                            if (itx != pt) fetch(b0, l0, c, itx);            // later rounds load on demand
+                            emit(dst, l0, c, itx, xr);
+                        }
                         pref = false;
-                        // next upsampled unit of this CTA: next chunk of this tile, or chunk 0 of the next tile
+                        // next upsampled unit of this CTA (K-loop order): prefetch its first-round item
                         int nt = tile, nc = c + 1;
-                        for (int hop = 0; hop < p.nchunks; ++hop) {               // next upsampled chunk in K-loop order
+                        for (int hop = 0; hop < p.nchunks; ++hop) {
                             if (nc >= p.nchunks) { nc = 0; nt += gridDim.x; }
                             if (chunk_info<UPCAT>(p, nc).up) break;
                             ++nc;
@@ -685,24 +678,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (nt < total_tiles && unit_fast(nc)) {
                             int nb0, nl0, nn0;
                             tile_coords(nt, nb0, nl0, nn0);
-                            fetch(nb0, nl0, nc);
+                            fetch(nb0, nl0, nc, pt);
                             pref = true;
-                        }
-                    } else if (!p.packed) {
-                        for (int itx = pt; itx < nruns * nvec; itx += NPROD) {
-                            uint4 w[10];
-                            const int run = itx / nvec, vec = itx - run * nvec;
-                            const int ch = cu.idx * 64 + vec * 8;
-                            const int ms = (l0 - PAD + 16 * run) >> 1;
-                            const bool chok = ch < p.Cin0;
-                            const __nv_bfloat16 *pb = p.prev + (size_t)b0 * p.Lin * p.Cin0 + ch;
-#pragma unroll
-                            for (int qq = 0; qq < 10; ++qq) {
-                                int m = ms - 1 + qq;
-                                m = m < 0 ? 0 : (m > p.Lin - 1 ? p.Lin - 1 : m);
-                                w[qq] = chok ? __ldg(reinterpret_cast<const uint4 *>(pb + (size_t)m * p.Cin0)) : make_uint4(0u, 0u, 0u, 0u);
-                            }
-                            emit(dst, l0, c, itx, w);
                         }
                     } else {
                         // frames shorter than a tile (packed): generic per-(row, vector) path, ATen index math in fp32
