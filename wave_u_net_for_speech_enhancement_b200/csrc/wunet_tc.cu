@@ -51,7 +51,7 @@ int tc_fail(const char *fmt, ...)
 }
 
 constexpr int kEpiWarpsEnc = 8;                   // encoder kernels: two epilogue warps per TMEM lane quadrant
-constexpr int kEpiWarpsDec = 4;                   // decoder kernels: one per quadrant ...
+constexpr int kEpiWarpsDec = 8;                   // decoder kernels: two per quadrant as well ...
 constexpr int kProducerWarps = 9;                 // ... plus nine upsample-producer warps (one item per thread at MT=4)
 constexpr int kThreadsEnc = 64 + 32 * kEpiWarpsEnc;                    // TMA, MMA, epilogue warps
 constexpr int kThreadsDec = 64 + 32 * (kEpiWarpsDec + kProducerWarps);
@@ -526,9 +526,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 else { bb = b0; l = l0 + row; }
                 const bool valid = (bb < p.B) && (l < p.L);
                 float hacc = p.head ? hw[p.Cout + 1] : 0.f;
+                bool did = false;                                 // this warp converted the row's (single) chunk
 #pragma unroll 1
                 for (int cc = 0; cc < ncc; ++cc) {
                     if (NSHARE > 1) { const bool mine = (turn == half); turn = (turn + 1 == NSHARE) ? 0 : turn + 1; if (!mine) continue; }
+                    did = true;
                     const int colbase = cc * 32;
                     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc_col + (uint32_t)(mt * p.Nstride + colbase);
 #pragma unroll 1
@@ -576,7 +578,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                 }
-                if (p.head && valid) {
+                if (p.head && valid && did) {
                     // cat([o, input], 1) -> Conv1d(C+1 -> 1, k=1) -> Tanh   (model/unet_basic.py:98-99); Cout <= 32: one chunk
                     hacc = fmaf(hw[p.Cout], mt == 0 ? xin0 : (mt == 1 ? xin1 : (mt == 2 ? xin2 : xin3)), hacc);
                     p.y[(size_t)bb * p.T + l] = tanh_fast(hacc);
