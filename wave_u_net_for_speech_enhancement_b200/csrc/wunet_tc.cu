@@ -1092,11 +1092,11 @@ static int build_plan(TcState *st, const float *x, float *y, int B, int T, void 
             const int mt_pref = p.MT;
             for (int MT = mt_pref; MT >= std::max(1, mt_pref / (dec ? 1 : 2)) && !p.resident; MT >>= 1) {
                 geometry(MT, 1);
-                const int stage = round_up(p.Nh * 128 * 5, 1024);
-                const int wbytes = p.nchunks * (KS / 5) * stage;
+                const int stage = round_up(p.Nh * 128 * KS, 1024);
+                const int wbytes = p.nchunks * stage;
                 const int na = (dec && p.nchunks >= 3) ? 3 : 2;
                 if (na * (int)p.a_stage_bytes + wbytes <= budget) {
-                    p.resident = 1; p.na = na; p.tg = 5; p.ngroups = KS / 5;
+                    p.resident = 1; p.na = na; p.tg = KS; p.ngroups = 1;
                     p.b_stage_bytes = (uint32_t)stage;
                     p.nb = p.nchunks * p.ngroups;
                 }
@@ -1110,10 +1110,11 @@ static int build_plan(TcState *st, const float *x, float *y, int B, int T, void 
             const int na_want = (dec && !packed && p.nchunks >= 3 && p.MT <= 2) ? 3 : 2;
             bool ok = false;
             for (int na = na_want; na >= 1 && !ok; --na) {
-                for (int tg : {5, 3, 1}) {
-                    if (KS % tg != 0) continue;
+                for (int tg = KS; tg >= 1; --tg) {
+                    // every stage handshake costs a ~400-cycle tensor-pipe bubble (trace): prefer the fattest stage
+                    // (most taps per handshake) that still leaves a 2-deep ring; taps past KS in the last group are zero-filled
                     const int stage = round_up(p.Nh * 128 * tg, 1024);
-                    const int min_stages = (tg == 1) ? 4 : 2;   // fewer, fatter weight stages beat a deeper ring (measured)
+                    const int min_stages = 2;
                     if (na * (int)p.a_stage_bytes + min_stages * stage > budget) continue;
                     p.na = na; p.tg = tg;
                     p.ngroups = (KS + tg - 1) / tg;
