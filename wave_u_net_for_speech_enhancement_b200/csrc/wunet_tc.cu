@@ -414,12 +414,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else if (warp == kMmaWarp) {
         // ======================= MMA issuer =======================
-        // The whole warp runs the (uniform) control flow; one elected lane issues tcgen05.mma / commit.
-        {
+        // One elected lane runs the whole role (barrier waits included): every warp-level reconvergence between two weight
+        // stages costs tensor-pipe idle time, because the asynchronous MMA queue is only a few instructions deep.
+        if (elect_one()) {
             int sa = 0, pa = 0, sb = 0, pb = 0, it = 0;
             int tr1 = 0; (void)tr1;
             int tr3 = 0; (void)tr3;
             const uint32_t tile_bytes = (uint32_t)p.Nh * 128;
+            const uint32_t b_step = tile_bytes >> 4;
+            // descriptor words: hi = SBO(1024 B) | version 1 | SWIZZLE_128B, lo = (addr >> 4) | LBO(1)
+            const uint32_t hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
             if (p.resident) { mbar_wait(b_full, 0); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
             for (int tile = first_tile; tile < total_tiles; tile += gridDim.x, ++it) {
                 int b0, l0, n0;
@@ -429,54 +433,44 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Nthis >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
                 const int buf = (p.nacc == 2) ? (it & 1) : 0;
                 const uint32_t use = (p.nacc == 2) ? (uint32_t)(it >> 1) : (uint32_t)it;
-                if (lane == 0) TRACE(1, tr1);
+                TRACE(1, tr1);
                 mbar_wait(acc_empty + 8 * buf, (use & 1) ^ 1);
-                if (lane == 0) TRACE(1, tr1);
+                TRACE(1, tr1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t acc_col = tmem_base + buf * p.MT * p.Nstride;
                 for (int c = 0; c < p.nchunks; ++c) {
                     const int nk = chunk_info<UPCAT>(p, c).nk;
                     mbar_wait(a_full + 8 * sa, pa);
-                    if (lane == 0) TRACE(1, tr1);
+                    TRACE(1, tr1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a_base = base + sm.a + sa * p.a_stage_bytes;
+                    uint32_t a_lo = ((a_base >> 4) & 0x3FFFu) | (1u << 16);
                     for (int g = 0; g < p.ngroups; ++g) {
                         uint32_t b_base;
                         if (p.resident) {
                             b_base = base + sm.b + (uint32_t)(c * p.ngroups + g) * p.b_stage_bytes;
                         } else {
                             mbar_wait(b_full + 8 * sb, pb);
-                            if (lane == 0) TRACE(1, tr1);
+                            TRACE(1, tr1);
                             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                             b_base = base + sm.b + sb * p.b_stage_bytes;
                         }
+                        uint32_t b_lo = ((b_base >> 4) & 0x3FFFu) | (1u << 16);
                         const int t_end = min(KS, (g + 1) * p.tg);
-                        if (elect_one()) {
-                            // descriptor words: hi = SBO(1024 B) | version 1 | SWIZZLE_128B, lo = (addr >> 4) | LBO(1)
-                            const uint32_t hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
-                            uint32_t a_lo = ((a_base >> 4) & 0x3FFFu) | (1u << 16);
-                            uint32_t b_lo = ((b_base >> 4) & 0x3FFFu) | (1u << 16);
-                            a_lo += (uint32_t)(g * p.tg) * 8;                      // tap shift: +128 B per tap
-                            const uint32_t b_step = tile_bytes >> 4;
 #pragma unroll 1
-                            for (int t = g * p.tg; t < t_end; ++t) {
-                                TRACE(3, tr3);
-                                const uint32_t accf = (c | t) ? 1u : 0u;
-                                issue_tap(acc_col, p.MT, p.Nstride, nk, a_lo, b_lo, hi, idesc, accf);
-                                a_lo += 8;
-                                b_lo += b_step;
-                            }
-                            if (!p.resident) umma_commit(b_empty + 8 * sb);
+                        for (int t = g * p.tg; t < t_end; ++t) {
+                            TRACE(3, tr3);
+                            issue_tap(acc_col, p.MT, p.Nstride, nk, a_lo, b_lo, hi, idesc, (c | t) ? 1u : 0u);
+                            a_lo += 8;                                     // tap shift: +128 B
+                            b_lo += b_step;
                         }
-                        __syncwarp();
+                        if (!p.resident) umma_commit(b_empty + 8 * sb);
                         if (++sb == p.nb) { sb = 0; pb ^= 1; }
                     }
-                    if (elect_one()) umma_commit(a_empty + 8 * sa);
-                    __syncwarp();
+                    umma_commit(a_empty + 8 * sa);
                     if (++sa == p.na) { sa = 0; pa ^= 1; }
                 }
-                if (elect_one()) umma_commit(acc_full + 8 * buf);
-                __syncwarp();
+                umma_commit(acc_full + 8 * buf);
             }
         }
     } else if (warp < kEpilogueWarps) {
