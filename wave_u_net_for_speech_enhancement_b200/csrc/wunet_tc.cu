@@ -1063,8 +1063,8 @@ static int build_plan(TcState *st, const float *x, float *y, int B, int T, void 
             int MT;
             if (ns32 <= 64) MT = 4;            // 2 x 4 x 64 TMEM columns: double-buffered accumulators
             else if (ns32 <= 96) MT = 2;       // 2 x 2 x 96
-            else if (ns32 <= 128) MT = 4;      // single buffer, weights shared by 4 sub-tiles
-            else MT = 2;
+            else if (ns32 <= 128) MT = 2;      // 2 x 2 x 128 columns: double-buffered accumulators beat the bigger MT=4 tile (73 vs 105 us on enc4)
+            else MT = dec ? 2 : 1;             // N > 128: encoders gain from double buffering at MT=1 (enc5: 60 vs 74 us); decoders do not
             while (MT > 1 && 128 * MT > L) MT >>= 1;
             geometry(MT, base_split);
         } else {
