@@ -1,3 +1,5 @@
+import signal
+signal.signal(signal.SIGPIPE, signal.SIG_DFL)
 """Print the per-level table of a bench JSON."""
 import json, sys
 d = json.load(open(sys.argv[1]))

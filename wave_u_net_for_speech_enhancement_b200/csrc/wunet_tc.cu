@@ -114,27 +114,11 @@ __device__ __forceinline__ void umma_commit(uint32_t bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-// K-major, 128B-swizzled operand: 8-row groups 1024 B apart; base_offset stays 0 for any start row
-// (swizzle acts on absolute shared-memory address bits; tools/umma_probe.cu)
-__device__ __forceinline__ uint64_t sw128_desc(uint32_t saddr)
-{
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)1 << 16;                       // LBO (ignored for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;             // SBO
-    d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
-    return d;
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
-}
-// Same MMA with the descriptors passed as (lo, hi) words: hi is loop-invariant, lo = base + small offsets, so the
-// issuing lane spends one uniform add per operand per MMA (tools/umma_rate.cu: 40 cyc/MMA at N=32 instead of ~110).
+// UMMA shared-memory descriptor of a K-major, 128B-swizzled operand (8-row groups 1024 B apart), as (lo, hi) words:
+//   lo = (addr >> 4) | LBO(1) << 16,  hi = SBO(1024 >> 4) | version(1) << 14 | SWIZZLE_128B(2) << 29.
+// base_offset stays 0 for ANY start row: the swizzle acts on absolute shared-memory address bits (tools/umma_probe.cu).
+// hi is loop-invariant and lo = base + small offsets, so the issuing lane spends one uniform add per operand per MMA
+// (tools/umma_rate.cu: 40 cycles/MMA at N=32 instead of ~110 with 64-bit descriptor arithmetic in the loop).
 __device__ __forceinline__ void umma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc,
                                                uint32_t accumulate)
 {
@@ -1013,9 +997,16 @@ static int build_plan(TcState *st, const float *x, float *y, int B, int T, void 
             if (!dec) { for (int c = 0; c < p.nchunks; ++c) p.chunk_map[k++] = (unsigned char)c; }
             else {
                 const int nfull0 = lv.cin0 / 64, n1 = p.nchunks - p.nchunks0;
-                for (int c = 0; c < nfull0; ++c) p.chunk_map[k++] = (unsigned char)(0x80 | c);
-                for (int c = 0; c < n1; ++c) p.chunk_map[k++] = (unsigned char)c;
-                if (nfull0 < p.nchunks0) p.chunk_map[k++] = (unsigned char)(0x80 | nfull0);
+                if (nfull0 == 0) {
+                    // the only upsampled chunk is partial (e.g. the last decoder: 48 + 24 channels): produce it FIRST, so that its
+                    // shared-memory stage is released half a tile before the producers need it again
+                    p.chunk_map[k++] = (unsigned char)0x80;
+                    for (int c = 0; c < n1; ++c) p.chunk_map[k++] = (unsigned char)c;
+                } else {
+                    for (int c = 0; c < nfull0; ++c) p.chunk_map[k++] = (unsigned char)(0x80 | c);
+                    for (int c = 0; c < n1; ++c) p.chunk_map[k++] = (unsigned char)c;
+                    if (nfull0 < p.nchunks0) p.chunk_map[k++] = (unsigned char)(0x80 | nfull0);
+                }
             }
             if (p.nchunks > 16) return tc_fail("too many K chunks");
         }
@@ -1061,7 +1052,7 @@ static int build_plan(TcState *st, const float *x, float *y, int B, int T, void 
         if (!packed) {
             const int ns32 = round_up(base_split == 1 ? lv.Npad : round_up((lv.Npad + 1) / 2, 16), 32);
             int MT;
-            if (ns32 <= 64) MT = 4;            // 2 x 4 x 64 TMEM columns: double-buffered accumulators
+            if (ns32 <= 64) MT = 4;            // 2 x 4 x 64 TMEM columns: double-buffered accumulators (MT=2 measured 40 % slower on dec10/dec11)
             else if (ns32 <= 96) MT = 2;       // 2 x 2 x 96
             else if (ns32 <= 128) MT = 2;      // 2 x 2 x 128 columns: double-buffered accumulators beat the bigger MT=4 tile (73 vs 105 us on enc4)
             else MT = dec ? 2 : 1;             // N > 128: encoders gain from double buffering at MT=1 (enc5: 60 vs 74 us); decoders do not
