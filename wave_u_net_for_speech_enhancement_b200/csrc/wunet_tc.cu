@@ -706,7 +706,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // -------------------------------------------------------------------------------------------------
 // enc0: Conv1d(1 -> C, k=15) + BN + LeakyReLU on CUDA cores (Cin = 1: K = 15, HBM-bound), fp32 in, bf16 NLC out
 // -------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 3) enc0_kernel(const float *__restrict__ x, const float *__restrict__ w /*[C][1][15]*/,
+__global__ void __launch_bounds__(256, 4) enc0_kernel(const float *__restrict__ x, const float *__restrict__ w /*[C][1][15]*/,
                                                       const float *__restrict__ scale, const float *__restrict__ shift,
                                                       __nv_bfloat16 *__restrict__ out, int B, int T, int C)
 {
