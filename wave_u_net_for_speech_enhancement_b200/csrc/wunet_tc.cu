@@ -23,8 +23,10 @@
 //     output never reaches HBM.
 //   * frames shorter than 128 samples (the bottom of the U) are packed several per tile with their own halo
 //     rows; rows that straddle two frames are computed and discarded.
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2-5 = upsample
-// producers during the main loop, then epilogue (TMEM lane quadrant = warp % 4).
+// Warp roles: epilogue warps (TMEM lane quadrant = warp % 4), upsample-producer warps (decoder blocks), one TMA
+// warp, one MMA-issue warp (highest warp id). Two kernel flavours per block type: "large" (one CTA per SM, 8 epilogue
+// + 9 producer warps) and "small" (two CTAs per SM: 4 + 4 warps, half the shared memory and TMEM each), so that one
+// CTA's pipeline bubbles are filled by the other's MMAs.
 #include "wunet_tc.cuh"
 #include "wunet_common.cuh"
 
@@ -34,6 +36,7 @@
 #include <cstring>
 #include <algorithm>
 #include <map>
+#include <string>
 #include <vector>
 
 namespace wunet {
@@ -50,11 +53,11 @@ int tc_fail(const char *fmt, ...)
     return -1;
 }
 
-constexpr int kEpiWarpsEnc = 8;                   // encoder kernels: two epilogue warps per TMEM lane quadrant
-constexpr int kEpiWarpsDec = 8;                   // decoder kernels: two per quadrant as well ...
-constexpr int kProducerWarps = 9;                 // ... plus nine upsample-producer warps (one item per thread at MT=4)
-constexpr int kThreadsEnc = 64 + 32 * kEpiWarpsEnc;                    // TMA, MMA, epilogue warps
-constexpr int kThreadsDec = 64 + 32 * (kEpiWarpsDec + kProducerWarps);
+constexpr int kEpiWarpsLarge = 8;                 // "large" flavour: two epilogue warps per TMEM lane quadrant ...
+constexpr int kProducerWarpsLarge = 9;            // ... plus nine upsample-producer warps in decoder blocks (one item per thread at MT=4)
+constexpr int kEpiWarpsSmall = 4;                 // "small" flavour (two CTAs per SM): one epilogue warp per quadrant,
+constexpr int kProducerWarpsSmall = 4;            // four producer warps
+constexpr int kSmemLimitSmall = 113 * 1024;       // 2 x (dynamic + 1 KB reserved) <= 228 KB per SM
 constexpr int kMaxBStages = 8;
 constexpr int kSmemLimit = 227 * 1024;
 
@@ -258,14 +261,15 @@ __device__ __forceinline__ ChunkInfo chunk_info(const TcParams &p, int c)
 // -------------------------------------------------------------------------------------------------
 // the conv kernel
 // -------------------------------------------------------------------------------------------------
-template <int KS, bool UPCAT>
-__global__ void __launch_bounds__(UPCAT ? kThreadsDec : kThreadsEnc, 1)
+template <int KS, bool UPCAT, int EW, int PW>
+__global__ void __launch_bounds__(64 + 32 * (EW + PW), EW == kEpiWarpsSmall ? 2 : 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmO, const TcParams p)
 {
     constexpr int PAD = (KS - 1) / 2;
+    constexpr int kProducerWarps = PW;
     constexpr int NPROD = kProducerWarps * 32;
-    constexpr int kEpilogueWarps = UPCAT ? kEpiWarpsDec : kEpiWarpsEnc;
+    constexpr int kEpilogueWarps = EW;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -831,6 +835,58 @@ struct TcPlanLevel {
     int per_sm;
     size_t smem;
     bool upcat;
+    bool small;                        // two-CTAs-per-SM kernel flavour
+};
+
+// Per-block tiling overrides for tuning sweeps: WUNET_TC_OVR="<block>:key=val,key=val;<block>:..." with keys
+// mt, ns (column splits), na, nacc, tg, res (0/1), small (0/1), bulk (0/1), packed (1: pack L=128 frames). Unset keys keep
+// the heuristic's choice.
+struct TcOverride { int mt = 0, ns = 0, na = 0, nacc = 0, tg = 0, res = -1, small = -1, bulk = -1, packed = -1; bool any = false; };
+static void parse_kv(const std::string &seg, TcOverride &ov)
+{
+    size_t q = 0;
+    while (q < seg.size()) {
+        size_t qe = seg.find(',', q);
+        if (qe == std::string::npos) qe = seg.size();
+        const std::string kv = seg.substr(q, qe - q);
+        q = qe + 1;
+        const size_t eq = kv.find('=');
+        if (eq == std::string::npos) continue;
+        const std::string k = kv.substr(0, eq);
+        const int v = atoi(kv.c_str() + eq + 1);
+        if (k == "mt") ov.mt = v; else if (k == "ns") ov.ns = v; else if (k == "na") ov.na = v;
+        else if (k == "nacc") ov.nacc = v; else if (k == "tg") ov.tg = v; else if (k == "res") ov.res = v;
+        else if (k == "small") ov.small = v; else if (k == "bulk") ov.bulk = v; else if (k == "packed") ov.packed = v;
+        ov.any = true;
+    }
+}
+static TcOverride parse_override(const std::string &env, int block)
+{
+    TcOverride ov;
+    size_t pos = 0;
+    while (pos < env.size()) {
+        size_t end = env.find(';', pos);
+        if (end == std::string::npos) end = env.size();
+        const std::string seg = env.substr(pos, end - pos);
+        pos = end + 1;
+        const size_t colon = seg.find(':');
+        if (colon == std::string::npos || atoi(seg.substr(0, colon).c_str()) != block) continue;
+        parse_kv(seg.substr(colon + 1), ov);
+    }
+    return ov;
+}
+
+// Tilings found by tools/sweep_levels.py on a B200 for the reference's default architecture (12 levels x 24 channels,
+// 16384-sample frames, batch 256) where they beat the generic rules of build_plan by more than 3 %. Keyed on the block's
+// shape, used for batches >= 128 frames (the tile-count regime they were measured in); anything else takes the rules.
+struct TunedTiling { int L, cin0, cin1, cout, k; const char *kv; };
+static const TunedTiling kTuned[] = {
+    {64, 192, 0, 216, 15, "mt=3,ns=2"},               // enc8:  34.3 us vs 38.6
+    {32, 216, 0, 240, 15, "mt=1,ns=3,small=1"},       // enc9:  25.9 us vs 29.2
+    {64, 240, 216, 216, 5, "mt=1,ns=1,small=1"},      // dec3:  37.3 us vs 38.9
+    {128, 216, 192, 192, 5, "mt=1,small=1"},          // dec4:  34.7 us vs 36.4
+    {512, 168, 144, 144, 5, "mt=1,small=1"},          // dec6:  73.8 us vs 77.9
+    {16384, 48, 24, 24, 5, "mt=2,small=1"},           // dec11 + head: 245 us vs 262
 };
 
 struct TcPlan {
@@ -856,6 +912,7 @@ struct TcState {
     int plan_B = 0, plan_T = 0;
     const float *plan_x = nullptr;
     float *plan_y = nullptr;
+    std::string plan_ovr;              // WUNET_TC_OVR value the cached plan was built with
     TcPlan plan;
 };
 
@@ -1011,7 +1068,15 @@ static int build_plan(TcState *st, const float *x, float *y, int B, int T, void 
             if (p.nchunks > 16) return tc_fail("too many K chunks");
         }
         // ---- tiling ---------------------------------------------------------------------------------
-        const bool packed = L < 128;
+        TcOverride ov = parse_override(st->plan_ovr, i);
+        if (!ov.any && B >= 128)
+            for (const TunedTiling &t : kTuned)
+                if (t.L == L && t.cin0 == lv.cin0 && t.cin1 == lv.cin1 && t.cout == lv.cout && t.k == KS) parse_kv(t.kv, ov);
+        const bool small = ov.small > 0;
+        const int smem_limit = small ? kSmemLimitSmall : kSmemLimit;
+        const int tmem_limit = small ? 256 : 512;
+        P.small = small;
+        const bool packed = L < 128 || (ov.packed > 0 && L + KS - 1 <= 256);
         auto geometry = [&](int MT, int nsplit) {
             p.nsplit = nsplit;
             p.Nh = nsplit == 1 ? lv.Npad : round_up((lv.Npad + nsplit - 1) / nsplit, 16);
@@ -1043,44 +1108,61 @@ static int build_plan(TcState *st, const float *x, float *y, int B, int T, void 
                 p.a_tx_bytes = FR * p.S * 128;
                 p.m_tiles = (B + FR - 1) / FR;
             }
-            p.nacc = (2 * MT * p.Nstride <= 512) ? 2 : 1;
+            p.nacc = (ov.nacc != 1 && 2 * MT * p.Nstride <= tmem_limit) ? 2 : 1;
             uint32_t cols = 32;
             while ((int)cols < p.nacc * MT * p.Nstride) cols <<= 1;
             p.tmem_cols = cols;
         };
         const int base_split = lv.Npad > 256 ? 2 : 1;
+        const int ns_sel = ov.ns > 0 ? ov.ns : base_split;
         if (!packed) {
-            const int ns32 = round_up(base_split == 1 ? lv.Npad : round_up((lv.Npad + 1) / 2, 16), 32);
+            const int ns32 = round_up(ns_sel == 1 ? lv.Npad : round_up((lv.Npad + ns_sel - 1) / ns_sel, 16), 32);
             int MT;
-            if (ns32 <= 64) MT = 4;            // 2 x 4 x 64 TMEM columns: double-buffered accumulators (MT=2 measured 40 % slower on dec10/dec11)
+            if (small) {
+                MT = ns32 <= 64 ? 2 : 1;       // 256 TMEM columns per CTA: double-buffered accumulators up to N = 128
+            } else if (ns32 <= 64) MT = 4;     // 2 x 4 x 64 TMEM columns: double-buffered accumulators (MT=2 measured 40 % slower on dec10/dec11)
             else if (ns32 <= 96) MT = 2;       // 2 x 2 x 96
             else if (ns32 <= 128) MT = 2;      // 2 x 2 x 128 columns: double-buffered accumulators beat the bigger MT=4 tile (73 vs 105 us on enc4)
             else MT = dec ? 2 : 1;             // N > 128: encoders gain from double buffering at MT=1 (enc5: 60 vs 74 us); decoders do not
-            while (MT > 1 && 128 * MT > L) MT >>= 1;
-            geometry(MT, base_split);
+            if (ov.mt > 0) MT = ov.mt;
+            while (MT > 1 && 128 * MT > L) --MT;
+            geometry(MT, ns_sel);
+        } else if (ov.mt > 0 || ov.ns > 0) {
+            geometry(ov.mt > 0 ? ov.mt : 1, ns_sel);
         } else {
-            // bottom of the U: few tiles, long K loops -> spread over the SMs with small tiles and column splits
-            int MT = 2, ns = base_split;
+            // bottom of the U: few tiles, long K loops. ONE wave of tiles (a second, partial wave costs a whole tile time:
+            // 172 tiles on 148 SMs measured 30-60 % slower than 129), the smallest M tile that allows it, and as many
+            // column splits as still fit in that wave (each CTA then streams a smaller share of the weights from L2).
+            int MT = 1, ns = base_split;
             geometry(MT, ns);
-            if (p.m_tiles * ns < st->num_sms) { MT = 1; geometry(MT, ns); }
-            while (p.m_tiles * ns * 2 <= st->num_sms + st->num_sms / 4 && ns < 4 && lv.Npad / (ns * 2) >= 48) { ns *= 2; geometry(MT, ns); }
+            while (p.m_tiles * ns > st->num_sms && MT < 4 && (MT + 1) * p.Nstride <= tmem_limit) geometry(++MT, ns);
+            const int m_tiles = p.m_tiles;
+            for (int cand : {2, 3, 4, 6}) {
+                if (cand <= ns) continue;
+                const int nh = round_up((lv.Npad + cand - 1) / cand, 16);
+                if (m_tiles * cand <= st->num_sms && nh >= 48 && (cand - 1) * nh < lv.Npad) ns = cand;
+            }
+            geometry(MT, ns);
         }
+        if ((int)p.tmem_cols > tmem_limit) return tc_fail("level %d: %u TMEM columns exceed %d", i, p.tmem_cols, tmem_limit);
+        if (p.Nh > 256) return tc_fail("level %d: N per CTA %d exceeds 256", i, p.Nh);
+        if ((p.nsplit - 1) * p.Nh >= lv.Npad) return tc_fail("level %d: %d column splits of %d leave an empty split", i, p.nsplit, p.Nh);
         // epilogue store mode (needs complete tiles of complete rows per warp)
         p.bulk_store = 0;
-        p.n_epi = dec ? kEpiWarpsDec : kEpiWarpsEnc;
+        p.n_epi = small ? kEpiWarpsSmall : kEpiWarpsLarge;
         p.resident = 0;
-        if (!packed && base_split == 1) {
+        const int ring_budget = smem_limit - 2048 - p.Npad * 8 - 512;
+        if (!packed && p.nsplit == 1 && ov.res != 0) {
             // weights-resident mode: if the block's packed weights fit in shared memory next to the input ring, the persistent
             // CTA loads them once instead of re-streaming them from L2 for every tile (the L2->SM stream, not HBM and not the
             // tensor pipe, is what bounds the shallow blocks otherwise).
-            const int budget = (int)kSmemLimit - 2048 - p.Npad * 8 - 512;
             const int mt_pref = p.MT;
             for (int MT = mt_pref; MT >= std::max(1, mt_pref / (dec ? 1 : 2)) && !p.resident; MT >>= 1) {
                 geometry(MT, 1);
                 const int stage = round_up(p.Nh * 128 * KS, 1024);
                 const int wbytes = p.nchunks * stage;
-                const int na = (dec && p.nchunks >= 3) ? 3 : 2;
-                if (na * (int)p.a_stage_bytes + wbytes <= budget) {
+                const int na = ov.na > 0 ? ov.na : ((dec && p.nchunks >= 3) ? 3 : 2);
+                if (na * (int)p.a_stage_bytes + wbytes <= ring_budget) {
                     p.resident = 1; p.na = na; p.tg = KS; p.ngroups = 1;
                     p.b_stage_bytes = (uint32_t)stage;
                     p.nb = p.nchunks * p.ngroups;
@@ -1091,20 +1173,19 @@ static int build_plan(TcState *st, const float *x, float *y, int B, int T, void 
         if (!p.resident) {
             // A ring depth: decoders whose K chunks are short (5 taps, few K-steps) need the TMA/producers to run two chunks
             // ahead; everything else double-buffers. Weight stages hold `tg` consecutive taps (one TMA box, one handshake).
-            const int budget = (int)kSmemLimit - 2048 - p.Npad * 8 - 512;
-            const int na_want = (dec && !packed && p.nchunks >= 3 && p.MT <= 2) ? 3 : 2;
+            const int na_want = ov.na > 0 ? ov.na : ((dec && !packed && p.nchunks >= 3 && p.MT <= 2) ? 3 : 2);
             bool ok = false;
             for (int na = na_want; na >= 1 && !ok; --na) {
-                for (int tg = KS; tg >= 1; --tg) {
+                for (int tg = (ov.tg > 0 ? std::min(KS, ov.tg) : KS); tg >= 1; --tg) {
                     // every stage handshake costs a ~400-cycle tensor-pipe bubble (trace): prefer the fattest stage
                     // (most taps per handshake) that still leaves a 2-deep ring; taps past KS in the last group are zero-filled
                     const int stage = round_up(p.Nh * 128 * tg, 1024);
                     const int min_stages = 2;
-                    if (na * (int)p.a_stage_bytes + min_stages * stage > budget) continue;
+                    if (na * (int)p.a_stage_bytes + min_stages * stage > ring_budget) continue;
                     p.na = na; p.tg = tg;
                     p.ngroups = (KS + tg - 1) / tg;
                     p.b_stage_bytes = (uint32_t)stage;
-                    int nb = (budget - na * (int)p.a_stage_bytes) / stage;
+                    int nb = (ring_budget - na * (int)p.a_stage_bytes) / stage;
                     if (nb > kMaxBStages) nb = kMaxBStages;
                     p.nb = nb;
                     ok = true;
@@ -1112,17 +1193,19 @@ static int build_plan(TcState *st, const float *x, float *y, int B, int T, void 
                 }
             }
             if (!ok) return tc_fail("level %d does not fit in shared memory", i);
+            if (ov.any && p.na < 2) return tc_fail("level %d: override leaves a single input stage", i);
         }
-        if (!packed && base_split == 1 && i != 2 * n && (L % (128 * p.MT) == 0) && (long long)B * L < (1LL << 31)) {
+        if (!packed && p.nsplit == 1 && ov.bulk != 0 && i != 2 * n && (L % (128 * p.MT) == 0) && (long long)B * L < (1LL << 31)) {
             // TMA-store epilogue if the slabs fit without giving up ring depth / residency / tile size
             const int need = p.n_epi * 2048 + 1024;
             const int min_nb = p.resident ? p.nb : (p.tg == 1 ? 4 : 2);
-            while ((int)smem_total(p) + need > (int)kSmemLimit && !p.resident && p.nb > min_nb) --p.nb;
-            if ((int)smem_total(p) + need <= (int)kSmemLimit) p.bulk_store = 1;
+            while ((int)smem_total(p) + need > smem_limit && !p.resident && p.nb > min_nb) --p.nb;
+            if ((int)smem_total(p) + need <= smem_limit) p.bulk_store = 1;
         }
         {
-            const int threads = dec ? kThreadsDec : kThreadsEnc;
-            const int per_sm = std::max(1, std::min({(int)(kSmemLimit / smem_total(p)), (int)(512 / p.tmem_cols), 2048 / threads}));
+            const int threads = 64 + 32 * (small ? kEpiWarpsSmall + (dec ? kProducerWarpsSmall : 0)
+                                                 : kEpiWarpsLarge + (dec ? kProducerWarpsLarge : 0));
+            const int per_sm = std::max(1, std::min({(int)((228 * 1024) / (smem_total(p) + 1024)), (int)(512 / p.tmem_cols), 2048 / threads}));
             const int total_tiles = p.m_tiles * p.nsplit;
             p.tile_begin = 0; p.tile_end = total_tiles;
             P.per_sm = per_sm;
@@ -1139,6 +1222,7 @@ static int build_plan(TcState *st, const float *x, float *y, int B, int T, void 
         p.x = x; p.y = y; p.head_w = st->out_w; p.head_b = st->out_b;
         p.trace = (st->trace && st->trace_level == i) ? st->trace : nullptr;
         if (last && lv.cout > 32) return tc_fail("fused head needs channels_interval <= 32");
+        if (last && (p.nsplit != 1 || p.packed)) return tc_fail("fused head needs the whole channel range of full frames in one CTA");
         // operand maps
         if (!dec) {
             // decimated view of the previous encoder output: element (c, l, b) -> prev[b][2l][c]   (o[:, :, ::2])
@@ -1163,9 +1247,9 @@ static int build_plan(TcState *st, const float *x, float *y, int B, int T, void 
     if (getenv("WUNET_TC_DEBUG")) {
         for (int i = 1; i < 2 * n + 1; ++i) {
             const TcParams &p = pl.lv[i].p;
-            fprintf(stderr, "[wunet tc] blk %2d L=%5d Cin=%3d+%3d Cout=%3d Nh=%3d x%d MT=%d nacc=%d packed=%d FR=%d res=%d bulk=%d na=%d nb=%d tg=%d smem=%zu tmem=%u tiles=%d grid=%u\n",
+            fprintf(stderr, "[wunet tc] blk %2d L=%5d Cin=%3d+%3d Cout=%3d Nh=%3d x%d MT=%d nacc=%d packed=%d FR=%d res=%d bulk=%d na=%d nb=%d tg=%d smem=%zu tmem=%u tiles=%d grid=%u small=%d per_sm=%d\n",
                     i, p.L, p.Cin0, p.Cin1, p.Cout, p.Nh, p.nsplit, p.MT, p.nacc, p.packed, p.FR, p.resident, p.bulk_store, p.na, p.nb, p.tg, pl.lv[i].smem, p.tmem_cols,
-                    p.m_tiles * p.nsplit, pl.lv[i].grid.x);
+                    p.m_tiles * p.nsplit, pl.lv[i].grid.x, (int)pl.lv[i].small, pl.lv[i].per_sm);
         }
     }
     st->plan_ws = ws; st->plan_B = B; st->plan_T = T; st->plan_x = x; st->plan_y = y;
@@ -1178,8 +1262,10 @@ static int tc_prepare(TcState *st, const float *x, float *y, int B, int T, void 
     const int ci = st->ci;
     if (ci % 8 != 0 || ci > 32) return tc_fail("bf16 tcgen05 path needs channels_interval %% 8 == 0 and <= 32 (got %d)", ci);
     if (!st->attr_set) {
-        cudaFuncSetAttribute(conv_tc_kernel<15, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
-        cudaFuncSetAttribute(conv_tc_kernel<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+        cudaFuncSetAttribute(conv_tc_kernel<15, false, kEpiWarpsLarge, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+        cudaFuncSetAttribute(conv_tc_kernel<5, true, kEpiWarpsLarge, kProducerWarpsLarge>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+        cudaFuncSetAttribute(conv_tc_kernel<15, false, kEpiWarpsSmall, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+        cudaFuncSetAttribute(conv_tc_kernel<5, true, kEpiWarpsSmall, kProducerWarpsSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         cudaFuncSetAttribute(enc0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
         int dev = 0, sms = 0;
         if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
@@ -1187,8 +1273,13 @@ static int tc_prepare(TcState *st, const float *x, float *y, int B, int T, void 
         st->attr_set = true;
     }
     (void)x; (void)y;
-    if (st->plan_ws != ws || st->plan_B != B || st->plan_T != T)
+    const char *ovr = getenv("WUNET_TC_OVR");
+    const std::string ovr_s = ovr ? ovr : "";
+    if (st->plan_ws != ws || st->plan_B != B || st->plan_T != T || st->plan_ovr != ovr_s) {
+        st->plan_ovr = ovr_s;
+        st->plan_ws = nullptr;
         if (build_plan(st, nullptr, nullptr, B, T, ws)) return -1;
+    }
     return 0;
 }
 
@@ -1227,8 +1318,10 @@ static int launch_block(TcState *st, int i, int t0, int t1, cudaStream_t stream,
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = st->pdl ? 1 : 0;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    if (P.upcat) cudaLaunchKernelEx(&cfg, conv_tc_kernel<5, true>, P.tmA, P.tmW, P.tmO, p);
-    else cudaLaunchKernelEx(&cfg, conv_tc_kernel<15, false>, P.tmA, P.tmW, P.tmO, p);
+    if (P.upcat && !P.small) cudaLaunchKernelEx(&cfg, conv_tc_kernel<5, true, kEpiWarpsLarge, kProducerWarpsLarge>, P.tmA, P.tmW, P.tmO, p);
+    else if (P.upcat) cudaLaunchKernelEx(&cfg, conv_tc_kernel<5, true, kEpiWarpsSmall, kProducerWarpsSmall>, P.tmA, P.tmW, P.tmO, p);
+    else if (!P.small) cudaLaunchKernelEx(&cfg, conv_tc_kernel<15, false, kEpiWarpsLarge, 0>, P.tmA, P.tmW, P.tmO, p);
+    else cudaLaunchKernelEx(&cfg, conv_tc_kernel<15, false, kEpiWarpsSmall, 0>, P.tmA, P.tmW, P.tmO, p);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return tc_fail("conv_tc level %d launch failed: %s", i, cudaGetErrorString(e));
     return 0;
