@@ -5,7 +5,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libwunet_b200.so")
+SO_PATH = os.environ.get("WUNET_LIB_PATH") or os.path.join(_HERE, "libwunet_b200.so")   # env: development builds (tracing)
 
 PREC_FP32 = 0
 PREC_BF16 = 1

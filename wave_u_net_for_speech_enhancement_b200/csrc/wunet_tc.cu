@@ -581,6 +581,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // for the shared-memory stage.
         const int pt = (warp - kFirstProducer) * 32 + lane;
         int sa = 0, pa = 0;
+        int tr4 = 0; (void)tr4;
         uint4 xr[10];
         bool pref = false;
         const int nruns = (p.rows_used + 15) >> 4;
@@ -639,7 +640,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int c = 0; c < p.nchunks; ++c) {
                 const bool fast = unit_fast(c);
                 if (fast && !pref) fetch(b0, l0, c, pt);
+                if (pt == 0) TRACE(4, tr4);
                 mbar_wait(a_empty + 8 * sa, pa ^ 1);
+                if (pt == 0) TRACE(4, tr4);
                 const ChunkInfo cu = chunk_info<UPCAT>(p, c);
                 if (cu.up) {
                     const int nvec = cu.nk * 2;                              // 16-byte vectors per row
@@ -697,6 +700,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor core reads
                 }
                 __syncwarp();
+                if (pt == 0) TRACE(4, tr4);
                 if (lane == 0) mbar_arrive(a_full + 8 * sa);
                 if (++sa == p.na) { sa = 0; pa ^= 1; }
             }
@@ -962,8 +966,8 @@ int tc_set_weights(TcState **pst, int n, int ci, const TcBlockSrc *blocks, int n
 #ifdef WUNET_TC_TRACE
         if (const char *tl = getenv("WUNET_TC_TRACE_LEVEL")) {
             st->trace_level = atoi(tl);
-            cudaMalloc(&st->trace, 4 * 512 * sizeof(long long));
-            cudaMemset(st->trace, 0, 4 * 512 * sizeof(long long));
+            cudaMalloc(&st->trace, 5 * 512 * sizeof(long long));
+            cudaMemset(st->trace, 0, 5 * 512 * sizeof(long long));
         }
 #endif
         *pst = st;
@@ -1422,13 +1426,13 @@ void tc_destroy(TcState *st)
         for (int i = 0; i < 8; ++i) { cudaEventDestroy(st->ev_in[i]); cudaEventDestroy(st->ev_out[i]); }
     }
     if (st->trace) {
-        std::vector<long long> h(4 * 512);
+        std::vector<long long> h(5 * 512);
         cudaDeviceSynchronize();
         cudaMemcpy(h.data(), st->trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
         long long t0 = h[512];
-        for (int r = 0; r < 4; ++r) {
+        for (int r = 0; r < 5; ++r) {
             fprintf(stderr, "[trace role %d]", r);
-            for (int i = 0; i < 140 && h[r * 512 + i]; ++i) fprintf(stderr, " %lld", h[r * 512 + i] - t0);
+            for (int i = 0; i < 200 && h[r * 512 + i]; ++i) fprintf(stderr, " %lld", h[r * 512 + i] - t0);
             fprintf(stderr, "\n");
         }
         cudaFree(st->trace);
