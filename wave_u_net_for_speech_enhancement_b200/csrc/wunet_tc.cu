@@ -167,6 +167,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void st_shared_v4_if(uint32_t addr, const uint4 &v, bool pred)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t@p st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n\t}"
+                 ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"((uint32_t)pred) : "memory");
+}
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b)
 {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -604,7 +609,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 xr[qq] = chok ? __ldg(reinterpret_cast<const uint4 *>(pb + (size_t)m * p.Cin0)) : make_uint4(0u, 0u, 0u, 0u);
             }
         };
-        // interpolate + store the 16 rows of one item from the register window
+        // interpolate + store the 16 rows of one item from the register window. Straight-line code (masks and a predicated
+        // store instead of branches): the 16 rows are independent, and a branch per row serialises their dependent chains
+        // (trace: ~3600 cycles per item with branches, the stage hand-off was waiting on it).
         auto emit = [&](uint8_t *dst, int l0, int c, int item, const uint4 (&w)[10]) {
             const ChunkInfo u = chunk_info<UPCAT>(p, c);
             const int nvec = u.nk * 2;
@@ -613,25 +620,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int lstart = l0 - PAD + 16 * run;                            // even
             const int ms = lstart >> 1;
             const bool chok = ch < p.Cin0;
+            const float lf0 = (float)lstart, mf0 = (float)(ms - 1);            // small integers: exact in fp32
+            const uint32_t drow = smem_u32(dst) + (uint32_t)(16 * run) * 128u;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                const int row = 16 * run + j;
-                if (row >= p.rows_used) break;
                 const int l = lstart + j;
-                uint4 o = make_uint4(0u, 0u, 0u, 0u);
-                if (chok && l >= 0 && l < p.L) {
-                    const int qa = (j >> 1) + (j & 1);
-                    // out = a + lam1 * (b - a) in packed bf16 (HFMA2)
-                    const float lam1 = p.up_scale * (float)l - (float)(ms - 1 + qa);
-                    const __nv_bfloat162 lam = __float2bfloat162_rn(lam1);
-                    const __nv_bfloat162 *a2 = reinterpret_cast<const __nv_bfloat162 *>(&w[qa]);
-                    const __nv_bfloat162 *b2 = reinterpret_cast<const __nv_bfloat162 *>(&w[qa + 1]);
-                    __nv_bfloat162 r2[4];
+                const int qa = (j >> 1) + (j & 1);
+                // out = a + lam1 * (b - a) in packed bf16 (HFMA2); lam1 = up_scale * l - (ms - 1 + qa), one fused rounding
+                const float lam1 = fmaf(p.up_scale, lf0 + (float)j, -(mf0 + (float)qa));
+                const __nv_bfloat162 lam = __float2bfloat162_rn(lam1);
+                const __nv_bfloat162 *a2 = reinterpret_cast<const __nv_bfloat162 *>(&w[qa]);
+                const __nv_bfloat162 *b2 = reinterpret_cast<const __nv_bfloat162 *>(&w[qa + 1]);
+                __nv_bfloat162 r2[4];
 #pragma unroll
-                    for (int q4 = 0; q4 < 4; ++q4) r2[q4] = __hfma2(lam, __hsub2(b2[q4], a2[q4]), a2[q4]);
-                    o = *reinterpret_cast<const uint4 *>(r2);
-                }
-                *reinterpret_cast<uint4 *>(dst + row * 128 + ((vec ^ (row & 7)) << 4)) = o;
+                for (int q4 = 0; q4 < 4; ++q4) r2[q4] = __hfma2(lam, __hsub2(b2[q4], a2[q4]), a2[q4]);
+                uint4 o = *reinterpret_cast<const uint4 *>(r2);
+                const uint32_t keep = (chok && (unsigned)l < (unsigned)p.L) ? 0xffffffffu : 0u;   // zero rows = Conv1d padding
+                o.x &= keep; o.y &= keep; o.z &= keep; o.w &= keep;
+                // predicated (not branched) 16-byte store; (16 * run + j) & 7 == j & 7
+                st_shared_v4_if(drow + (uint32_t)(j * 128 + ((vec ^ (j & 7)) << 4)), o, 16 * run + j < p.rows_used);
             }
         };
         for (int tile = first_tile; tile < total_tiles; tile += gridDim.x) {
@@ -644,6 +651,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_wait(a_empty + 8 * sa, pa ^ 1);
                 if (pt == 0) TRACE(4, tr4);
                 const ChunkInfo cu = chunk_info<UPCAT>(p, c);
+                bool emitted_fast = false;
                 if (cu.up) {
                     const int nvec = cu.nk * 2;                              // 16-byte vectors per row
                     uint8_t *dst = base_ptr + sm.a + sa * p.a_stage_bytes;
@@ -655,19 +663,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             emit(dst, l0, c, itx, xr);
                         }
                         pref = false;
-                        // next upsampled unit of this CTA (K-loop order): prefetch its first-round item
-                        int nt = tile, nc = c + 1;
-                        for (int hop = 0; hop < p.nchunks; ++hop) {
-                            if (nc >= p.nchunks) { nc = 0; nt += gridDim.x; }
-                            if (chunk_info<UPCAT>(p, nc).up) break;
-                            ++nc;
-                        }
-                        if (nt < total_tiles && unit_fast(nc)) {
-                            int nb0, nl0, nn0;
-                            tile_coords(nt, nb0, nl0, nn0);
-                            fetch(nb0, nl0, nc, pt);
-                            pref = true;
-                        }
+                        emitted_fast = true;
                     } else {
                         // frames shorter than a tile (packed): generic per-(row, vector) path, ATen index math in fp32
                         const int items = p.rows_used * nvec;
@@ -703,6 +699,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (pt == 0) TRACE(4, tr4);
                 if (lane == 0) mbar_arrive(a_full + 8 * sa);
                 if (++sa == p.na) { sa = 0; pa ^= 1; }
+                if (emitted_fast) {
+                    // next upsampled unit of this CTA (K-loop order): prefetch its first-round item. Issued AFTER the hand-off:
+                    // fence.proxy.async compiles to MEMBAR.ALL.CTA, which would otherwise hold the arrive back until these
+                    // loads have returned (trace: ~1900 cycles per unit).
+                    int nt = tile, nc = c + 1;
+                    for (int hop = 0; hop < p.nchunks; ++hop) {
+                        if (nc >= p.nchunks) { nc = 0; nt += gridDim.x; }
+                        if (chunk_info<UPCAT>(p, nc).up) break;
+                        ++nc;
+                    }
+                    if (nt < total_tiles && unit_fast(nc)) {
+                        int nb0, nl0, nn0;
+                        tile_coords(nt, nb0, nl0, nn0);
+                        fetch(nb0, nl0, nc, pt);
+                        pref = true;
+                    }
+                }
             }
         }
     }
