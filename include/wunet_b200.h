@@ -128,6 +128,17 @@ int wunet_profile_read(wunet_ctx *ctx, float *ms, int capacity, int *count);
 /* Number of kernel launches the last wunet_forward()/wunet_forward_host() enqueued. */
 int wunet_last_launch_count(const wunet_ctx *ctx);
 
+/* Introspection for tests and tuning, host-only (needs no GPU, no context): the tiling the bf16 path would use for conv
+ * block `block` (1 .. 2*n_layers; block 0 = first encoder runs on CUDA cores) at batch B, frame length T, on a device with
+ * num_sms SMs. No reference counterpart. Writes 32 ints:
+ *  [0] L  [1] Cin0  [2] Cin1  [3] Cout  [4] Npad  [5] N per CTA  [6] column splits  [7] TMEM column stride  [8] MT (128-row
+ *  sub-tiles per tile)  [9] accumulator buffers  [10] packed frames  [11] frames per tile  [12] rows per packed frame
+ *  [13] M tiles  [14] K chunks  [15] weights resident  [16] TMA-store epilogue  [17] input stages  [18] weight stages
+ *  [19] taps per weight stage  [20] weight stages per chunk  [21] input stage bytes  [22] weight stage bytes
+ *  [23] TMA bytes per input chunk  [24] input rows used  [25] TMEM columns  [26] dynamic shared memory bytes
+ *  [27] threads per CTA  [28] CTAs per SM  [29] grid  [30] small (two-CTAs-per-SM) flavour  [31] tiles per frame */
+int wunet_debug_plan(int n_layers, int channels_interval, int B, int T, int block, int num_sms, int *fields, int capacity);
+
 #ifdef __cplusplus
 }
 #endif

@@ -47,6 +47,7 @@ def load() -> ctypes.CDLL:
     lib.wunet_last_launch_count.argtypes = [vp]
     lib.wunet_profile_enable.argtypes = [vp, ci]
     lib.wunet_profile_read.argtypes = [vp, vp, ci, ctypes.POINTER(ci)]
+    lib.wunet_debug_plan.argtypes = [ci, ci, ci, ci, ci, ci, ctypes.POINTER(ci), ci]
     _lib = lib
     return lib
 
@@ -59,5 +60,16 @@ def check(rc: int) -> None:
 EXPORTED_SYMBOLS = [
     "wunet_version", "wunet_last_error", "wunet_create", "wunet_destroy", "wunet_num_blocks", "wunet_block_shape",
     "wunet_set_weights", "wunet_workspace_bytes", "wunet_forward", "wunet_forward_host", "wunet_stream_submit", "wunet_stream_wait", "wunet_read_level",
-    "wunet_last_launch_count", "wunet_profile_enable", "wunet_profile_read",
+    "wunet_last_launch_count", "wunet_profile_enable", "wunet_profile_read", "wunet_debug_plan",
 ]
+
+PLAN_FIELDS = ["L", "Cin0", "Cin1", "Cout", "Npad", "Nh", "nsplit", "Nstride", "MT", "nacc", "packed", "FR", "S", "m_tiles",
+               "nchunks", "resident", "bulk_store", "na", "nb", "tg", "ngroups", "a_stage_bytes", "b_stage_bytes", "a_tx_bytes",
+               "rows_used", "tmem_cols", "smem", "threads", "per_sm", "grid", "small", "tiles_per_frame"]
+
+
+def debug_plan(n_layers: int, channels_interval: int, B: int, T: int, block: int, num_sms: int = 148) -> dict:
+    """The tiling the bf16 path would choose for one conv block (host-only query: works without a GPU)."""
+    buf = (ctypes.c_int * 32)()
+    check(load().wunet_debug_plan(n_layers, channels_interval, B, T, block, num_sms, buf, 32))
+    return dict(zip(PLAN_FIELDS, [int(v) for v in buf]))

@@ -444,6 +444,21 @@ int wunet_read_level(wunet_ctx *c, int block, const void *workspace, int B, int 
 
 int wunet_last_launch_count(const wunet_ctx *c) { return c ? c->last_launches : 0; }
 
+int wunet_debug_plan(int n_layers, int channels_interval, int B, int T, int block, int num_sms, int *fields, int capacity)
+{
+    if (n_layers < 1 || n_layers > 16 || channels_interval < 1 || B < 1 || T < 1 || (T % (1 << n_layers)) != 0 || num_sms < 1)
+        return fail(WUNET_EINVAL, "bad plan query");
+    const int n = n_layers, ci = channels_interval;
+    std::vector<TcBlockSrc> src;            // same channel plan as wunet_create (model/unet_basic.py:38-39, :52-57, :59-62)
+    for (int i = 0; i < n; ++i) src.push_back(TcBlockSrc{i == 0 ? 1 : i * ci, (i + 1) * ci, 15, nullptr, nullptr, nullptr});
+    src.push_back(TcBlockSrc{n * ci, n * ci, 15, nullptr, nullptr, nullptr});
+    for (int j = 0; j < n; ++j)
+        src.push_back(TcBlockSrc{j == 0 ? 2 * n * ci : (2 * (n - j) + 1) * ci, (n - j) * ci, 5, nullptr, nullptr, nullptr});
+    if (tc_debug_plan(n, ci, src.data(), (int)src.size(), B, T, block, num_sms, fields, capacity))
+        return fail(WUNET_EINVAL, "%s", tc_error());
+    return WUNET_OK;
+}
+
 int wunet_profile_enable(wunet_ctx *c, int enable)
 {
     if (!c) return fail(WUNET_EINVAL, "null context");

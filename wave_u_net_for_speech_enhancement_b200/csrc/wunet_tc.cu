@@ -956,6 +956,21 @@ size_t tc_workspace_bytes(int n, int ci, int B, int T)
     return total;
 }
 
+// K segments and padded sizes of every block: encoders have one input segment, decoder block i concatenates the previous
+// block's (upsampled) output with the skip of encoder 2n - i (model/unet_basic.py:93-95)
+static void derive_levels(std::vector<TcLevel> &levels, const TcBlockSrc *blocks, int nblocks, int n)
+{
+    for (int i = 0; i < nblocks; ++i) {
+        TcLevel &lv = levels[i];
+        lv.cout = blocks[i].cout; lv.k = blocks[i].k;
+        if (i <= n) { lv.cin0 = blocks[i].cin; lv.cin1 = 0; }
+        else { lv.cin0 = levels[i - 1].cout; lv.cin1 = blocks[i].cin - lv.cin0; }
+        lv.Npad = round_up(lv.cout, 16);
+        lv.Ktot = round_up(lv.cin0, 64) + (lv.cin1 ? round_up(lv.cin1, 64) : 0);
+        lv.w_src = blocks[i].w; lv.scale = blocks[i].scale; lv.shift = blocks[i].shift;
+    }
+}
+
 int tc_set_weights(TcState **pst, int n, int ci, const TcBlockSrc *blocks, int nblocks, const float *out_w,
                    const float *out_b, cudaStream_t stream)
 {
@@ -987,15 +1002,7 @@ int tc_set_weights(TcState **pst, int n, int ci, const TcBlockSrc *blocks, int n
     }
     st->out_w = out_w; st->out_b = out_b;
     st->plan_ws = nullptr;                               // weights moved: rebuild maps lazily
-    for (int i = 0; i < nblocks; ++i) {
-        TcLevel &lv = st->levels[i];
-        lv.cout = blocks[i].cout; lv.k = blocks[i].k;
-        if (i <= n) { lv.cin0 = blocks[i].cin; lv.cin1 = 0; }
-        else { lv.cin0 = st->levels[i - 1].cout; lv.cin1 = blocks[i].cin - lv.cin0; }
-        lv.Npad = round_up(lv.cout, 16);
-        lv.Ktot = round_up(lv.cin0, 64) + (lv.cin1 ? round_up(lv.cin1, 64) : 0);
-        lv.w_src = blocks[i].w; lv.scale = blocks[i].scale; lv.shift = blocks[i].shift;
-    }
+    derive_levels(st->levels, blocks, nblocks, n);
     if (ci % 8 != 0 || ci > 32) return 0;                // tensor-core path unsupported for this plan; forward reports it
     for (int i = 1; i < nblocks; ++i) {                  // enc0 runs on CUDA cores from the fp32 weights
         TcLevel &lv = st->levels[i];
@@ -1041,6 +1048,196 @@ static int make_map(TcState *st, CUtensorMap *m, const void *base, uint64_t d0, 
     return 0;
 }
 
+// Tiling decision for conv block i: pure host logic (no CUDA calls), so that tests can exercise it without a GPU
+// (wunet_debug_plan). Fills every tiling field of P.p and the launch shape; pointers and tensor maps are added by build_plan.
+static int plan_block(const TcLevel &lv, int i, int n, int B, int T, int num_sms, const std::string &ovr, TcPlanLevel &P)
+{
+    TcParams &p = P.p;
+    memset(&p, 0, sizeof(p));
+    const bool dec = i > n;
+    const int KS = lv.k;
+    const int L = (i <= n) ? (T >> i) : (T >> (2 * n - i));
+    P.upcat = dec;
+    p.B = B; p.L = L; p.Cout = lv.cout; p.T = T;
+    p.Cin0 = lv.cin0; p.Cin1 = lv.cin1;
+    p.nchunks0 = (lv.cin0 + 63) / 64;
+    p.nchunks = p.nchunks0 + (lv.cin1 + 63) / 64;
+    p.Npad = lv.Npad;
+    {
+        // K-loop order. Encoders: natural. Decoders: full upsampled chunks, then the skip chunks (TMA), then the partial
+        // upsampled chunk: a TMA chunk is never preceded by a short chunk, so its load latency hides behind MMAs.
+        int k = 0;
+        if (!dec) { for (int c = 0; c < p.nchunks; ++c) p.chunk_map[k++] = (unsigned char)c; }
+        else {
+            const int nfull0 = lv.cin0 / 64, n1 = p.nchunks - p.nchunks0;
+            if (nfull0 == 0) {
+                // the only upsampled chunk is partial (e.g. the last decoder: 48 + 24 channels): produce it FIRST, so that its
+                // shared-memory stage is released half a tile before the producers need it again
+                p.chunk_map[k++] = (unsigned char)0x80;
+                for (int c = 0; c < n1; ++c) p.chunk_map[k++] = (unsigned char)c;
+            } else {
+                for (int c = 0; c < nfull0; ++c) p.chunk_map[k++] = (unsigned char)(0x80 | c);
+                for (int c = 0; c < n1; ++c) p.chunk_map[k++] = (unsigned char)c;
+                if (nfull0 < p.nchunks0) p.chunk_map[k++] = (unsigned char)(0x80 | nfull0);
+            }
+        }
+        if (p.nchunks > 16) return tc_fail("too many K chunks");
+    }
+    // ---- tiling ---------------------------------------------------------------------------------
+    TcOverride ov = parse_override(ovr, i);
+    if (!ov.any && B >= 128)
+        for (const TunedTiling &t : kTuned)
+            if (t.L == L && t.cin0 == lv.cin0 && t.cin1 == lv.cin1 && t.cout == lv.cout && t.k == KS) parse_kv(t.kv, ov);
+    const bool small = ov.small > 0;
+    const int smem_limit = small ? kSmemLimitSmall : kSmemLimit;
+    const int tmem_limit = small ? 256 : 512;
+    P.small = small;
+    const bool packed = L < 128 || (ov.packed > 0 && L + KS - 1 <= 256);
+    auto geometry = [&](int MT, int nsplit) {
+        p.nsplit = nsplit;
+        p.Nh = nsplit == 1 ? lv.Npad : round_up((lv.Npad + nsplit - 1) / nsplit, 16);
+        p.Nstride = round_up(p.Nh, 32);
+        p.MT = MT;
+        if (!packed) {
+            p.packed = 0;
+            p.tiles_per_frame = (L + 128 * MT - 1) / (128 * MT);
+            const int rows = 128 * MT + KS - 1;
+            p.nops = (rows + 255) / 256;
+            p.R1 = round_up((rows + p.nops - 1) / p.nops, 8);
+            p.S = 0; p.FR = 1;
+            p.rows_used = rows;
+            p.a_stage_bytes = (uint32_t)round_up(p.nops * p.R1 * 128, 1024);
+            p.a_tx_bytes = p.nops * p.R1 * 128;
+            p.m_tiles = B * p.tiles_per_frame;
+        } else {
+            p.packed = 1;
+            p.S = L + KS - 1;
+            int FR = (128 * MT - L) / p.S + 1;
+            if (FR > B) FR = B;
+            if (FR > 256) FR = 256;
+            p.FR = FR;
+            p.tiles_per_frame = 0;
+            p.nops = 1; p.R1 = p.S;
+            p.rows_used = FR * p.S;
+            const int rows_alloc = round_up(std::max(FR * p.S, 128 * MT + KS - 1), 8);
+            p.a_stage_bytes = (uint32_t)round_up(rows_alloc * 128, 1024);
+            p.a_tx_bytes = FR * p.S * 128;
+            p.m_tiles = (B + FR - 1) / FR;
+        }
+        p.nacc = (ov.nacc != 1 && 2 * MT * p.Nstride <= tmem_limit) ? 2 : 1;
+        uint32_t cols = 32;
+        while ((int)cols < p.nacc * MT * p.Nstride) cols <<= 1;
+        p.tmem_cols = cols;
+    };
+    const int base_split = lv.Npad > 256 ? 2 : 1;
+    const int ns_sel = ov.ns > 0 ? ov.ns : base_split;
+    if (!packed) {
+        const int ns32 = round_up(ns_sel == 1 ? lv.Npad : round_up((lv.Npad + ns_sel - 1) / ns_sel, 16), 32);
+        int MT;
+        if (small) {
+            MT = ns32 <= 64 ? 2 : 1;       // 256 TMEM columns per CTA: double-buffered accumulators up to N = 128
+        } else if (ns32 <= 64) MT = 4;     // 2 x 4 x 64 TMEM columns: double-buffered accumulators (MT=2 measured 40 % slower on dec10/dec11)
+        else if (ns32 <= 96) MT = 2;       // 2 x 2 x 96
+        else if (ns32 <= 128) MT = 2;      // 2 x 2 x 128 columns: double-buffered accumulators beat the bigger MT=4 tile (73 vs 105 us on enc4)
+        else MT = dec ? 2 : 1;             // N > 128: encoders gain from double buffering at MT=1 (enc5: 60 vs 74 us); decoders do not
+        if (ov.mt > 0) MT = ov.mt;
+        while (MT > 1 && 128 * MT > L) --MT;
+        geometry(MT, ns_sel);
+    } else if (ov.mt > 0 || ov.ns > 0) {
+        geometry(ov.mt > 0 ? ov.mt : 1, ns_sel);
+    } else {
+        // bottom of the U: few tiles, long K loops. ONE wave of tiles (a second, partial wave costs a whole tile time:
+        // 172 tiles on 148 SMs measured 30-60 % slower than 129), the smallest M tile that allows it, and as many
+        // column splits as still fit in that wave (each CTA then streams a smaller share of the weights from L2).
+        int MT = 1, ns = base_split;
+        geometry(MT, ns);
+        while (p.m_tiles * ns > num_sms && MT < 4 && (MT + 1) * p.Nstride <= tmem_limit) geometry(++MT, ns);
+        const int m_tiles = p.m_tiles;
+        for (int cand : {2, 3, 4, 6}) {
+            if (cand <= ns) continue;
+            const int nh = round_up((lv.Npad + cand - 1) / cand, 16);
+            if (m_tiles * cand <= num_sms && nh >= 48 && (cand - 1) * nh < lv.Npad) ns = cand;
+        }
+        geometry(MT, ns);
+    }
+    if ((int)p.tmem_cols > tmem_limit) return tc_fail("level %d: %u TMEM columns exceed %d", i, p.tmem_cols, tmem_limit);
+    if (p.Nh > 256) return tc_fail("level %d: N per CTA %d exceeds 256", i, p.Nh);
+    if ((p.nsplit - 1) * p.Nh >= lv.Npad) return tc_fail("level %d: %d column splits of %d leave an empty split", i, p.nsplit, p.Nh);
+    // epilogue store mode (needs complete tiles of complete rows per warp)
+    p.bulk_store = 0;
+    p.n_epi = small ? kEpiWarpsSmall : kEpiWarpsLarge;
+    p.resident = 0;
+    const int ring_budget = smem_limit - 2048 - p.Npad * 8 - 512;
+    if (!packed && p.nsplit == 1 && ov.res != 0) {
+        // weights-resident mode: if the block's packed weights fit in shared memory next to the input ring, the persistent
+        // CTA loads them once instead of re-streaming them from L2 for every tile (the L2->SM stream, not HBM and not the
+        // tensor pipe, is what bounds the shallow blocks otherwise).
+        const int mt_pref = p.MT;
+        for (int MT = mt_pref; MT >= std::max(1, mt_pref / (dec ? 1 : 2)) && !p.resident; MT >>= 1) {
+            geometry(MT, 1);
+            const int stage = round_up(p.Nh * 128 * KS, 1024);
+            const int wbytes = p.nchunks * stage;
+            const int na = ov.na > 0 ? ov.na : ((dec && p.nchunks >= 3) ? 3 : 2);
+            if (na * (int)p.a_stage_bytes + wbytes <= ring_budget) {
+                p.resident = 1; p.na = na; p.tg = KS; p.ngroups = 1;
+                p.b_stage_bytes = (uint32_t)stage;
+                p.nb = p.nchunks * p.ngroups;
+            }
+        }
+        if (!p.resident) geometry(mt_pref, 1);
+    }
+    if (!p.resident) {
+        // A ring depth: decoders whose K chunks are short (5 taps, few K-steps) need the TMA/producers to run two chunks
+        // ahead; everything else double-buffers. Weight stages hold `tg` consecutive taps (one TMA box, one handshake).
+        const int na_want = ov.na > 0 ? ov.na : ((dec && !packed && p.nchunks >= 3 && p.MT <= 2) ? 3 : 2);
+        bool ok = false;
+        for (int na = na_want; na >= 1 && !ok; --na) {
+            for (int tg = (ov.tg > 0 ? std::min(KS, ov.tg) : KS); tg >= 1; --tg) {
+                // every stage handshake costs a ~400-cycle tensor-pipe bubble (trace): prefer the fattest stage
+                // (most taps per handshake) that still leaves a 2-deep ring; taps past KS in the last group are zero-filled
+                const int stage = round_up(p.Nh * 128 * tg, 1024);
+                const int min_stages = 2;
+                if (na * (int)p.a_stage_bytes + min_stages * stage > ring_budget) continue;
+                p.na = na; p.tg = tg;
+                p.ngroups = (KS + tg - 1) / tg;
+                p.b_stage_bytes = (uint32_t)stage;
+                int nb = (ring_budget - na * (int)p.a_stage_bytes) / stage;
+                if (nb > kMaxBStages) nb = kMaxBStages;
+                p.nb = nb;
+                ok = true;
+                break;
+            }
+        }
+        if (!ok) return tc_fail("level %d does not fit in shared memory", i);
+        if (ov.any && p.na < 2) return tc_fail("level %d: override leaves a single input stage", i);
+    }
+    if (!packed && p.nsplit == 1 && ov.bulk != 0 && i != 2 * n && (L % (128 * p.MT) == 0) && (long long)B * L < (1LL << 31)) {
+        // TMA-store epilogue if the slabs fit without giving up ring depth / residency / tile size
+        const int need = p.n_epi * 2048 + 1024;
+        const int min_nb = p.resident ? p.nb : (p.tg == 1 ? 4 : 2);
+        while ((int)smem_total(p) + need > smem_limit && !p.resident && p.nb > min_nb) --p.nb;
+        if ((int)smem_total(p) + need <= smem_limit) p.bulk_store = 1;
+    }
+    {
+        const int threads = 64 + 32 * (small ? kEpiWarpsSmall + (dec ? kProducerWarpsSmall : 0)
+                                             : kEpiWarpsLarge + (dec ? kProducerWarpsLarge : 0));
+        const int per_sm = std::max(1, std::min({(int)((228 * 1024) / (smem_total(p) + 1024)), (int)(512 / p.tmem_cols), 2048 / threads}));
+        const int total_tiles = p.m_tiles * p.nsplit;
+        p.tile_begin = 0; p.tile_end = total_tiles;
+        P.per_sm = per_sm;
+        P.grid = dim3((unsigned)std::min(total_tiles, num_sms * per_sm), 1, 1);
+        P.threads = threads;
+    }
+    P.smem = smem_total(p);
+    if (P.smem > (size_t)kSmemLimit) return tc_fail("level %d: smem %zu too large", i, P.smem);
+
+    const bool last_block = (i == 2 * n);
+    if (last_block && lv.cout > 32) return tc_fail("fused head needs channels_interval <= 32");
+    if (last_block && p.packed) return tc_fail("bf16 path needs frames of at least 128 samples (T=%d): the fused head works on full frames", T);
+    if (last_block && p.nsplit != 1) return tc_fail("fused head needs the whole channel range in one CTA");
+    return 0;
+}
+
 static int build_plan(TcState *st, const float *x, float *y, int B, int T, void *ws)
 {
     const int n = st->n;
@@ -1053,193 +1250,16 @@ static int build_plan(TcState *st, const float *x, float *y, int B, int T, void 
     for (int i = 1; i < 2 * n + 1; ++i) {
         const TcLevel &lv = st->levels[i];
         TcPlanLevel &P = pl.lv[i];
+        if (plan_block(lv, i, n, B, T, st->num_sms, st->plan_ovr, P)) return -1;
         TcParams &p = P.p;
-        memset(&p, 0, sizeof(p));
         const bool dec = i > n;
-        const int KS = lv.k;
-        const int L = (i <= n) ? (T >> i) : (T >> (2 * n - i));
-        P.upcat = dec;
-        p.B = B; p.L = L; p.Cout = lv.cout; p.T = T;
-        p.Cin0 = lv.cin0; p.Cin1 = lv.cin1;
-        p.nchunks0 = (lv.cin0 + 63) / 64;
-        p.nchunks = p.nchunks0 + (lv.cin1 + 63) / 64;
-        p.Npad = lv.Npad;
-        {
-            // K-loop order. Encoders: natural. Decoders: full upsampled chunks, then the skip chunks (TMA), then the partial
-            // upsampled chunk: a TMA chunk is never preceded by a short chunk, so its load latency hides behind MMAs.
-            int k = 0;
-            if (!dec) { for (int c = 0; c < p.nchunks; ++c) p.chunk_map[k++] = (unsigned char)c; }
-            else {
-                const int nfull0 = lv.cin0 / 64, n1 = p.nchunks - p.nchunks0;
-                if (nfull0 == 0) {
-                    // the only upsampled chunk is partial (e.g. the last decoder: 48 + 24 channels): produce it FIRST, so that its
-                    // shared-memory stage is released half a tile before the producers need it again
-                    p.chunk_map[k++] = (unsigned char)0x80;
-                    for (int c = 0; c < n1; ++c) p.chunk_map[k++] = (unsigned char)c;
-                } else {
-                    for (int c = 0; c < nfull0; ++c) p.chunk_map[k++] = (unsigned char)(0x80 | c);
-                    for (int c = 0; c < n1; ++c) p.chunk_map[k++] = (unsigned char)c;
-                    if (nfull0 < p.nchunks0) p.chunk_map[k++] = (unsigned char)(0x80 | nfull0);
-                }
-            }
-            if (p.nchunks > 16) return tc_fail("too many K chunks");
-        }
-        // ---- tiling ---------------------------------------------------------------------------------
-        TcOverride ov = parse_override(st->plan_ovr, i);
-        if (!ov.any && B >= 128)
-            for (const TunedTiling &t : kTuned)
-                if (t.L == L && t.cin0 == lv.cin0 && t.cin1 == lv.cin1 && t.cout == lv.cout && t.k == KS) parse_kv(t.kv, ov);
-        const bool small = ov.small > 0;
-        const int smem_limit = small ? kSmemLimitSmall : kSmemLimit;
-        const int tmem_limit = small ? 256 : 512;
-        P.small = small;
-        const bool packed = L < 128 || (ov.packed > 0 && L + KS - 1 <= 256);
-        auto geometry = [&](int MT, int nsplit) {
-            p.nsplit = nsplit;
-            p.Nh = nsplit == 1 ? lv.Npad : round_up((lv.Npad + nsplit - 1) / nsplit, 16);
-            p.Nstride = round_up(p.Nh, 32);
-            p.MT = MT;
-            if (!packed) {
-                p.packed = 0;
-                p.tiles_per_frame = (L + 128 * MT - 1) / (128 * MT);
-                const int rows = 128 * MT + KS - 1;
-                p.nops = (rows + 255) / 256;
-                p.R1 = round_up((rows + p.nops - 1) / p.nops, 8);
-                p.S = 0; p.FR = 1;
-                p.rows_used = rows;
-                p.a_stage_bytes = (uint32_t)round_up(p.nops * p.R1 * 128, 1024);
-                p.a_tx_bytes = p.nops * p.R1 * 128;
-                p.m_tiles = B * p.tiles_per_frame;
-            } else {
-                p.packed = 1;
-                p.S = L + KS - 1;
-                int FR = (128 * MT - L) / p.S + 1;
-                if (FR > B) FR = B;
-                if (FR > 256) FR = 256;
-                p.FR = FR;
-                p.tiles_per_frame = 0;
-                p.nops = 1; p.R1 = p.S;
-                p.rows_used = FR * p.S;
-                const int rows_alloc = round_up(std::max(FR * p.S, 128 * MT + KS - 1), 8);
-                p.a_stage_bytes = (uint32_t)round_up(rows_alloc * 128, 1024);
-                p.a_tx_bytes = FR * p.S * 128;
-                p.m_tiles = (B + FR - 1) / FR;
-            }
-            p.nacc = (ov.nacc != 1 && 2 * MT * p.Nstride <= tmem_limit) ? 2 : 1;
-            uint32_t cols = 32;
-            while ((int)cols < p.nacc * MT * p.Nstride) cols <<= 1;
-            p.tmem_cols = cols;
-        };
-        const int base_split = lv.Npad > 256 ? 2 : 1;
-        const int ns_sel = ov.ns > 0 ? ov.ns : base_split;
-        if (!packed) {
-            const int ns32 = round_up(ns_sel == 1 ? lv.Npad : round_up((lv.Npad + ns_sel - 1) / ns_sel, 16), 32);
-            int MT;
-            if (small) {
-                MT = ns32 <= 64 ? 2 : 1;       // 256 TMEM columns per CTA: double-buffered accumulators up to N = 128
-            } else if (ns32 <= 64) MT = 4;     // 2 x 4 x 64 TMEM columns: double-buffered accumulators (MT=2 measured 40 % slower on dec10/dec11)
-            else if (ns32 <= 96) MT = 2;       // 2 x 2 x 96
-            else if (ns32 <= 128) MT = 2;      // 2 x 2 x 128 columns: double-buffered accumulators beat the bigger MT=4 tile (73 vs 105 us on enc4)
-            else MT = dec ? 2 : 1;             // N > 128: encoders gain from double buffering at MT=1 (enc5: 60 vs 74 us); decoders do not
-            if (ov.mt > 0) MT = ov.mt;
-            while (MT > 1 && 128 * MT > L) --MT;
-            geometry(MT, ns_sel);
-        } else if (ov.mt > 0 || ov.ns > 0) {
-            geometry(ov.mt > 0 ? ov.mt : 1, ns_sel);
-        } else {
-            // bottom of the U: few tiles, long K loops. ONE wave of tiles (a second, partial wave costs a whole tile time:
-            // 172 tiles on 148 SMs measured 30-60 % slower than 129), the smallest M tile that allows it, and as many
-            // column splits as still fit in that wave (each CTA then streams a smaller share of the weights from L2).
-            int MT = 1, ns = base_split;
-            geometry(MT, ns);
-            while (p.m_tiles * ns > st->num_sms && MT < 4 && (MT + 1) * p.Nstride <= tmem_limit) geometry(++MT, ns);
-            const int m_tiles = p.m_tiles;
-            for (int cand : {2, 3, 4, 6}) {
-                if (cand <= ns) continue;
-                const int nh = round_up((lv.Npad + cand - 1) / cand, 16);
-                if (m_tiles * cand <= st->num_sms && nh >= 48 && (cand - 1) * nh < lv.Npad) ns = cand;
-            }
-            geometry(MT, ns);
-        }
-        if ((int)p.tmem_cols > tmem_limit) return tc_fail("level %d: %u TMEM columns exceed %d", i, p.tmem_cols, tmem_limit);
-        if (p.Nh > 256) return tc_fail("level %d: N per CTA %d exceeds 256", i, p.Nh);
-        if ((p.nsplit - 1) * p.Nh >= lv.Npad) return tc_fail("level %d: %d column splits of %d leave an empty split", i, p.nsplit, p.Nh);
-        // epilogue store mode (needs complete tiles of complete rows per warp)
-        p.bulk_store = 0;
-        p.n_epi = small ? kEpiWarpsSmall : kEpiWarpsLarge;
-        p.resident = 0;
-        const int ring_budget = smem_limit - 2048 - p.Npad * 8 - 512;
-        if (!packed && p.nsplit == 1 && ov.res != 0) {
-            // weights-resident mode: if the block's packed weights fit in shared memory next to the input ring, the persistent
-            // CTA loads them once instead of re-streaming them from L2 for every tile (the L2->SM stream, not HBM and not the
-            // tensor pipe, is what bounds the shallow blocks otherwise).
-            const int mt_pref = p.MT;
-            for (int MT = mt_pref; MT >= std::max(1, mt_pref / (dec ? 1 : 2)) && !p.resident; MT >>= 1) {
-                geometry(MT, 1);
-                const int stage = round_up(p.Nh * 128 * KS, 1024);
-                const int wbytes = p.nchunks * stage;
-                const int na = ov.na > 0 ? ov.na : ((dec && p.nchunks >= 3) ? 3 : 2);
-                if (na * (int)p.a_stage_bytes + wbytes <= ring_budget) {
-                    p.resident = 1; p.na = na; p.tg = KS; p.ngroups = 1;
-                    p.b_stage_bytes = (uint32_t)stage;
-                    p.nb = p.nchunks * p.ngroups;
-                }
-            }
-            if (!p.resident) geometry(mt_pref, 1);
-        }
-        if (!p.resident) {
-            // A ring depth: decoders whose K chunks are short (5 taps, few K-steps) need the TMA/producers to run two chunks
-            // ahead; everything else double-buffers. Weight stages hold `tg` consecutive taps (one TMA box, one handshake).
-            const int na_want = ov.na > 0 ? ov.na : ((dec && !packed && p.nchunks >= 3 && p.MT <= 2) ? 3 : 2);
-            bool ok = false;
-            for (int na = na_want; na >= 1 && !ok; --na) {
-                for (int tg = (ov.tg > 0 ? std::min(KS, ov.tg) : KS); tg >= 1; --tg) {
-                    // every stage handshake costs a ~400-cycle tensor-pipe bubble (trace): prefer the fattest stage
-                    // (most taps per handshake) that still leaves a 2-deep ring; taps past KS in the last group are zero-filled
-                    const int stage = round_up(p.Nh * 128 * tg, 1024);
-                    const int min_stages = 2;
-                    if (na * (int)p.a_stage_bytes + min_stages * stage > ring_budget) continue;
-                    p.na = na; p.tg = tg;
-                    p.ngroups = (KS + tg - 1) / tg;
-                    p.b_stage_bytes = (uint32_t)stage;
-                    int nb = (ring_budget - na * (int)p.a_stage_bytes) / stage;
-                    if (nb > kMaxBStages) nb = kMaxBStages;
-                    p.nb = nb;
-                    ok = true;
-                    break;
-                }
-            }
-            if (!ok) return tc_fail("level %d does not fit in shared memory", i);
-            if (ov.any && p.na < 2) return tc_fail("level %d: override leaves a single input stage", i);
-        }
-        if (!packed && p.nsplit == 1 && ov.bulk != 0 && i != 2 * n && (L % (128 * p.MT) == 0) && (long long)B * L < (1LL << 31)) {
-            // TMA-store epilogue if the slabs fit without giving up ring depth / residency / tile size
-            const int need = p.n_epi * 2048 + 1024;
-            const int min_nb = p.resident ? p.nb : (p.tg == 1 ? 4 : 2);
-            while ((int)smem_total(p) + need > smem_limit && !p.resident && p.nb > min_nb) --p.nb;
-            if ((int)smem_total(p) + need <= smem_limit) p.bulk_store = 1;
-        }
-        {
-            const int threads = 64 + 32 * (small ? kEpiWarpsSmall + (dec ? kProducerWarpsSmall : 0)
-                                                 : kEpiWarpsLarge + (dec ? kProducerWarpsLarge : 0));
-            const int per_sm = std::max(1, std::min({(int)((228 * 1024) / (smem_total(p) + 1024)), (int)(512 / p.tmem_cols), 2048 / threads}));
-            const int total_tiles = p.m_tiles * p.nsplit;
-            p.tile_begin = 0; p.tile_end = total_tiles;
-            P.per_sm = per_sm;
-            P.grid = dim3((unsigned)std::min(total_tiles, st->num_sms * per_sm), 1, 1);
-            P.threads = threads;
-        }
-        P.smem = smem_total(p);
-        if (P.smem > (size_t)kSmemLimit) return tc_fail("level %d: smem %zu too large", i, P.smem);
-
+        const int L = p.L;
         p.ss = lv.ss;
         const bool last = (i == 2 * n);
         p.out = (last && !st->store_last) ? nullptr : lvl(i);
         p.head = last ? 1 : 0;
         p.x = x; p.y = y; p.head_w = st->out_w; p.head_b = st->out_b;
         p.trace = (st->trace && st->trace_level == i) ? st->trace : nullptr;
-        if (last && lv.cout > 32) return tc_fail("fused head needs channels_interval <= 32");
-        if (last && (p.nsplit != 1 || p.packed)) return tc_fail("fused head needs the whole channel range of full frames in one CTA");
         // operand maps
         if (!dec) {
             // decimated view of the previous encoder output: element (c, l, b) -> prev[b][2l][c]   (o[:, :, ::2])
@@ -1270,6 +1290,25 @@ static int build_plan(TcState *st, const float *x, float *y, int B, int T, void 
         }
     }
     st->plan_ws = ws; st->plan_B = B; st->plan_T = T; st->plan_x = x; st->plan_y = y;
+    return 0;
+}
+
+int tc_debug_plan(int n, int ci, const TcBlockSrc *blocks, int nblocks, int B, int T, int block, int num_sms, int *f, int cap)
+{
+    if (nblocks != 2 * n + 1 || block < 1 || block >= nblocks) return tc_fail("block %d out of range (1..%d)", block, 2 * n);
+    if (ci % 8 != 0 || ci > 32) return tc_fail("bf16 tcgen05 path needs channels_interval %% 8 == 0 and <= 32 (got %d)", ci);
+    if (cap < 32 || !f) return tc_fail("need room for 32 fields");
+    std::vector<TcLevel> levels(nblocks);
+    derive_levels(levels, blocks, nblocks, n);
+    const char *ovr = getenv("WUNET_TC_OVR");
+    TcPlanLevel P{};
+    if (plan_block(levels[block], block, n, B, T, num_sms, ovr ? ovr : "", P)) return -1;
+    const TcParams &p = P.p;
+    const int v[32] = {p.L, p.Cin0, p.Cin1, p.Cout, p.Npad, p.Nh, p.nsplit, p.Nstride, p.MT, p.nacc, p.packed, p.FR, p.S, p.m_tiles,
+                       p.nchunks, p.resident, p.bulk_store, p.na, p.nb, p.tg, p.ngroups, (int)p.a_stage_bytes, (int)p.b_stage_bytes,
+                       p.a_tx_bytes, p.rows_used, (int)p.tmem_cols, (int)P.smem, P.threads, P.per_sm, (int)P.grid.x, (int)P.small,
+                       p.tiles_per_frame};
+    for (int k = 0; k < 32; ++k) f[k] = v[k];
     return 0;
 }
 

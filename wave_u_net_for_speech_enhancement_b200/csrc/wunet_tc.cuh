@@ -28,5 +28,8 @@ int tc_forward_host(TcState *st, const float *x_host, float *y_host, float *x_de
                     cudaStream_t stream, int *launches);
 int tc_read_level(TcState *st, int block, const void *ws, int B, int T, float *out_ncl, cudaStream_t stream);
 void tc_destroy(TcState *st);
+// host-only: the tiling build_plan would choose for `block` (32 ints, see wunet_debug_plan in include/wunet_b200.h)
+int tc_debug_plan(int n_layers, int ci, const TcBlockSrc *blocks, int nblocks, int B, int T, int block, int num_sms, int *fields,
+                  int capacity);
 
 }  // namespace wunet
