@@ -229,6 +229,7 @@ struct TcParams {
     const float *head_w;       // [C+1]
     const float *head_b;       // [1]
     long long *trace;          // WUNET_TC_TRACE builds: per-role clock64 stamps of CTA 0 (development)
+    int exp;                   // experimental code paths of the X = 1 kernel instantiations (WUNET_TC_EXP bit mask); 0 otherwise
 };
 
 // smem carve-up (offsets from the 1024-aligned base): A stages | B stages | ss | barriers
@@ -266,7 +267,9 @@ __device__ __forceinline__ ChunkInfo chunk_info(const TcParams &p, int c)
 // -------------------------------------------------------------------------------------------------
 // the conv kernel
 // -------------------------------------------------------------------------------------------------
-template <int KS, bool UPCAT, int EW, int PW>
+// X = 0: the validated kernel. X = 1: the same kernel plus experimental paths selected at run time by p.exp (kept in separate
+// instantiations so that the code of the validated ones does not change while they are being developed).
+template <int KS, bool UPCAT, int EW, int PW, int X>
 __global__ void __launch_bounds__(64 + 32 * (EW + PW), EW == kEpiWarpsSmall ? 2 : 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmO, const TcParams p)
@@ -409,6 +412,92 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ======================= MMA issuer =======================
         // One elected lane runs the whole role (barrier waits included): every warp-level reconvergence between two weight
         // stages costs tensor-pipe idle time, because the asynchronous MMA queue is only a few instructions deep.
+        if (X != 0 && (p.exp & 1)) {
+            // ---- experimental issue loop (WUNET_TC_EXP bit 0): the barriers of the NEXT weight stage are tested and its
+            // descriptors built before the LAST tap of the current stage is issued, so that the boundary bookkeeping
+            // (chunk lookup, two barrier tests, fences, descriptor words) overlaps MMAs that are still queued; a failed
+            // test falls back to the blocking wait after the tap. Trace of dec10: ~900 cycles per K-chunk boundary.
+            if (elect_one()) {
+                int sa = 0, pa = 0, sb = 0, pb = 0, it = 0;
+                const uint32_t b_step = ((uint32_t)p.Nh * 128) >> 4;
+                const uint32_t hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+                auto desc_lo = [](uint32_t addr) { return ((addr >> 4) & 0x3FFFu) | (1u << 16); };
+                if (p.resident) { mbar_wait(b_full, 0); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+                const int nstages = p.nchunks * p.ngroups;
+                for (int tile = first_tile; tile < total_tiles; tile += gridDim.x, ++it) {
+                    int b0, l0, n0;
+                    tile_coords(tile, b0, l0, n0);
+                    const int Nthis = min(p.Nh, p.Npad - n0);
+                    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Nthis >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+                    const int buf = (p.nacc == 2) ? (it & 1) : 0;
+                    const uint32_t use = (p.nacc == 2) ? (uint32_t)(it >> 1) : (uint32_t)it;
+                    mbar_wait(acc_empty + 8 * buf, (use & 1) ^ 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t acc_col = tmem_base + buf * p.MT * p.Nstride;
+                    int c = 0, g = 0, nk = 0, nnk = 0;
+                    uint32_t a_lo = 0, b_lo = 0, na_lo = 0, nb_lo = 0;
+                    bool have = false;
+                    for (int s = 0; s < nstages; ++s) {
+                        if (!have) {
+                            if (g == 0) {
+                                nk = chunk_info<UPCAT>(p, c).nk;
+                                mbar_wait(a_full + 8 * sa, pa);
+                                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                                a_lo = desc_lo(base + sm.a + sa * p.a_stage_bytes);
+                            }
+                            uint32_t b_base;
+                            if (p.resident) {
+                                b_base = base + sm.b + (uint32_t)(c * p.ngroups + g) * p.b_stage_bytes;
+                            } else {
+                                mbar_wait(b_full + 8 * sb, pb);
+                                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                                b_base = base + sm.b + sb * p.b_stage_bytes;
+                            }
+                            b_lo = desc_lo(b_base);
+                        } else {
+                            a_lo = na_lo; b_lo = nb_lo; nk = nnk;
+                        }
+                        const int t_end = min(KS, (g + 1) * p.tg);
+#pragma unroll 1
+                        for (int t = g * p.tg; t < t_end - 1; ++t) {
+                            issue_tap(acc_col, p.MT, p.Nstride, nk, a_lo, b_lo, hi, idesc, (c | t) ? 1u : 0u);
+                            a_lo += 8;
+                            b_lo += b_step;
+                        }
+                        // peek at the next stage of this tile
+                        have = false;
+                        int c2 = c, g2 = g + 1;
+                        if (g2 == p.ngroups) { g2 = 0; ++c2; }
+                        if (c2 < p.nchunks) {
+                            int sa2 = sa, pa2 = pa, sb2 = sb, pb2 = pb;
+                            if (g2 == 0 && ++sa2 == p.na) { sa2 = 0; pa2 ^= 1; }
+                            if (++sb2 == p.nb) { sb2 = 0; pb2 ^= 1; }
+                            bool ok = true;
+                            if (g2 == 0) ok = mbar_test(a_full + 8 * sa2, pa2);
+                            if (ok && !p.resident) ok = mbar_test(b_full + 8 * sb2, pb2);
+                            if (ok) {
+                                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                                nnk = (g2 == 0) ? chunk_info<UPCAT>(p, c2).nk : nk;
+                                na_lo = (g2 == 0) ? desc_lo(base + sm.a + sa2 * p.a_stage_bytes) : a_lo + 8;   // + 8: past the tap issued below
+                                nb_lo = desc_lo(p.resident ? base + sm.b + (uint32_t)(c2 * p.ngroups + g2) * p.b_stage_bytes
+                                                           : base + sm.b + sb2 * p.b_stage_bytes);
+                                have = true;
+                            }
+                        }
+                        issue_tap(acc_col, p.MT, p.Nstride, nk, a_lo, b_lo, hi, idesc, (c | (t_end - 1)) ? 1u : 0u);
+                        a_lo += 8;
+                        if (!p.resident) umma_commit(b_empty + 8 * sb);
+                        if (++sb == p.nb) { sb = 0; pb ^= 1; }
+                        if (g == p.ngroups - 1) {
+                            umma_commit(a_empty + 8 * sa);
+                            if (++sa == p.na) { sa = 0; pa ^= 1; }
+                        }
+                        c = c2; g = g2;
+                    }
+                    umma_commit(acc_full + 8 * buf);
+                }
+            }
+        } else
         if (elect_one()) {
             int sa = 0, pa = 0, sb = 0, pb = 0, it = 0;
             int tr1 = 0; (void)tr1;
@@ -919,6 +1008,7 @@ struct TcState {
     bool store_last = false;           // WUNET_TC_STORE_LAST=1: also materialise the last decoder block (tests)
     bool attr_set = false;
     bool pdl = false;                  // programmatic dependent launch between the blocks (WUNET_TC_PDL=1); measured slower, off
+    int exp = 0;                       // WUNET_TC_EXP bit mask: experimental kernel paths (X = 1 instantiations), default 0
     int num_sms = 148;
     cudaStream_t copy_in = nullptr, copy_out = nullptr;     // host pipeline: H2D / D2H streams
     cudaEvent_t ev_in[8] = {}, ev_out[8] = {};
@@ -991,6 +1081,7 @@ int tc_set_weights(TcState **pst, int n, int ci, const TcBlockSrc *blocks, int n
         st->store_last = e && e[0] == '1';
         const char *pe = getenv("WUNET_TC_PDL");
         st->pdl = pe && pe[0] == '1';
+        if (const char *xe = getenv("WUNET_TC_EXP")) st->exp = atoi(xe);
 #ifdef WUNET_TC_TRACE
         if (const char *tl = getenv("WUNET_TC_TRACE_LEVEL")) {
             st->trace_level = atoi(tl);
@@ -1318,10 +1409,14 @@ static int tc_prepare(TcState *st, const float *x, float *y, int B, int T, void 
     const int ci = st->ci;
     if (ci % 8 != 0 || ci > 32) return tc_fail("bf16 tcgen05 path needs channels_interval %% 8 == 0 and <= 32 (got %d)", ci);
     if (!st->attr_set) {
-        cudaFuncSetAttribute(conv_tc_kernel<15, false, kEpiWarpsLarge, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
-        cudaFuncSetAttribute(conv_tc_kernel<5, true, kEpiWarpsLarge, kProducerWarpsLarge>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
-        cudaFuncSetAttribute(conv_tc_kernel<15, false, kEpiWarpsSmall, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
-        cudaFuncSetAttribute(conv_tc_kernel<5, true, kEpiWarpsSmall, kProducerWarpsSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+        cudaFuncSetAttribute(conv_tc_kernel<15, false, kEpiWarpsLarge, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+        cudaFuncSetAttribute(conv_tc_kernel<5, true, kEpiWarpsLarge, kProducerWarpsLarge, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+        cudaFuncSetAttribute(conv_tc_kernel<15, false, kEpiWarpsSmall, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+        cudaFuncSetAttribute(conv_tc_kernel<5, true, kEpiWarpsSmall, kProducerWarpsSmall, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+        cudaFuncSetAttribute(conv_tc_kernel<15, false, kEpiWarpsLarge, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+        cudaFuncSetAttribute(conv_tc_kernel<5, true, kEpiWarpsLarge, kProducerWarpsLarge, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+        cudaFuncSetAttribute(conv_tc_kernel<15, false, kEpiWarpsSmall, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+        cudaFuncSetAttribute(conv_tc_kernel<5, true, kEpiWarpsSmall, kProducerWarpsSmall, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         cudaFuncSetAttribute(enc0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
         int dev = 0, sms = 0;
         if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
@@ -1374,10 +1469,18 @@ static int launch_block(TcState *st, int i, int t0, int t1, cudaStream_t stream,
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = st->pdl ? 1 : 0;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    if (P.upcat && !P.small) cudaLaunchKernelEx(&cfg, conv_tc_kernel<5, true, kEpiWarpsLarge, kProducerWarpsLarge>, P.tmA, P.tmW, P.tmO, p);
-    else if (P.upcat) cudaLaunchKernelEx(&cfg, conv_tc_kernel<5, true, kEpiWarpsSmall, kProducerWarpsSmall>, P.tmA, P.tmW, P.tmO, p);
-    else if (!P.small) cudaLaunchKernelEx(&cfg, conv_tc_kernel<15, false, kEpiWarpsLarge, 0>, P.tmA, P.tmW, P.tmO, p);
-    else cudaLaunchKernelEx(&cfg, conv_tc_kernel<15, false, kEpiWarpsSmall, 0>, P.tmA, P.tmW, P.tmO, p);
+    p.exp = st->exp;
+    if (st->exp == 0) {
+        if (P.upcat && !P.small) cudaLaunchKernelEx(&cfg, conv_tc_kernel<5, true, kEpiWarpsLarge, kProducerWarpsLarge, 0>, P.tmA, P.tmW, P.tmO, p);
+        else if (P.upcat) cudaLaunchKernelEx(&cfg, conv_tc_kernel<5, true, kEpiWarpsSmall, kProducerWarpsSmall, 0>, P.tmA, P.tmW, P.tmO, p);
+        else if (!P.small) cudaLaunchKernelEx(&cfg, conv_tc_kernel<15, false, kEpiWarpsLarge, 0, 0>, P.tmA, P.tmW, P.tmO, p);
+        else cudaLaunchKernelEx(&cfg, conv_tc_kernel<15, false, kEpiWarpsSmall, 0, 0>, P.tmA, P.tmW, P.tmO, p);
+    } else {
+        if (P.upcat && !P.small) cudaLaunchKernelEx(&cfg, conv_tc_kernel<5, true, kEpiWarpsLarge, kProducerWarpsLarge, 1>, P.tmA, P.tmW, P.tmO, p);
+        else if (P.upcat) cudaLaunchKernelEx(&cfg, conv_tc_kernel<5, true, kEpiWarpsSmall, kProducerWarpsSmall, 1>, P.tmA, P.tmW, P.tmO, p);
+        else if (!P.small) cudaLaunchKernelEx(&cfg, conv_tc_kernel<15, false, kEpiWarpsLarge, 0, 1>, P.tmA, P.tmW, P.tmO, p);
+        else cudaLaunchKernelEx(&cfg, conv_tc_kernel<15, false, kEpiWarpsSmall, 0, 1>, P.tmA, P.tmW, P.tmO, p);
+    }
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return tc_fail("conv_tc level %d launch failed: %s", i, cudaGetErrorString(e));
     return 0;
