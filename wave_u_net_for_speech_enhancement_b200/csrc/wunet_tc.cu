@@ -230,6 +230,11 @@ struct TcParams {
     const float *head_b;       // [1]
     long long *trace;          // WUNET_TC_TRACE builds: per-role clock64 stamps of CTA 0 (development)
     int exp;                   // experimental code paths of the X = 1 kernel instantiations (WUNET_TC_EXP bit mask); 0 otherwise
+    // experimental (exp bit 1): the last K chunk of a decoder block is [skip tail (TMA) | upsampled tail (producers)] in ONE stage
+    int mg;                    // 1: chunk_map's last entry (0x40) is such a merged chunk
+    int mg_vo, mg_nvec;        // first 16-byte vector / number of vectors the producers write in it
+    int mg_nk, mg_kslot;       // its K16 steps, its 64-wide slot in the packed weights
+    int mg_skip_idx, mg_up_idx;// 64-channel chunk index of the tails inside their segments
 };
 
 // smem carve-up (offsets from the 1024-aligned base): A stages | B stages | ss | barriers
@@ -247,20 +252,27 @@ __host__ __device__ inline SmemMap smem_map(const TcParams &p)
     m.bars = (m.bars + 15) & ~15u;
     return m;
 }
-inline size_t smem_total(const TcParams &p) { return smem_map(p).bars + 8 * (8 + 2 * kMaxBStages + 4) + 16 + 1024; }
+inline size_t smem_total(const TcParams &p) { return smem_map(p).bars + 8 * (8 + 2 * kMaxBStages + 4) + 16 + (p.mg ? 32 : 0) + 1024; }
 
 // K-loop position c -> (segment, chunk index inside the segment, K16 steps, 64-wide slot in the packed weights)
-struct ChunkInfo { bool up; int idx, nk, kslot; };
-template <bool UPCAT>
+struct ChunkInfo { bool up; int idx, nk, kslot; bool merged; int vo, nvec; };
+template <bool UPCAT, int X>
 __device__ __forceinline__ ChunkInfo chunk_info(const TcParams &p, int c)
 {
     ChunkInfo ci;
     const int m = p.chunk_map[c];
+    if (X != 0 && UPCAT && (m & 0x40)) {          // merged tail chunk: TMA fills the leading vectors, the producers the next ones
+        ci.up = true; ci.merged = true;
+        ci.idx = p.mg_up_idx; ci.nk = p.mg_nk; ci.kslot = p.mg_kslot; ci.vo = p.mg_vo; ci.nvec = p.mg_nvec;
+        return ci;
+    }
+    ci.merged = false;
     ci.up = UPCAT && (m & 0x80);
     ci.idx = m & 0x7f;
     const int seg_c = (ci.up || !UPCAT) ? p.Cin0 - 64 * ci.idx : p.Cin1 - 64 * ci.idx;
     ci.nk = ((seg_c < 64 ? seg_c : 64) + 15) >> 4;
     ci.kslot = (ci.up || !UPCAT) ? ci.idx : p.nchunks0 + ci.idx;
+    ci.vo = 0; ci.nvec = ci.nk * 2;
     return ci;
 }
 
@@ -287,6 +299,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t a_full = bars, a_empty = bars + 32, b_full = bars + 64, b_empty = bars + 64 + 8 * kMaxBStages;
     const uint32_t acc_full = bars + 64 + 16 * kMaxBStages, acc_empty = acc_full + 16;
     const uint32_t tmem_slot = acc_empty + 16;
+    const uint32_t a_tma = tmem_slot + 16;            // [4], X = 1 kernels with a merged chunk only (smem_total reserves them)
     volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(base_ptr + sm.bars + 64 + 16 * kMaxBStages + 32);
 
     // Programmatic dependent launch: let the next block's kernel be scheduled as our CTAs retire, so its prologue (barrier
@@ -314,6 +327,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_init(acc_empty + 8 * s, kEpilogueWarps);
         }
         for (int s = 0; s < min(p.nb, kMaxBStages); ++s) { mbar_init(b_full + 8 * s, 1); mbar_init(b_empty + 8 * s, 1); }
+        if (X != 0 && p.mg)
+            for (int s = 0; s < 4; ++s) mbar_init(a_tma + 8 * s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kMmaWarp) {
@@ -357,7 +372,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (!blocking && !mbar_test(a_empty + 8 * sa, pa ^ 1)) return false;
                 int b0, l0, n0;
                 tile_coords(a_tile, b0, l0, n0);
-                const ChunkInfo aci = chunk_info<UPCAT>(p, a_c);
+                const ChunkInfo aci = chunk_info<UPCAT, X>(p, a_c);
                 const bool from_tma = !aci.up;
                 TRACE(0, tr0);
                 mbar_wait(a_empty + 8 * sa, pa ^ 1);
@@ -369,6 +384,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int op = 0; op < p.nops; ++op)
                         tma_load_3d(base + sm.a + sa * p.a_stage_bytes + op * p.R1 * 128, &tmA, a_full + 8 * sa, cc * 64,
                                     lcoord + op * p.R1, b0);
+                } else if (X != 0 && aci.merged) {
+                    // skip tail by TMA into the leading vectors of the stage (zero fill behind it), completion on a_tma: the
+                    // producers add the upsampled tail once it has landed and complete a_full
+                    const int lcoord = l0 - PAD;
+                    mbar_expect_tx(a_tma + 8 * sa, p.a_tx_bytes);
+                    for (int op = 0; op < p.nops; ++op)
+                        tma_load_3d(base + sm.a + sa * p.a_stage_bytes + op * p.R1 * 128, &tmA, a_tma + 8 * sa, p.mg_skip_idx * 64,
+                                    lcoord + op * p.R1, b0);
+                    mbar_arrive(a_full + 8 * sa);
                 } else {
                     mbar_arrive(a_full + 8 * sa);
                 }
@@ -380,7 +404,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 // the whole packed weight set of this block (nchunks x KS tiles of [Nh x 64]) is loaded once per CTA
                 mbar_expect_tx(b_full, (uint32_t)p.nchunks * p.ngroups * p.tg * p.Nh * 128);
                 for (int c = 0; c < p.nchunks; ++c) {
-                    const int kslot = chunk_info<UPCAT>(p, c).kslot;
+                    const int kslot = chunk_info<UPCAT, X>(p, c).kslot;
                     for (int g = 0; g < p.ngroups; ++g)
                         tma_load_3d(base + sm.b + (uint32_t)(c * p.ngroups + g) * p.b_stage_bytes, &tmW, b_full, kslot * 64, 0, g * p.tg);
                 }
@@ -395,7 +419,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     // the weight groups of this chunk go out as soon as their ring slots free up; the A tile of the NEXT
                     // chunk is slipped in between them the moment its stage is released (it never blocks the weights)
                     bool a_done = false;
-                    const int kslot = chunk_info<UPCAT>(p, c).kslot;
+                    const int kslot = chunk_info<UPCAT, X>(p, c).kslot;
                     for (int g = 0; g < (p.resident ? 0 : p.ngroups); ++g) {
                         if (!a_done) a_done = issue_a(false);
                         mbar_wait(b_empty + 8 * sb, pb ^ 1);
@@ -440,7 +464,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int s = 0; s < nstages; ++s) {
                         if (!have) {
                             if (g == 0) {
-                                nk = chunk_info<UPCAT>(p, c).nk;
+                                nk = chunk_info<UPCAT, X>(p, c).nk;
                                 mbar_wait(a_full + 8 * sa, pa);
                                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                                 a_lo = desc_lo(base + sm.a + sa * p.a_stage_bytes);
@@ -477,7 +501,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             if (ok && !p.resident) ok = mbar_test(b_full + 8 * sb2, pb2);
                             if (ok) {
                                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                                nnk = (g2 == 0) ? chunk_info<UPCAT>(p, c2).nk : nk;
+                                nnk = (g2 == 0) ? chunk_info<UPCAT, X>(p, c2).nk : nk;
                                 na_lo = (g2 == 0) ? desc_lo(base + sm.a + sa2 * p.a_stage_bytes) : a_lo + 8;   // + 8: past the tap issued below
                                 nb_lo = desc_lo(p.resident ? base + sm.b + (uint32_t)(c2 * p.ngroups + g2) * p.b_stage_bytes
                                                            : base + sm.b + sb2 * p.b_stage_bytes);
@@ -521,7 +545,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t acc_col = tmem_base + buf * p.MT * p.Nstride;
                 for (int c = 0; c < p.nchunks; ++c) {
-                    const int nk = chunk_info<UPCAT>(p, c).nk;
+                    const int nk = chunk_info<UPCAT, X>(p, c).nk;
                     mbar_wait(a_full + 8 * sa, pa);
                     TRACE(1, tr1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -676,15 +700,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int pt = (warp - kFirstProducer) * 32 + lane;
         int sa = 0, pa = 0;
         int tr4 = 0; (void)tr4;
+        uint32_t tma_par = 0;                              // merged chunks: phase parity of a_tma[stage], one bit per stage
         uint4 xr[10];
         bool pref = false;
         const int nruns = (p.rows_used + 15) >> 4;
         // a chunk whose first-round items can be prefetched into the register window one work unit ahead
-        auto unit_fast = [&](int c) { return !p.packed && chunk_info<UPCAT>(p, c).up; };
+        auto unit_fast = [&](int c) { return !p.packed && chunk_info<UPCAT, X>(p, c).up; };
         // loads of item `item` of unit (frame ub0, first row ul0, K-loop position c) into the window
         auto fetch = [&](int ub0, int ul0, int c, int item) {
-            const ChunkInfo u = chunk_info<UPCAT>(p, c);
-            const int nvec = u.nk * 2;
+            const ChunkInfo u = chunk_info<UPCAT, X>(p, c);
+            const int nvec = u.nvec;
             if (item >= nruns * nvec) return;
             const int run = item / nvec, vec = item - run * nvec;
             const int ch = u.idx * 64 + vec * 8;
@@ -702,10 +727,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // store instead of branches): the 16 rows are independent, and a branch per row serialises their dependent chains
         // (trace: ~3600 cycles per item with branches, the stage hand-off was waiting on it).
         auto emit = [&](uint8_t *dst, int l0, int c, int item, const uint4 (&w)[10]) {
-            const ChunkInfo u = chunk_info<UPCAT>(p, c);
-            const int nvec = u.nk * 2;
+            const ChunkInfo u = chunk_info<UPCAT, X>(p, c);
+            const int nvec = u.nvec;
             const int run = item / nvec, vec = item - run * nvec;
             const int ch = u.idx * 64 + vec * 8;
+            const int dvec = u.vo + vec;                                       // 16-byte vector inside the stage row
             const int lstart = l0 - PAD + 16 * run;                            // even
             const int ms = lstart >> 1;
             const bool chok = ch < p.Cin0;
@@ -727,7 +753,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint32_t keep = (chok && (unsigned)l < (unsigned)p.L) ? 0xffffffffu : 0u;   // zero rows = Conv1d padding
                 o.x &= keep; o.y &= keep; o.z &= keep; o.w &= keep;
                 // predicated (not branched) 16-byte store; (16 * run + j) & 7 == j & 7
-                st_shared_v4_if(drow + (uint32_t)(j * 128 + ((vec ^ (j & 7)) << 4)), o, 16 * run + j < p.rows_used);
+                st_shared_v4_if(drow + (uint32_t)(j * 128 + ((dvec ^ (j & 7)) << 4)), o, 16 * run + j < p.rows_used);
             }
         };
         for (int tile = first_tile; tile < total_tiles; tile += gridDim.x) {
@@ -739,10 +765,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (pt == 0) TRACE(4, tr4);
                 mbar_wait(a_empty + 8 * sa, pa ^ 1);
                 if (pt == 0) TRACE(4, tr4);
-                const ChunkInfo cu = chunk_info<UPCAT>(p, c);
+                const ChunkInfo cu = chunk_info<UPCAT, X>(p, c);
                 bool emitted_fast = false;
                 if (cu.up) {
-                    const int nvec = cu.nk * 2;                              // 16-byte vectors per row
+                    if (X != 0 && cu.merged) {                               // the TMA part of this stage must have landed
+                        mbar_wait(a_tma + 8 * sa, (tma_par >> sa) & 1u);
+                        tma_par ^= 1u << sa;
+                    }
+                    const int nvec = cu.nvec;                                // 16-byte vectors per row
                     uint8_t *dst = base_ptr + sm.a + sa * p.a_stage_bytes;
                     if (fast) {
                         const int nitems = nruns * nvec;
@@ -795,7 +825,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     int nt = tile, nc = c + 1;
                     for (int hop = 0; hop < p.nchunks; ++hop) {
                         if (nc >= p.nchunks) { nc = 0; nt += gridDim.x; }
-                        if (chunk_info<UPCAT>(p, nc).up) break;
+                        if (chunk_info<UPCAT, X>(p, nc).up) break;
                         ++nc;
                     }
                     if (nt < total_tiles && unit_fast(nc)) {
@@ -906,6 +936,25 @@ __global__ void pack_tc_kernel(const float *__restrict__ w, const float *__restr
     if (i < Npad) ss[i] = (i < Cout) ? make_float2(scale[i], shift[i]) : make_float2(0.f, 0.f);
 }
 
+// experimental: the extra K slot of a merged tail chunk, [t][co][Ktot - 64 + j]: j < s -> skip tail channel, j < s + u ->
+// upsampled tail channel, else 0 (the regular slots are written by pack_tc_kernel, which leaves this one untouched = 0)
+__global__ void pack_tc_merged_kernel(const float *__restrict__ w, __nv_bfloat16 *__restrict__ wp, int Cout, int Cin0, int Cin1,
+                                      int K, int Npad, int Ktot, int s, int u)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n = (long long)K * Npad * 64;
+    if (i >= n) return;
+    const int j = (int)(i % 64);
+    const int co = (int)((i / 64) % Npad);
+    const int t = (int)(i / (64LL * Npad));
+    int ci = -1;
+    if (j < s) ci = Cin0 + (Cin1 / 64) * 64 + j;
+    else if (j < s + u) ci = (Cin0 / 64) * 64 + (j - s);
+    float v = 0.f;
+    if (co < Cout && ci >= 0) v = w[((size_t)co * (Cin0 + Cin1) + ci) * K + t];
+    wp[((size_t)t * Npad + co) * Ktot + (Ktot - 64) + j] = __float2bfloat16(v);
+}
+
 __global__ void nlc_bf16_to_ncl_f32_kernel(const __nv_bfloat16 *__restrict__ src, float *__restrict__ dst, int B, int L, int C)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;       // index into dst [B][C][L]
@@ -927,6 +976,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
 struct TcLevel {
     int cin0, cin1, cout, k;
     int Npad, Ktot;
+    int mg_s = 0, mg_u = 0;            // experimental (WUNET_TC_EXP bit 1): channel tails of the skip / upsampled segment that share
+                                       // one extra 64-wide K slot at the end of the packed weights (0 = not merged)
     __nv_bfloat16 *wp = nullptr;
     float2 *ss = nullptr;
     const float *w_src = nullptr;      // enc0 only: fp32 weights / scale / shift pointers (owned elsewhere)
@@ -1048,7 +1099,7 @@ size_t tc_workspace_bytes(int n, int ci, int B, int T)
 
 // K segments and padded sizes of every block: encoders have one input segment, decoder block i concatenates the previous
 // block's (upsampled) output with the skip of encoder 2n - i (model/unet_basic.py:93-95)
-static void derive_levels(std::vector<TcLevel> &levels, const TcBlockSrc *blocks, int nblocks, int n)
+static void derive_levels(std::vector<TcLevel> &levels, const TcBlockSrc *blocks, int nblocks, int n, int exp = 0)
 {
     for (int i = 0; i < nblocks; ++i) {
         TcLevel &lv = levels[i];
@@ -1058,6 +1109,12 @@ static void derive_levels(std::vector<TcLevel> &levels, const TcBlockSrc *blocks
         lv.Npad = round_up(lv.cout, 16);
         lv.Ktot = round_up(lv.cin0, 64) + (lv.cin1 ? round_up(lv.cin1, 64) : 0);
         lv.w_src = blocks[i].w; lv.scale = blocks[i].scale; lv.shift = blocks[i].shift;
+        lv.mg_s = lv.mg_u = 0;
+        const int u = lv.cin0 % 64, sk = lv.cin1 % 64;
+        if ((exp & 2) && i > n && u > 0 && sk > 0 && u + sk <= 64 && u % 8 == 0 && sk % 8 == 0) {
+            lv.mg_s = sk; lv.mg_u = u;
+            lv.Ktot += 64;                                  // slot [skip tail | upsampled tail | 0] after the regular slots
+        }
     }
 }
 
@@ -1093,7 +1150,7 @@ int tc_set_weights(TcState **pst, int n, int ci, const TcBlockSrc *blocks, int n
     }
     st->out_w = out_w; st->out_b = out_b;
     st->plan_ws = nullptr;                               // weights moved: rebuild maps lazily
-    derive_levels(st->levels, blocks, nblocks, n);
+    derive_levels(st->levels, blocks, nblocks, n, st->exp);
     if (ci % 8 != 0 || ci > 32) return 0;                // tensor-core path unsupported for this plan; forward reports it
     for (int i = 1; i < nblocks; ++i) {                  // enc0 runs on CUDA cores from the fp32 weights
         TcLevel &lv = st->levels[i];
@@ -1105,6 +1162,12 @@ int tc_set_weights(TcState **pst, int n, int ci, const TcBlockSrc *blocks, int n
         pack_tc_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, stream>>>(blocks[i].w, blocks[i].scale, blocks[i].shift, lv.wp,
                                                                           lv.ss, lv.cout, lv.cin0, lv.cin1, lv.k, lv.Npad, lv.Ktot);
         if (cudaGetLastError() != cudaSuccess) return tc_fail("pack_tc_kernel launch failed");
+        if (lv.mg_s) {
+            const size_t nm = (size_t)lv.k * lv.Npad * 64;
+            pack_tc_merged_kernel<<<(unsigned)((nm + 255) / 256), 256, 0, stream>>>(blocks[i].w, lv.wp, lv.cout, lv.cin0, lv.cin1, lv.k,
+                                                                                    lv.Npad, lv.Ktot, lv.mg_s, lv.mg_u);
+            if (cudaGetLastError() != cudaSuccess) return tc_fail("pack_tc_merged_kernel launch failed");
+        }
     }
     return 0;
 }
@@ -1159,7 +1222,19 @@ static int plan_block(const TcLevel &lv, int i, int n, int B, int T, int num_sms
         // upsampled chunk: a TMA chunk is never preceded by a short chunk, so its load latency hides behind MMAs.
         int k = 0;
         if (!dec) { for (int c = 0; c < p.nchunks; ++c) p.chunk_map[k++] = (unsigned char)c; }
-        else {
+        else if (lv.mg_s && L >= 128) {
+            // experimental: [full upsampled chunks][full skip chunks][skip tail | upsampled tail] - one chunk fewer
+            const int nfull0 = lv.cin0 / 64, nfull1 = lv.cin1 / 64;
+            for (int c = 0; c < nfull0; ++c) p.chunk_map[k++] = (unsigned char)(0x80 | c);
+            for (int c = 0; c < nfull1; ++c) p.chunk_map[k++] = (unsigned char)c;
+            p.chunk_map[k++] = (unsigned char)0x40;
+            p.nchunks = k;
+            p.mg = 1;
+            p.mg_vo = lv.mg_s / 8; p.mg_nvec = lv.mg_u / 8;
+            p.mg_nk = (lv.mg_s + lv.mg_u + 15) / 16;
+            p.mg_kslot = lv.Ktot / 64 - 1;
+            p.mg_skip_idx = nfull1; p.mg_up_idx = nfull0;
+        } else {
             const int nfull0 = lv.cin0 / 64, n1 = p.nchunks - p.nchunks0;
             if (nfull0 == 0) {
                 // the only upsampled chunk is partial (e.g. the last decoder: 48 + 24 channels): produce it FIRST, so that its
