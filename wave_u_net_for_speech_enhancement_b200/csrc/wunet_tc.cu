@@ -690,6 +690,72 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (lane == 0) mbar_arrive(acc_empty + 8 * buf);
         }
         if (p.bulk_store && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    } else if (UPCAT && KS == 1) {
+        // ======================= Toeplitz producers (experimental: first encoder block on the tensor cores) ============
+        // Conv1d(1 -> C, k=15) (model/unet_basic.py:10, first DownSamplingLayer) as a K = 48 GEMM per position:
+        // A[l][t] = x[l + t - 7], split into bf16 high and low parts, laid out [hi | lo | hi] (16 columns each, column 15 = 0),
+        // against B[co] = [w_hi | w_hi | w_lo]: D = x_hi w_hi + x_lo w_hi + x_hi w_lo, relative error ~2^-16 (the dropped
+        // x_lo w_lo term), i.e. fp32-grade before the bf16 store. A work item is (16 rows) x (one 16-column part): 32 aligned
+        // floats of x, the 31 bf16 pairs of both alignments, 32 16-byte stores. The loads for the next tile are issued after
+        // the stage hand-off (the fence before the arrive is a MEMBAR and would wait for them).
+        const int pt = (warp - kFirstProducer) * 32 + lane;
+        int sa = 0, pa = 0;
+        const int nitems = (p.rows_used >> 4) * 3;                     // rows_used = 128 * MT
+        float v[32];
+        auto load_x = [&](int tile, int item) {
+            int tb0, tl0, tn0;
+            tile_coords(tile, tb0, tl0, tn0);
+            const int run = item / 3;
+            const int first = tl0 + 16 * run - 8;                      // v[i] = x[first + i]; multiple of 8
+            const float *xp = p.x + (size_t)tb0 * p.T;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int i0 = first + 4 * q;
+                float4 f = make_float4(0.f, 0.f, 0.f, 0.f);                // Conv1d zero padding at the frame ends
+                if (tb0 < p.B && i0 >= 0 && i0 + 3 < p.T) f = __ldg(reinterpret_cast<const float4 *>(xp + i0));
+                v[4 * q] = f.x; v[4 * q + 1] = f.y; v[4 * q + 2] = f.z; v[4 * q + 3] = f.w;
+            }
+        };
+        if (first_tile < total_tiles && pt < nitems) load_x(first_tile, pt);
+        for (int tile = first_tile; tile < total_tiles; tile += gridDim.x) {
+            mbar_wait(a_empty + 8 * sa, pa ^ 1);
+            const uint32_t stage = base + sm.a + sa * p.a_stage_bytes;
+#pragma unroll 1
+            for (int item = pt; item < nitems; item += NPROD) {
+                if (item != pt) load_x(tile, item);                    // later rounds (fewer producer threads than items)
+                const int run = item / 3, part = item - run * 3;
+                const bool low = part == 1;
+                float sv[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) sv[i] = low ? v[i] - __bfloat162float(__float2bfloat16_rn(v[i])) : v[i];
+                uint32_t wo[15], we[16];
+#pragma unroll
+                for (int k = 0; k < 15; ++k) wo[k] = pack_bf16(sv[2 * k + 1], sv[2 * k + 2]);
+#pragma unroll
+                for (int k = 0; k < 16; ++k) we[k] = pack_bf16(sv[2 * k], sv[2 * k + 1]);
+#pragma unroll
+                for (int r = 0; r < 16; ++r) {
+                    // column t of row r is s[r + t + 1]; column 15 (high half of the last word) is forced to zero
+                    const int m = r >> 1;
+                    uint4 o0, o1;
+                    if (r & 1) {
+                        o0 = make_uint4(we[m + 1], we[m + 2], we[m + 3], we[m + 4]);
+                        o1 = make_uint4(we[m + 5], we[m + 6], we[m + 7], we[m + 8] & 0x0000ffffu);
+                    } else {
+                        o0 = make_uint4(wo[m], wo[m + 1], wo[m + 2], wo[m + 3]);
+                        o1 = make_uint4(wo[m + 4], wo[m + 5], wo[m + 6], wo[m + 7] & 0x0000ffffu);
+                    }
+                    const uint32_t rowaddr = stage + (uint32_t)(16 * run + r) * 128u;
+                    st_shared_v4_if(rowaddr + (uint32_t)(((2 * part) ^ (r & 7)) << 4), o0, true);
+                    st_shared_v4_if(rowaddr + (uint32_t)(((2 * part + 1) ^ (r & 7)) << 4), o1, true);
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor core reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_full + 8 * sa);
+            if (++sa == p.na) { sa = 0; pa ^= 1; }
+            if (tile + (int)gridDim.x < total_tiles && pt < nitems) load_x(tile + gridDim.x, pt);
+        }
     } else if (UPCAT) {
         // ======================= upsample producers (decoder) =======================
         // F.interpolate(scale_factor=2, mode="linear", align_corners=True) of the previous block's output, written straight
@@ -955,6 +1021,26 @@ __global__ void pack_tc_merged_kernel(const float *__restrict__ w, __nv_bfloat16
     wp[((size_t)t * Npad + co) * Ktot + (Ktot - 64) + j] = __float2bfloat16(v);
 }
 
+// experimental (WUNET_TC_EXP bit 2): first encoder block on the tensor cores. Weights [C][1][15] fp32 -> one [Npad][64] bf16 tile,
+// columns [w_hi(15) 0 | w_hi(15) 0 | w_lo(15) 0 | 0 x 16] matching the [x_hi | x_lo | x_hi] columns the Toeplitz producers write
+__global__ void pack_enc0_tc_kernel(const float *__restrict__ w, const float *__restrict__ scale, const float *__restrict__ shift,
+                                    __nv_bfloat16 *__restrict__ wp, float2 *__restrict__ ss, int C, int Npad)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < Npad * 64) {
+        const int co = i / 64, j = i - co * 64;
+        const int grp = j >> 4, t = j & 15;
+        float v = 0.f;
+        if (co < C && t < 15 && grp < 3) {
+            const float wf = w[co * 15 + t];
+            const float hi = __bfloat162float(__float2bfloat16_rn(wf));
+            v = (grp == 2) ? wf - hi : hi;
+        }
+        wp[i] = __float2bfloat16_rn(v);
+    }
+    if (i < Npad) ss[i] = (i < C) ? make_float2(scale[i], shift[i]) : make_float2(0.f, 0.f);
+}
+
 __global__ void nlc_bf16_to_ncl_f32_kernel(const __nv_bfloat16 *__restrict__ src, float *__restrict__ dst, int B, int L, int C)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;       // index into dst [B][C][L]
@@ -993,6 +1079,7 @@ struct TcPlanLevel {
     size_t smem;
     bool upcat;
     bool small;                        // two-CTAs-per-SM kernel flavour
+    bool ks1;                          // experimental first-encoder block on the tensor cores (KS = 1 instantiation, Toeplitz producers)
 };
 
 // Per-block tiling overrides for tuning sweeps: WUNET_TC_OVR="<block>:key=val,key=val;<block>:..." with keys
@@ -1152,6 +1239,16 @@ int tc_set_weights(TcState **pst, int n, int ci, const TcBlockSrc *blocks, int n
     st->plan_ws = nullptr;                               // weights moved: rebuild maps lazily
     derive_levels(st->levels, blocks, nblocks, n, st->exp);
     if (ci % 8 != 0 || ci > 32) return 0;                // tensor-core path unsupported for this plan; forward reports it
+    if (st->exp & 4) {
+        TcLevel &l0 = st->levels[0];
+        if (!l0.wp) {
+            if (cudaMalloc(&l0.wp, (size_t)l0.Npad * 64 * sizeof(__nv_bfloat16)) != cudaSuccess) return tc_fail("cudaMalloc(wp0) failed");
+            if (cudaMalloc(&l0.ss, l0.Npad * sizeof(float2)) != cudaSuccess) return tc_fail("cudaMalloc(ss0) failed");
+        }
+        pack_enc0_tc_kernel<<<(l0.Npad * 64 + 255) / 256, 256, 0, stream>>>(blocks[0].w, blocks[0].scale, blocks[0].shift, l0.wp, l0.ss,
+                                                                            l0.cout, l0.Npad);
+        if (cudaGetLastError() != cudaSuccess) return tc_fail("pack_enc0_tc_kernel launch failed");
+    }
     for (int i = 1; i < nblocks; ++i) {                  // enc0 runs on CUDA cores from the fp32 weights
         TcLevel &lv = st->levels[i];
         const size_t nel = (size_t)lv.k * lv.Npad * lv.Ktot;
@@ -1404,6 +1501,37 @@ static int plan_block(const TcLevel &lv, int i, int n, int B, int T, int num_sms
     return 0;
 }
 
+// experimental: the first encoder block as an implicit GEMM with K = 48 (see the Toeplitz producers of conv_tc_kernel<1, ...>)
+static void plan_enc0_tc(int C, int B, int T, int num_sms, TcPlanLevel &P)
+{
+    TcParams &p = P.p;
+    memset(&p, 0, sizeof(p));
+    P.upcat = true; P.small = false; P.ks1 = true;
+    p.B = B; p.L = T; p.T = T; p.Cout = C;
+    p.Cin0 = 48; p.Cin1 = 0; p.nchunks0 = 1; p.nchunks = 1; p.chunk_map[0] = (unsigned char)0x80;
+    p.Npad = round_up(C, 16); p.Nh = p.Npad; p.Nstride = round_up(p.Nh, 32); p.nsplit = 1;
+    int MT = 4;
+    while (MT > 1 && 128 * MT > T) --MT;
+    p.MT = MT; p.packed = 0; p.S = 0; p.FR = 1;
+    p.tiles_per_frame = (T + 128 * MT - 1) / (128 * MT);
+    p.m_tiles = B * p.tiles_per_frame;
+    p.nacc = 2;
+    uint32_t cols = 32;
+    while ((int)cols < 2 * MT * p.Nstride) cols <<= 1;
+    p.tmem_cols = cols;
+    p.rows_used = 128 * MT; p.nops = 1; p.R1 = 128 * MT; p.a_tx_bytes = 0;
+    p.a_stage_bytes = (uint32_t)(128 * MT * 128);
+    p.b_stage_bytes = (uint32_t)round_up(p.Nh * 128, 1024);
+    p.resident = 1; p.nb = 1; p.tg = 1; p.ngroups = 1; p.na = 3;
+    p.n_epi = kEpiWarpsLarge;
+    p.bulk_store = (T % (128 * MT) == 0 && (long long)B * T < (1LL << 31)) ? 1 : 0;
+    p.tile_begin = 0; p.tile_end = p.m_tiles;
+    P.threads = 64 + 32 * (kEpiWarpsLarge + kProducerWarpsLarge);
+    P.per_sm = 1;
+    P.smem = smem_total(p);
+    P.grid = dim3((unsigned)std::min(p.m_tiles, num_sms), 1, 1);
+}
+
 static int build_plan(TcState *st, const float *x, float *y, int B, int T, void *ws)
 {
     const int n = st->n;
@@ -1413,6 +1541,16 @@ static int build_plan(TcState *st, const float *x, float *y, int B, int T, void 
     pl.lv.assign(2 * n + 1, TcPlanLevel{});
     char *base = static_cast<char *>(ws);
     auto lvl = [&](int i) { return reinterpret_cast<__nv_bfloat16 *>(base + pl.off[i]); };
+    if (st->exp & 4) {
+        const TcLevel &lv = st->levels[0];
+        TcPlanLevel &P = pl.lv[0];
+        plan_enc0_tc(lv.cout, B, T, st->num_sms, P);
+        TcParams &p = P.p;
+        p.ss = lv.ss; p.out = lvl(0);
+        if (make_map(st, &P.tmW, lv.wp, 64, (uint64_t)lv.Npad, 1, 128, (uint64_t)lv.Npad * 128, 64, (uint32_t)p.Nh, 1)) return -1;
+        P.tmA = P.tmW;                                   // no TMA input chunks: the producers build the whole operand
+        if (make_map_out(st, &P.tmO, p.out, (uint64_t)lv.cout, (uint64_t)B * T)) return -1;
+    }
     for (int i = 1; i < 2 * n + 1; ++i) {
         const TcLevel &lv = st->levels[i];
         TcPlanLevel &P = pl.lv[i];
@@ -1492,6 +1630,7 @@ static int tc_prepare(TcState *st, const float *x, float *y, int B, int T, void 
         cudaFuncSetAttribute(conv_tc_kernel<5, true, kEpiWarpsLarge, kProducerWarpsLarge, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         cudaFuncSetAttribute(conv_tc_kernel<15, false, kEpiWarpsSmall, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         cudaFuncSetAttribute(conv_tc_kernel<5, true, kEpiWarpsSmall, kProducerWarpsSmall, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+        cudaFuncSetAttribute(conv_tc_kernel<1, true, kEpiWarpsLarge, kProducerWarpsLarge, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         cudaFuncSetAttribute(enc0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
         int dev = 0, sms = 0;
         if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
@@ -1550,6 +1689,8 @@ static int launch_block(TcState *st, int i, int t0, int t1, cudaStream_t stream,
         else if (P.upcat) cudaLaunchKernelEx(&cfg, conv_tc_kernel<5, true, kEpiWarpsSmall, kProducerWarpsSmall, 0>, P.tmA, P.tmW, P.tmO, p);
         else if (!P.small) cudaLaunchKernelEx(&cfg, conv_tc_kernel<15, false, kEpiWarpsLarge, 0, 0>, P.tmA, P.tmW, P.tmO, p);
         else cudaLaunchKernelEx(&cfg, conv_tc_kernel<15, false, kEpiWarpsSmall, 0, 0>, P.tmA, P.tmW, P.tmO, p);
+    } else if (P.ks1) {
+        cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, true, kEpiWarpsLarge, kProducerWarpsLarge, 1>, P.tmA, P.tmW, P.tmO, p);
     } else {
         if (P.upcat && !P.small) cudaLaunchKernelEx(&cfg, conv_tc_kernel<5, true, kEpiWarpsLarge, kProducerWarpsLarge, 1>, P.tmA, P.tmW, P.tmO, p);
         else if (P.upcat) cudaLaunchKernelEx(&cfg, conv_tc_kernel<5, true, kEpiWarpsSmall, kProducerWarpsSmall, 1>, P.tmA, P.tmW, P.tmO, p);
@@ -1568,7 +1709,8 @@ int tc_forward(TcState *st, const float *x, float *y, int B, int T, void *ws, cu
     const int n = st->n;
     int nl = 0;
     if (ev) cudaEventRecord(ev[0], stream);
-    if (launch_enc0(st, x, 0, B, T, ws, stream)) return -1;
+    if (st->exp & 4) { if (launch_block(st, 0, 0, -1, stream, x, y)) return -1; }
+    else if (launch_enc0(st, x, 0, B, T, ws, stream)) return -1;
     ++nl;
     if (ev) cudaEventRecord(ev[1], stream);
     for (int i = 1; i < 2 * n + 1; ++i) {
@@ -1610,7 +1752,10 @@ int tc_forward_host(TcState *st, const float *x_host, float *y_host, float *x_de
         cudaMemcpyAsync(x_dev + c * chunk, x_host + c * chunk, chunk * sizeof(float), cudaMemcpyHostToDevice, st->copy_in);
         cudaEventRecord(st->ev_in[c], st->copy_in);
         cudaStreamWaitEvent(stream, st->ev_in[c], 0);
-        if (launch_enc0(st, x_dev, c * bc, bc, T, ws, stream)) return -1;
+        if (st->exp & 4) {
+            const int tpf = st->plan.lv[0].p.tiles_per_frame;
+            if (launch_block(st, 0, c * bc * tpf, (c + 1) * bc * tpf, stream, x_dev, y_dev)) return -1;
+        } else if (launch_enc0(st, x_dev, c * bc, bc, T, ws, stream)) return -1;
         ++nl;
     }
     for (int i = 1; i < 2 * n; ++i) {
