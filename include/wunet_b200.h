@@ -128,6 +128,23 @@ int wunet_profile_read(wunet_ctx *ctx, float *ms, int capacity, int *count);
 /* Number of kernel launches the last wunet_forward()/wunet_forward_host() enqueued. */
 int wunet_last_launch_count(const wunet_ctx *ctx);
 
+/* ---- training step (fp32; correctness-first kernels, opt-in from the host mirror) --------------------
+ * Replaces, together, what autograd records and replays for trainer/trainer.py:35-37 (enhanced = model(mixture) in .train()
+ * mode; loss.backward()). Parameters are read in the reference's layouts straight from the caller's tensors.
+ * wunet_train_forward: y = model(x) with BatchNorm1d (model/unet_basic.py:12,25,55) using batch statistics; updates the
+ *   running_mean / running_var buffers in place (momentum, unbiased variance) as torch does; keeps the activations in `workspace`.
+ * wunet_train_backward: gradients of all parameters (same layouts, fully overwritten) for the upstream gradient dy [B][1][T];
+ *   `workspace` must be the one the matching forward left behind. */
+size_t wunet_train_workspace_bytes(const wunet_ctx *ctx, int B, int T);
+int wunet_train_forward(wunet_ctx *ctx, const float *x, float *y, int B, int T, const float *const *conv_w,
+                        const float *const *conv_b, const float *const *bn_weight, const float *const *bn_bias,
+                        float *const *bn_running_mean, float *const *bn_running_var, const float *out_w, const float *out_b,
+                        float momentum, void *workspace, size_t workspace_bytes, void *stream);
+int wunet_train_backward(wunet_ctx *ctx, const float *x, const float *y, const float *dy, int B, int T,
+                         const float *const *conv_w, const float *const *bn_weight, const float *const *bn_bias, const float *out_w,
+                         float *const *g_conv_w, float *const *g_conv_b, float *const *g_bn_weight, float *const *g_bn_bias,
+                         float *g_out_w, float *g_out_b, void *workspace, size_t workspace_bytes, void *stream);
+
 /* Introspection for tests and tuning, host-only (needs no GPU, no context): the tiling the bf16 path would use for conv
  * block `block` (1 .. 2*n_layers; block 0 = first encoder runs on CUDA cores) at batch B, frame length T, on a device with
  * num_sms SMs. No reference counterpart. Writes 32 ints:

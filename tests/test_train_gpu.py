@@ -1,0 +1,105 @@
+"""Native training step (wunet_train_forward / wunet_train_backward through Model(train_backend="native"))
+against the training oracle's golden vectors and the composite PyTorch path.
+
+The kernels of csrc/wunet_train.cu have not been run on a GPU yet, so these tests only run when WUNET_TEST_NATIVE_TRAIN=1
+(first GPU session of the next round: `WUNET_TEST_NATIVE_TRAIN=1 timeout 300 python -m pytest tests/test_train_gpu.py -x -q`)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import wunet_oracle as wo
+from wave_u_net_for_speech_enhancement_b200 import Model
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("WUNET_TEST_NATIVE_TRAIN") != "1",
+                                 reason="native training kernels not validated on a GPU yet (set WUNET_TEST_NATIVE_TRAIN=1)")]
+
+GRAD_REL = 2e-4       # fp32 kernels vs the float64 reference step; relative to the largest entry of each gradient
+
+
+def make_pair(B, T, seed):
+    g = np.random.Generator(np.random.PCG64(seed))
+    clean = (0.1 * g.standard_normal((B, 1, T))).astype(np.float32)
+    noisy = (clean + 0.05 * g.standard_normal((B, 1, T))).astype(np.float32)
+    return noisy, clean
+
+
+def make_model(n, ci, st, backend):
+    m = Model(n, ci, precision="fp32", train_backend=backend)
+    m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in st.items()}, strict=True)
+    return m.to("cuda:0").train()
+
+
+def step(m, noisy, clean):
+    y = m(torch.from_numpy(noisy).cuda())
+    loss = torch.nn.MSELoss()(torch.from_numpy(clean).cuda(), y)          # trainer/trainer.py:36 argument order
+    loss.backward()
+    return float(loss.detach()), y.detach().cpu().numpy()
+
+
+def rel_err(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def test_small_config_step_vs_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "train_small_n4_c8.npz"))
+    n, ci, B, T = int(g["n_layers"]), int(g["channels_interval"]), int(g["B"]), int(g["T"])
+    st = wo.make_state(n, ci, seed=int(g["state_seed"]))
+    noisy, clean = make_pair(B, T, int(g["pair_seed"]))
+    m = make_model(n, ci, st, "native")
+    loss, y = step(m, noisy, clean)
+    assert abs(loss - float(g["loss"])) <= 1e-5 * float(g["loss"])
+    assert np.abs(y - g["y"]).max() <= 1e-5
+    for k, p in m.named_parameters():
+        want = g["grad:" + k]
+        got = p.grad.cpu().numpy()
+        if k.endswith(".0.bias") and not k.startswith("out."):
+            assert np.abs(got).max() <= 1e-5 * max(np.abs(g["grad:" + k.replace(".0.bias", ".0.weight")]).max(), 1e-30), k
+            continue
+        assert rel_err(got, want) <= GRAD_REL, k
+    sd = m.state_dict()
+    for k in [k[5:] for k in g.files if k.startswith("stat:")]:
+        if "num_batches" in k:
+            assert int(sd[k]) == 1
+        else:
+            assert rel_err(sd[k].cpu().numpy(), g["stat:" + k]) <= 1e-5, k
+
+
+def test_reference_architecture_step_vs_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "train_full_n12_c24_b2_t4096.npz"))
+    n, ci, B, T = int(g["n_layers"]), int(g["channels_interval"]), int(g["B"]), int(g["T"])
+    st = wo.make_state(n, ci, seed=int(g["state_seed"]))
+    noisy, clean = make_pair(B, T, int(g["pair_seed"]))
+    m = make_model(n, ci, st, "native")
+    loss, y = step(m, noisy, clean)
+    assert abs(loss - float(g["loss"])) <= 1e-5 * float(g["loss"])
+    assert np.abs(y - g["y"]).max() <= 1e-5
+    for k, p in m.named_parameters():
+        if k.endswith(".0.bias") and not k.startswith("out."):
+            continue
+        got = p.grad.cpu().numpy().astype(np.float64)
+        norm = float(g["gnorm:" + k])
+        assert abs(np.sqrt((got ** 2).sum()) - norm) <= GRAD_REL * norm, k
+        assert np.abs(got.reshape(-1)[g["gidx:" + k]] - g["gval:" + k]).max() <= GRAD_REL * np.abs(got).max(), k
+
+
+def test_three_adam_steps_track_the_composite_torch_path():
+    """trainer/trainer.py:34-38 + train.py:31-35 (Adam lr 1e-3): the same three steps on both backends stay together."""
+    n, ci, B, T = 4, 8, 4, 256
+    st = wo.make_state(n, ci, seed=31)
+    ms = [make_model(n, ci, st, b) for b in ("native", "torch")]
+    opts = [torch.optim.Adam(m.parameters(), lr=1e-3, betas=(0.9, 0.999)) for m in ms]
+    for it in range(3):
+        noisy, clean = make_pair(B, T, 40 + it)
+        losses = []
+        for m, opt in zip(ms, opts):
+            opt.zero_grad()
+            losses.append(step(m, noisy, clean)[0])
+            opt.step()
+        assert abs(losses[0] - losses[1]) <= 1e-4 * abs(losses[1]), (it, losses)
+    for (k, a), (_, b) in zip(ms[0].state_dict().items(), ms[1].state_dict().items()):
+        if k.endswith(".0.bias") and not k.startswith("out."):
+            continue                      # gradient is rounding noise, Adam turns it into +-lr steps on both sides
+        assert rel_err(a.float().cpu().numpy(), b.float().cpu().numpy()) <= 2e-3, k

@@ -7,8 +7,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libwunet_b200.so")
-SOURCES = ["wunet_api.cu", "wunet_fp32.cu", "wunet_tc.cu"]
-HEADERS = ["wunet_common.cuh", "wunet_tc.cuh", os.path.join("..", "..", "include", "wunet_b200.h")]
+SOURCES = ["wunet_api.cu", "wunet_fp32.cu", "wunet_tc.cu", "wunet_train.cu"]
+HEADERS = ["wunet_common.cuh", "wunet_tc.cuh", "wunet_train.cuh", os.path.join("..", "..", "include", "wunet_b200.h")]
 
 
 def nvcc_path() -> str:

@@ -3,6 +3,7 @@
 #include "../../include/wunet_b200.h"
 #include "wunet_common.cuh"
 #include "wunet_tc.cuh"
+#include "wunet_train.cuh"
 
 #include <cstdarg>
 #include <cstdio>
@@ -443,6 +444,50 @@ int wunet_read_level(wunet_ctx *c, int block, const void *workspace, int B, int 
 }
 
 int wunet_last_launch_count(const wunet_ctx *c) { return c ? c->last_launches : 0; }
+
+size_t wunet_train_workspace_bytes(const wunet_ctx *c, int B, int T)
+{
+    if (check_shape(c, B, T) != WUNET_OK) return 0;
+    return train_workspace_bytes(c->n, c->ci, B, T);
+}
+
+int wunet_train_forward(wunet_ctx *c, const float *x, float *y, int B, int T, const float *const *conv_w,
+                        const float *const *conv_b, const float *const *bn_weight, const float *const *bn_bias,
+                        float *const *bn_running_mean, float *const *bn_running_var, const float *out_w, const float *out_b,
+                        float momentum, void *workspace, size_t workspace_bytes, void *stream)
+{
+    int rc = check_shape(c, B, T);
+    if (rc != WUNET_OK) return rc;
+    if (!x || !y || !workspace || !conv_w || !conv_b || !bn_weight || !bn_bias || !bn_running_mean || !bn_running_var || !out_w || !out_b)
+        return fail(WUNET_EINVAL, "null argument");
+    const size_t need = train_workspace_bytes(c->n, c->ci, B, T);
+    if (workspace_bytes < need) return fail(WUNET_ENOMEM, "training workspace too small: %zu < %zu bytes", workspace_bytes, need);
+    CUDA_TRY(cudaSetDevice(c->device));
+    const TrainParams P{conv_w, conv_b, bn_weight, bn_bias, bn_running_mean, bn_running_var, out_w, out_b};
+    if (train_forward(c->n, c->ci, x, y, B, T, P, momentum, workspace, static_cast<cudaStream_t>(stream)))
+        return fail(WUNET_ECUDA, "%s", train_error());
+    return WUNET_OK;
+}
+
+int wunet_train_backward(wunet_ctx *c, const float *x, const float *y, const float *dy, int B, int T,
+                         const float *const *conv_w, const float *const *bn_weight, const float *const *bn_bias, const float *out_w,
+                         float *const *g_conv_w, float *const *g_conv_b, float *const *g_bn_weight, float *const *g_bn_bias,
+                         float *g_out_w, float *g_out_b, void *workspace, size_t workspace_bytes, void *stream)
+{
+    int rc = check_shape(c, B, T);
+    if (rc != WUNET_OK) return rc;
+    if (!x || !y || !dy || !workspace || !conv_w || !bn_weight || !bn_bias || !out_w || !g_conv_w || !g_conv_b || !g_bn_weight ||
+        !g_bn_bias || !g_out_w || !g_out_b)
+        return fail(WUNET_EINVAL, "null argument");
+    const size_t need = train_workspace_bytes(c->n, c->ci, B, T);
+    if (workspace_bytes < need) return fail(WUNET_ENOMEM, "training workspace too small: %zu < %zu bytes", workspace_bytes, need);
+    CUDA_TRY(cudaSetDevice(c->device));
+    const TrainParams P{conv_w, nullptr, bn_weight, bn_bias, nullptr, nullptr, out_w, nullptr};
+    const TrainGrads G{g_conv_w, g_conv_b, g_bn_weight, g_bn_bias, g_out_w, g_out_b};
+    if (train_backward(c->n, c->ci, x, y, dy, B, T, P, G, workspace, static_cast<cudaStream_t>(stream)))
+        return fail(WUNET_ECUDA, "%s", train_error());
+    return WUNET_OK;
+}
 
 int wunet_debug_plan(int n_layers, int channels_interval, int B, int T, int block, int num_sms, int *fields, int capacity)
 {

@@ -63,6 +63,66 @@ class UpSamplingLayer(nn.Module):
         return self.main(ipt)
 
 
+class _NativeTrainStep(torch.autograd.Function):
+    """forward = wunet_train_forward, backward = wunet_train_backward (include/wunet_b200.h). The activations live in a
+    workspace tensor kept on the autograd context; parameter order: 4 per conv block (conv.weight, conv.bias, bn.weight,
+    bn.bias) in forward order, then out.weight, out.bias."""
+
+    @staticmethod
+    def _ptr_array(tensors):
+        return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+    @staticmethod
+    def forward(ctx, model, x, *params):
+        lib = _lib.load()
+        blocks = model._blocks()
+        nb = len(blocks)
+        B, _, T = x.shape
+        with torch.cuda.device(x.device):
+            c = model._context(x.device)
+            nbytes = lib.wunet_train_workspace_bytes(c, B, T)
+            if nbytes == 0:
+                _lib.check(-1)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+            y = torch.empty_like(x)
+            conv_w = [params[4 * i] for i in range(nb)]
+            conv_b = [params[4 * i + 1] for i in range(nb)]
+            bn_w = [params[4 * i + 2] for i in range(nb)]
+            bn_b = [params[4 * i + 3] for i in range(nb)]
+            rmean = [blk[1].running_mean for blk in blocks]
+            rvar = [blk[1].running_var for blk in blocks]
+            momentum = float(blocks[0][1].momentum)
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+            P = _NativeTrainStep._ptr_array
+            _lib.check(lib.wunet_train_forward(c, x.data_ptr(), y.data_ptr(), B, T, P(conv_w), P(conv_b), P(bn_w), P(bn_b),
+                                               P(rmean), P(rvar), params[-2].data_ptr(), params[-1].data_ptr(), momentum,
+                                               ws.data_ptr(), ws.numel(), stream))
+        ctx.model, ctx.ws, ctx.nb = model, ws, nb
+        ctx.save_for_backward(x, y, *params)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _lib.load()
+        x, y, *params = ctx.saved_tensors
+        nb = ctx.nb
+        B, _, T = x.shape
+        gy = gy.contiguous()
+        grads = [torch.empty_like(p) for p in params]
+        with torch.cuda.device(x.device):
+            c = ctx.model._context(x.device)
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+            P = _NativeTrainStep._ptr_array
+            sel = lambda ts, k: [ts[4 * i + k] for i in range(nb)]          # noqa: E731
+            _lib.check(lib.wunet_train_backward(c, x.data_ptr(), y.data_ptr(), gy.data_ptr(), B, T, P(sel(params, 0)),
+                                                P(sel(params, 2)), P(sel(params, 3)), params[-2].data_ptr(),
+                                                P(sel(grads, 0)), P(sel(grads, 1)), P(sel(grads, 2)), P(sel(grads, 3)),
+                                                grads[-2].data_ptr(), grads[-1].data_ptr(), ctx.ws.data_ptr(), ctx.ws.numel(),
+                                                stream))
+        ctx.ws = None
+        return (None, None, *grads)                          # no gradient for the model handle and for the input
+
+
 class Model(nn.Module):
     """Wave-U-Net whose eval forward runs on hand-written sm_100a kernels.
 
@@ -81,8 +141,8 @@ class Model(nn.Module):
         super().__init__()
         if precision not in _lib.PRECISIONS:
             raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}, got {precision!r}")
-        if train_backend not in ("none", "torch"):
-            raise ValueError("train_backend must be 'none' or 'torch'")
+        if train_backend not in ("none", "torch", "native"):
+            raise ValueError("train_backend must be 'none', 'torch' or 'native'")
         self.n_layers = n_layers
         self.channels_interval = channels_interval
         self.precision = precision
@@ -189,6 +249,8 @@ class Model(nn.Module):
         if self.training:
             if self.train_backend == "torch":
                 return self._forward_torch_reference_semantics(input)
+            if self.train_backend == "native":
+                return self._forward_train_native(input)
             raise NotImplementedError(
                 "libwunet_b200 implements the eval-mode forward (SURVEY §8 rows a–e). Training-mode BatchNorm / "
                 "autograd (row N1) is not built yet: call model.eval(), or construct the model with "
@@ -196,6 +258,28 @@ class Model(nn.Module):
         # eval mode: like enhancement.py:66 (`model(chunk).detach().cpu()`, no torch.no_grad()) the result is
         # returned detached — the native path records no autograd graph.
         return self._forward_native(input)
+
+    def _forward_train_native(self, x: torch.Tensor) -> torch.Tensor:
+        """Training-mode forward through libwunet_b200 (wunet_train_forward / wunet_train_backward behind a
+        torch.autograd.Function): BatchNorm uses batch statistics and updates its running buffers, ``loss.backward()`` fills
+        ``.grad`` of all 102 parameters, the caller's optimizer is used unchanged (trainer/trainer.py:34-38). fp32,
+        correctness-first kernels."""
+        self._check_input(x)
+        if not x.is_cuda:
+            raise RuntimeError("wave_u_net_for_speech_enhancement_b200 has no CPU fallback: move the model and the "
+                               "input to a CUDA (sm_100a) device")
+        blocks = self._blocks()
+        params = []
+        for blk in blocks:
+            params += [blk[0].weight, blk[0].bias, blk[1].weight, blk[1].bias]
+        params += [self.out[0].weight, self.out[0].bias]
+        for t in params:
+            if t.device != x.device or t.dtype != torch.float32 or not t.is_contiguous():
+                raise RuntimeError("libwunet_b200 needs contiguous float32 parameters on the input's device")
+        y = _NativeTrainStep.apply(self, x.contiguous(), *params)
+        for blk in blocks:                                   # torch.nn.BatchNorm1d bookkeeping (momentum is not None: unused)
+            blk[1].num_batches_tracked += 1
+        return y
 
     def _check_input(self, x: torch.Tensor):
         if x.dim() != 3 or x.size(1) != 1:
