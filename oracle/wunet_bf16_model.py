@@ -1,0 +1,110 @@
+"""
+oracle/wunet_bf16_model.py — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+The arithmetic of the bf16 tensor-core path (csrc/wunet_tc.cu) restated on the CPU, rounding where the kernels round:
+
+* first encoder block: fp32 operands (CUDA cores), folded BatchNorm scale/shift in fp32, LeakyReLU, bf16 store;
+* every other block: bf16 activations x bf16 weights (round-to-nearest-even of the fp32 parameters), wide accumulation
+  (float64 here; the tensor core accumulates exact products in fp32 — the difference is ~1e-6 relative and only matters
+  where it flips a bf16 rounding), fp32 scale/shift + LeakyReLU, bf16 store;
+* decoder inputs: the interpolated half in packed-bf16 arithmetic (lam = bf16(fma(up_scale, l, -m)), d = bf16(b - a),
+  r = bf16(fma(lam, d, a))) for levels of at least 128 samples, in fp32 (lam0*f0 + lam1*f1, then bf16) for the packed
+  short levels — exactly the two producer code paths;
+* head: the last block's fp32 (unrounded) activations, fp32 fma chain, tanh.
+
+A GPU result that differs from this model by more than a bf16 ulp at a handful of rounding flips is a kernel bug; the
+fp32 oracle alone cannot show that (the bf16 path sits 3e-3 of the level range away from it).  Only ``tests/`` may
+import this module.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from .wunet_oracle import BN_EPS, LRELU_SLOPE, channel_plan
+
+
+def _bf16(t: torch.Tensor) -> torch.Tensor:
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def _fold(st, prefix):
+    """scale / shift exactly as pack_fp32_kernel computes them (fp32)."""
+    g = torch.from_numpy(np.asarray(st[f"{prefix}.1.weight"], np.float32))
+    beta = torch.from_numpy(np.asarray(st[f"{prefix}.1.bias"], np.float32))
+    mean = torch.from_numpy(np.asarray(st[f"{prefix}.1.running_mean"], np.float32))
+    var = torch.from_numpy(np.asarray(st[f"{prefix}.1.running_var"], np.float32))
+    bias = torch.from_numpy(np.asarray(st[f"{prefix}.0.bias"], np.float32))
+    s = g / torch.sqrt(var + np.float32(BN_EPS))
+    shift = torch.addcmul(beta, bias - mean, s)               # fmaf(bias - mean, s, beta) up to one rounding
+    return s, shift
+
+
+def _block(x: torch.Tensor, st, prefix: str, k: int, quantise_operands: bool) -> torch.Tensor:
+    """conv (wide accumulate) -> fp32 scale/shift -> LeakyReLU, fp32 result (not yet rounded to bf16)."""
+    w = torch.from_numpy(np.asarray(st[f"{prefix}.0.weight"], np.float32))
+    if quantise_operands:
+        w = _bf16(w)
+    acc = F.conv1d(x.double(), w.double(), None, padding=(k - 1) // 2).float()
+    s, shift = _fold(st, prefix)
+    v = acc * s[None, :, None] + shift[None, :, None]
+    return torch.where(v >= 0, v, np.float32(LRELU_SLOPE) * v)
+
+
+def _upsample_hfma2(prev: torch.Tensor) -> torch.Tensor:
+    """Producer fast path (levels >= 128 samples): packed-bf16 interpolation between prev rows (l-1)>>1 and that + 1."""
+    Lin = prev.shape[2]
+    L = 2 * Lin
+    up_scale = np.float32(Lin - 1) / np.float32(L - 1)
+    l = torch.arange(L)
+    m0 = torch.div(l - 1, 2, rounding_mode="floor")
+    a = prev[:, :, m0.clamp(0, Lin - 1)]
+    b = prev[:, :, (m0 + 1).clamp(0, Lin - 1)]
+    lam = _bf16((l.double() * float(up_scale) - m0.double()).float())       # one fused rounding to fp32, then bf16
+    d = _bf16(b - a)
+    return _bf16((lam[None, None, :].double() * d.double() + a.double()).float())
+
+
+def _upsample_fp32(prev: torch.Tensor) -> torch.Tensor:
+    """Producer generic path (packed short levels): ATen index math and lam0*f0 + lam1*f1 in fp32, then bf16."""
+    Lin = prev.shape[2]
+    L = 2 * Lin
+    up_scale = np.float32(Lin - 1) / np.float32(L - 1) if L > 1 else np.float32(0)
+    s = (torch.arange(L, dtype=torch.float32) * up_scale)
+    i0 = s.to(torch.int64)
+    i1 = i0 + (i0 < Lin - 1).to(torch.int64)
+    lam1 = s - i0.to(torch.float32)
+    lam0 = 1.0 - lam1
+    return _bf16(lam0[None, None, :] * prev[:, :, i0] + lam1[None, None, :] * prev[:, :, i1])
+
+
+def forward_bf16_model(state, x: np.ndarray, n_layers: int = 12, channels_interval: int = 24, return_levels: bool = False):
+    """-> y [B,1,T] fp32 (and the bf16-valued outputs of the 2n+1 blocks as fp32 arrays; the last one unrounded)."""
+    plan = channel_plan(n_layers, channels_interval)
+    n = n_layers
+    xt = torch.from_numpy(np.asarray(x, np.float32))
+    levels, skips = [], []
+    o = _bf16(_block(xt, state, plan[0][0], 15, quantise_operands=False))
+    skips.append(o)
+    levels.append(o)
+    o = o[:, :, ::2]
+    for i in range(1, n):
+        o = _bf16(_block(o, state, plan[i][0], 15, True))
+        skips.append(o)
+        levels.append(o)
+        o = o[:, :, ::2]
+    o = _bf16(_block(o, state, "middle", 15, True))
+    levels.append(o)
+    for j in range(n):
+        L = 2 * o.shape[2]
+        up = _upsample_hfma2(o) if L >= 128 else _upsample_fp32(o)
+        v = _block(torch.cat([up, skips[n - 1 - j]], dim=1), state, plan[n + 1 + j][0], 5, True)
+        o = v if j == n - 1 else _bf16(v)                        # the last block feeds the fused head unrounded
+        levels.append(o)
+    w = torch.from_numpy(np.asarray(state["out.0.weight"], np.float32))[0, :, 0]
+    b = np.float32(np.asarray(state["out.0.bias"], np.float32)[0])
+    C = o.shape[1]
+    pre = (o.double() * w[:C].double()[None, :, None]).sum(dim=1) + w[C].double() * xt[:, 0].double() + float(b)
+    y = torch.tanh(pre).float()[:, None, :].numpy()
+    return (y, [t.numpy() for t in levels]) if return_levels else y

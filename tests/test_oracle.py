@@ -115,3 +115,21 @@ def test_batch_independence():
     y0 = orc.forward(st, x[0:1])
     y1 = orc.forward(st, x[1:2])
     assert np.array_equal(yb[0:1], y0) and np.array_equal(yb[1:2], y1)
+
+
+def test_bf16_arithmetic_model_sits_where_the_gpu_path_was_measured(golden_dir):
+    """oracle/wunet_bf16_model.py restates the bf16 path's roundings; against the fp32 golden vectors it must show the
+    distance the CUDA path showed on the B200 (0.3-0.5 % of each level's range, ~6e-4 on the output), not more."""
+    from oracle import wunet_bf16_model as wb
+    g = np.load(os.path.join(golden_dir, "small_n4_c8.npz"))
+    n, ci, T, B = int(g["n_layers"]), int(g["channels_interval"]), int(g["T"]), int(g["B"])
+    st = wo.make_state(n, ci, seed=int(g["state_seed"]))
+    x = wo.make_input(B, T, seed=int(g["input_seed"]))
+    y, levels = wb.forward_bf16_model(st, x, n, ci, return_levels=True)
+    assert np.abs(y - g["y"]).max() <= 5e-3
+    for i, lv in enumerate(levels):
+        ref = g[f"level_{i}"]
+        assert lv.shape == ref.shape
+        assert np.abs(lv - ref).max() <= 1.5e-2 * np.abs(ref).max(), i
+    # and it is a different function from the fp32 forward: the roundings are really applied
+    assert np.abs(levels[1] - g["level_1"]).max() > 1e-5
