@@ -14,10 +14,13 @@
 //     tap*128 B (verified on hardware by tools/umma_probe.cu);
 //   * encoder decimation o[:, :, ::2] is a tensor map with a doubled row stride (no copy);
 //   * decoder: the K axis is [upsampled previous output | skip]. The skip half comes by TMA; the upsampled
-//     half (F.interpolate linear, align_corners=True, index math in fp32 like ATen) is produced by four
+//     half (F.interpolate linear, align_corners=True, index math in fp32 like ATen) is produced by the producer
 //     warps straight into the swizzled operand tile — the interpolated/concatenated tensor never exists in HBM;
-//   * weights stream through a TMA ring, one [N x 64] tile per (chunk, tap), shared by the MT sub-tiles;
-//   * accumulators live in TMEM (MT x N fp32 columns); the epilogue warps read them with tcgen05.ld, apply the
+//   * weights come by TMA, shared by the MT sub-tiles: either a ring of stages holding several taps of one [N x 64]
+//     chunk each (as many as fit: every stage handshake idles the tensor pipe), or — where the whole packed weight
+//     set of the block fits next to the input ring — loaded once per persistent CTA;
+//   * accumulators live in TMEM (MT x N fp32 columns, double-buffered when 2 MT N <= 512 so that the next tile's MMAs
+//     overlap this tile's epilogue); the epilogue warps read them with tcgen05.ld, apply the
 //     folded BatchNorm scale/shift and LeakyReLU(0.1), and store bf16 NLC rows; the last decoder block also
 //     applies the 1x1 conv over [decoder out | raw input] and tanh (model/unet_basic.py:98-99) so its 24-channel
 //     output never reaches HBM.
@@ -26,7 +29,9 @@
 // Warp roles: epilogue warps (TMEM lane quadrant = warp % 4), upsample-producer warps (decoder blocks), one TMA
 // warp, one MMA-issue warp (highest warp id). Two kernel flavours per block type: "large" (one CTA per SM, 8 epilogue
 // + 9 producer warps) and "small" (two CTAs per SM: 4 + 4 warps, half the shared memory and TMEM each), so that one
-// CTA's pipeline bubbles are filled by the other's MMAs.
+// CTA's pipeline bubbles are filled by the other's MMAs. build_plan() chooses tile shapes, ring depths and the flavour
+// per block (rules + a small table of swept tilings for the reference architecture); DESIGN.md §5 has the role table and
+// the measured hardware facts the design rests on.
 #include "wunet_tc.cuh"
 #include "wunet_common.cuh"
 
@@ -130,7 +135,6 @@ __device__ __forceinline__ void umma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, u
         "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
         ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate) : "memory");
 }
-// all MMAs of one tap: MT sub-tiles x NK K-steps. a_lo/b_lo are descriptor low words (16-byte units).
 // all MMAs of one tap: MT sub-tiles x nk K-steps. a_lo / b_lo are descriptor low words (16-byte units). Deliberately a
 // small rolled loop: the kernel's instruction footprint must stay cache-resident next to the epilogue / producer code.
 __device__ __forceinline__ void issue_tap(uint32_t d_col, int MT, uint32_t nstride, int nk, uint32_t a_lo, uint32_t b_lo,
