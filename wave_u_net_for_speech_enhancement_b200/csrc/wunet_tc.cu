@@ -452,6 +452,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 auto desc_lo = [](uint32_t addr) { return ((addr >> 4) & 0x3FFFu) | (1u << 16); };
                 if (p.resident) { mbar_wait(b_full, 0); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
                 const int nstages = p.nchunks * p.ngroups;
+                int nk = 0, nnk = 0;
+                uint32_t a_lo = 0, b_lo = 0, na_lo = 0, nb_lo = 0;
+                bool have = false;                                   // the next stage's barriers passed and its descriptors are built
+                bool acc_ready = false;                              // ... including, across a tile boundary, the accumulator buffer
                 for (int tile = first_tile; tile < total_tiles; tile += gridDim.x, ++it) {
                     int b0, l0, n0;
                     tile_coords(tile, b0, l0, n0);
@@ -459,12 +463,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Nthis >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
                     const int buf = (p.nacc == 2) ? (it & 1) : 0;
                     const uint32_t use = (p.nacc == 2) ? (uint32_t)(it >> 1) : (uint32_t)it;
-                    mbar_wait(acc_empty + 8 * buf, (use & 1) ^ 1);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (!acc_ready) {
+                        mbar_wait(acc_empty + 8 * buf, (use & 1) ^ 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    }
+                    acc_ready = false;
                     const uint32_t acc_col = tmem_base + buf * p.MT * p.Nstride;
-                    int c = 0, g = 0, nk = 0, nnk = 0;
-                    uint32_t a_lo = 0, b_lo = 0, na_lo = 0, nb_lo = 0;
-                    bool have = false;
+                    int c = 0, g = 0;
                     for (int s = 0; s < nstages; ++s) {
                         if (!have) {
                             if (g == 0) {
@@ -496,20 +501,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         have = false;
                         int c2 = c, g2 = g + 1;
                         if (g2 == p.ngroups) { g2 = 0; ++c2; }
-                        if (c2 < p.nchunks) {
+                        const bool next_tile = c2 == p.nchunks;              // the next stage is the first one of this CTA's next tile
+                        if (!next_tile || tile + (int)gridDim.x < total_tiles) {
+                            const int cn = next_tile ? 0 : c2;
                             int sa2 = sa, pa2 = pa, sb2 = sb, pb2 = pb;
                             if (g2 == 0 && ++sa2 == p.na) { sa2 = 0; pa2 ^= 1; }
                             if (++sb2 == p.nb) { sb2 = 0; pb2 ^= 1; }
                             bool ok = true;
-                            if (g2 == 0) ok = mbar_test(a_full + 8 * sa2, pa2);
+                            if (next_tile) {
+                                const int it2 = it + 1;
+                                const int buf2 = (p.nacc == 2) ? (it2 & 1) : 0;
+                                const uint32_t use2 = (p.nacc == 2) ? (uint32_t)(it2 >> 1) : (uint32_t)it2;
+                                ok = mbar_test(acc_empty + 8 * buf2, (use2 & 1) ^ 1);
+                            }
+                            if (ok && g2 == 0) ok = mbar_test(a_full + 8 * sa2, pa2);
                             if (ok && !p.resident) ok = mbar_test(b_full + 8 * sb2, pb2);
                             if (ok) {
                                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                                nnk = (g2 == 0) ? chunk_info<UPCAT, X>(p, c2).nk : nk;
+                                nnk = (g2 == 0) ? chunk_info<UPCAT, X>(p, cn).nk : nk;
                                 na_lo = (g2 == 0) ? desc_lo(base + sm.a + sa2 * p.a_stage_bytes) : a_lo + 8;   // + 8: past the tap issued below
-                                nb_lo = desc_lo(p.resident ? base + sm.b + (uint32_t)(c2 * p.ngroups + g2) * p.b_stage_bytes
+                                nb_lo = desc_lo(p.resident ? base + sm.b + (uint32_t)(cn * p.ngroups + g2) * p.b_stage_bytes
                                                            : base + sm.b + sb2 * p.b_stage_bytes);
                                 have = true;
+                                acc_ready = next_tile;
                             }
                         }
                         issue_tap(acc_col, p.MT, p.Nstride, nk, a_lo, b_lo, hi, idesc, (c | (t_end - 1)) ? 1u : 0u);
