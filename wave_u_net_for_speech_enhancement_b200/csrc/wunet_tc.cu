@@ -1084,7 +1084,8 @@ struct TcLevel {
                                        // one extra 64-wide K slot at the end of the packed weights (0 = not merged)
     __nv_bfloat16 *wp = nullptr;
     float2 *ss = nullptr;
-    const float *w_src = nullptr;      // enc0 only: fp32 weights / scale / shift pointers (owned elsewhere)
+    const float *w_src = nullptr;      // enc0 only: fp32 weights (w_own, a library-owned copy) / scale / shift (the context's folded copies)
+    float *w_own = nullptr;            // enc0 only: [Cout][1][K] fp32 copy made by tc_set_weights (the caller's tensor is not read afterwards)
     const float *scale = nullptr, *shift = nullptr;
 };
 
@@ -1257,6 +1258,16 @@ int tc_set_weights(TcState **pst, int n, int ci, const TcBlockSrc *blocks, int n
     st->plan_ws = nullptr;                               // weights moved: rebuild maps lazily
     derive_levels(st->levels, blocks, nblocks, n, st->exp);
     if (ci % 8 != 0 || ci > 32) return 0;                // tensor-core path unsupported for this plan; forward reports it
+    {
+        // enc0 runs on CUDA cores from fp32 weights: keep a library-owned copy (include/wunet_b200.h: the caller's tensors are
+        // only read during wunet_set_weights)
+        TcLevel &l0 = st->levels[0];
+        const size_t wn = (size_t)l0.cout * blocks[0].cin * l0.k * sizeof(float);
+        if (!l0.w_own && cudaMalloc(&l0.w_own, wn) != cudaSuccess) return tc_fail("cudaMalloc(enc0 weights) failed");
+        if (cudaMemcpyAsync(l0.w_own, blocks[0].w, wn, cudaMemcpyDeviceToDevice, stream) != cudaSuccess)
+            return tc_fail("enc0 weight copy failed");
+        l0.w_src = l0.w_own;
+    }
     if (st->exp & 4) {
         TcLevel &l0 = st->levels[0];
         if (!l0.wp) {
@@ -1830,7 +1841,7 @@ void tc_destroy(TcState *st)
         }
         cudaFree(st->trace);
     }
-    for (auto &lv : st->levels) { cudaFree(lv.wp); cudaFree(lv.ss); }
+    for (auto &lv : st->levels) { cudaFree(lv.wp); cudaFree(lv.ss); cudaFree(lv.w_own); }
     delete st;
 }
 

@@ -22,6 +22,7 @@ There is no CPU or PyTorch fallback for the eval forward: a CPU tensor or a miss
 from __future__ import annotations
 
 import ctypes
+import threading
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -61,6 +62,72 @@ class UpSamplingLayer(nn.Module):
 
     def forward(self, ipt):  # pragma: no cover
         return self.main(ipt)
+
+
+class _DeviceState:
+    """Native context of one logical model on one CUDA device."""
+
+    __slots__ = ("ctx", "weights_key", "workspaces", "last_ws")
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self.weights_key: Optional[Tuple] = None
+        self.workspaces: Dict[Tuple, torch.Tensor] = {}
+        self.last_ws: Optional[Tuple] = None
+
+
+class _NativeState:
+    """Registry of the native contexts (one per CUDA device) of ONE logical model.
+
+    The Model holds it by reference and so does every shallow copy of the module: ``nn.DataParallel`` (what the unchanged
+    ``trainer/base_trainer.py:26-27`` uses when several GPUs are visible) replicates with ``replica.__dict__ =
+    self.__dict__.copy()``, so replicas SHARE this object, find the context of their device in it across forwards and never
+    own (or destroy) one. ``copy.deepcopy`` / pickling give the copy a fresh, empty registry (``__reduce__``). The
+    contexts are destroyed when the registry itself is collected, i.e. after the model and all its replicas are gone."""
+
+    def __init__(self):
+        self._lock = threading.Lock()
+        self._dev: Dict[int, _DeviceState] = {}
+
+    def __reduce__(self):
+        # copy.deepcopy / pickle of the owning module: the copy gets its own, EMPTY registry (native handles are neither
+        # copyable nor shareable between independent models)
+        return (_NativeState, ())
+
+    def device_state(self, idx: int, n_layers: int, channels_interval: int) -> _DeviceState:
+        with self._lock:
+            ds = self._dev.get(idx)
+            if ds is None:
+                ctx = ctypes.c_void_p()
+                _lib.check(_lib.load().wunet_create(n_layers, channels_interval, idx, ctypes.byref(ctx)))
+                ds = self._dev[idx] = _DeviceState(ctx)
+            return ds
+
+    def peek(self, idx: Optional[int] = None) -> Optional[_DeviceState]:
+        with self._lock:
+            if idx is None:
+                return next(iter(self._dev.values()), None)
+            return self._dev.get(idx)
+
+    def invalidate_weights(self):
+        with self._lock:
+            for ds in self._dev.values():
+                ds.weights_key = None
+
+    def release(self):
+        with self._lock:
+            dev, self._dev = self._dev, {}
+        for ds in dev.values():
+            try:
+                _lib.load().wunet_destroy(ds.ctx)
+            except Exception:  # pragma: no cover - interpreter shutdown
+                pass
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:  # interpreter shutdown
+            pass
 
 
 class _NativeTrainStep(torch.autograd.Function):
@@ -158,12 +225,8 @@ class Model(nn.Module):
         self.decoder = nn.ModuleList(UpSamplingLayer(a, b) for a, b in zip(dec_in, dec_out))
         self.out = nn.Sequential(nn.Conv1d(ci + 1, 1, kernel_size=1, stride=1), nn.Tanh())
 
-        # native state (not part of state_dict)
-        self._ctx: Optional[ctypes.c_void_p] = None
-        self._ctx_device: Optional[int] = None
-        self._weights_key: Optional[Tuple] = None
-        self._workspaces: Dict[Tuple, torch.Tensor] = {}
-        self._last_ws: Optional[Tuple] = None
+        # native state (not part of state_dict); shared by reference with DataParallel replicas, see _NativeState
+        self._native = _NativeState()
 
     # ------------------------------------------------------------------------------------------
     # native plumbing
@@ -171,35 +234,16 @@ class Model(nn.Module):
     def _blocks(self):
         return [e.main for e in self.encoder] + [self.middle] + [d.main for d in self.decoder]
 
-    def _context(self, device: torch.device) -> ctypes.c_void_p:
+    def _state(self, device: torch.device) -> _DeviceState:
         idx = device.index if device.index is not None else torch.cuda.current_device()
-        if self._ctx is not None and self._ctx_device == idx:
-            return self._ctx
-        self._release()
-        lib = _lib.load()
-        ctx = ctypes.c_void_p()
-        _lib.check(lib.wunet_create(self.n_layers, self.channels_interval, idx, ctypes.byref(ctx)))
-        self._ctx, self._ctx_device = ctx, idx
-        self._weights_key = None
-        return ctx
+        return self._native.device_state(idx, self.n_layers, self.channels_interval)
+
+    def _context(self, device: torch.device) -> ctypes.c_void_p:
+        return self._state(device).ctx
 
     def _release(self):
-        if self.__dict__.get("_ctx") is not None:
-            try:
-                _lib.load().wunet_destroy(self._ctx)
-            except Exception:  # pragma: no cover - interpreter shutdown
-                pass
-        self._ctx = None
-        self._ctx_device = None
-        self._weights_key = None
-        self._workspaces = {}
-        self._last_ws = None
-
-    def __del__(self):
-        try:
-            self._release()
-        except Exception:  # interpreter shutdown
-            pass
+        """Destroy the native contexts of this model (they are rebuilt lazily by the next forward)."""
+        self._native.release()
 
     def _param_tensors(self):
         ts = []
@@ -212,9 +256,10 @@ class Model(nn.Module):
     def _sync_weights(self, ctx, device: torch.device):
         """(Re)pack the library's weight copies when any parameter/buffer changed: optimizer.step()
         and load_state_dict bump ``_version``; .cpu()/.to() change ``data_ptr``."""
+        ds = self._state(device)
         ts = self._param_tensors()
         key = tuple((t.data_ptr(), t._version) for t in ts)
-        if key == self._weights_key:
+        if key == ds.weights_key:
             return
         for t in ts:
             if t.device != device:
@@ -227,19 +272,20 @@ class Model(nn.Module):
             arrs.append((ctypes.c_void_p * nb)(*[ts[6 * i + slot].data_ptr() for i in range(nb)]))
         stream = torch.cuda.current_stream(device).cuda_stream
         _lib.check(_lib.load().wunet_set_weights(ctx, *arrs, ts[-2].data_ptr(), ts[-1].data_ptr(), stream))
-        self._weights_key = key
+        ds.weights_key = key
 
     def _workspace(self, ctx, B: int, T: int, prec: int, device: torch.device) -> torch.Tensor:
-        key = (B, T, prec, device.index)
-        ws = self._workspaces.get(key)
+        ds = self._state(device)
+        key = (B, T, prec)
+        ws = ds.workspaces.get(key)
         if ws is None:
             nbytes = _lib.load().wunet_workspace_bytes(ctx, B, T, prec)
             if nbytes == 0:
                 _lib.check(-1)
-            self._workspaces = {}          # keep one shape resident (frames are fixed-length in practice)
+            ds.workspaces = {}             # keep one shape resident (frames are fixed-length in practice)
             ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
-            self._workspaces[key] = ws
-        self._last_ws = key
+            ds.workspaces[key] = ws
+        ds.last_ws = key
         return ws
 
     # ------------------------------------------------------------------------------------------
@@ -276,9 +322,11 @@ class Model(nn.Module):
         for t in params:
             if t.device != x.device or t.dtype != torch.float32 or not t.is_contiguous():
                 raise RuntimeError("libwunet_b200 needs contiguous float32 parameters on the input's device")
-        y = _NativeTrainStep.apply(self, x.contiguous(), *params)
+        y = _NativeTrainStep.apply(self, self._aligned(x), *params)
         for blk in blocks:                                   # torch.nn.BatchNorm1d bookkeeping (momentum is not None: unused)
             blk[1].num_batches_tracked += 1
+        # the kernels updated running_mean / running_var through raw pointers (no _version bump): drop the folded copies
+        self._native.invalidate_weights()
         return y
 
     def _check_input(self, x: torch.Tensor):
@@ -287,12 +335,19 @@ class Model(nn.Module):
         if x.dtype != torch.float32:
             raise RuntimeError(f"expected float32 input, got {x.dtype}")
 
+    @staticmethod
+    def _aligned(x: torch.Tensor) -> torch.Tensor:
+        """contiguous and 16-byte aligned (the kernels use 128-bit loads; a slice ``wave[:, :, off:off+T]`` of a B=1 tensor
+        is contiguous but only 4-byte aligned when ``off % 4 != 0``)"""
+        x = x.contiguous()
+        return x if x.data_ptr() % 16 == 0 else x.clone(memory_format=torch.contiguous_format)
+
     def _forward_native(self, x: torch.Tensor) -> torch.Tensor:
         self._check_input(x)
         if not x.is_cuda:
             raise RuntimeError("wave_u_net_for_speech_enhancement_b200 has no CPU fallback: move the model and the "
                                "input to a CUDA (sm_100a) device")
-        x = x.contiguous()
+        x = self._aligned(x)
         B, _, T = x.shape
         lib = _lib.load()
         with torch.cuda.device(x.device):
@@ -376,35 +431,38 @@ class Model(nn.Module):
         reference's encoder[i] / middle / decoder[j] returns. Used by the per-level parity tests."""
         prec = _lib.PRECISIONS[self.precision]
         device = self.out[0].weight.device
-        key = (B, T, prec, device.index)
-        if self._ctx is None or key not in self._workspaces:
+        ds = self._native.peek(device.index if device.type == "cuda" else None)
+        key = (B, T, prec)
+        if ds is None or key not in ds.workspaces:
             raise RuntimeError("read_level: run a native forward with this (B, T) first")
         n = self.n_layers
         cout = self._blocks()[block][0].out_channels
         L = (T >> block) if block <= n else (T >> (2 * n - block))
         out = torch.empty(B, cout, L, dtype=torch.float32, device=device)
-        ws = self._workspaces[key]
+        ws = ds.workspaces[key]
         with torch.cuda.device(device):
             stream = torch.cuda.current_stream(device).cuda_stream
-            _lib.check(_lib.load().wunet_read_level(self._ctx, block, ws.data_ptr(), B, T, prec, out.data_ptr(), stream))
+            _lib.check(_lib.load().wunet_read_level(ds.ctx, block, ws.data_ptr(), B, T, prec, out.data_ptr(), stream))
         return out
 
     def profile(self, enable: bool) -> None:
         """Measurement hook: record per-block CUDA events in subsequent native forwards."""
-        if self._ctx is None:
+        ds = self._native.peek()
+        if ds is None:
             raise RuntimeError("profile(): run a native forward first")
-        _lib.check(_lib.load().wunet_profile_enable(self._ctx, 1 if enable else 0))
+        _lib.check(_lib.load().wunet_profile_enable(ds.ctx, 1 if enable else 0))
 
     def profile_read(self):
         """Per-block device times (ms) of the last profiled forward: 2n+1 conv blocks, then the head."""
         cap = 2 * self.n_layers + 2
         buf = (ctypes.c_float * cap)()
         cnt = ctypes.c_int(0)
-        _lib.check(_lib.load().wunet_profile_read(self._ctx, buf, cap, ctypes.byref(cnt)))
+        _lib.check(_lib.load().wunet_profile_read(self._native.peek().ctx, buf, cap, ctypes.byref(cnt)))
         return [float(buf[i]) for i in range(cnt.value)]
 
     def last_launch_count(self) -> int:
-        return 0 if self._ctx is None else int(_lib.load().wunet_last_launch_count(self._ctx))
+        ds = self._native.peek()
+        return 0 if ds is None else int(_lib.load().wunet_last_launch_count(ds.ctx))
 
     # ------------------------------------------------------------------------------------------
     # opt-in composite path with the reference's training semantics (NOT the product hot path)
@@ -426,5 +484,5 @@ class Model(nn.Module):
     # nn.Module hooks: any structural move invalidates the native context lazily (keys are checked per call)
     def _apply(self, fn, *args, **kwargs):
         r = super()._apply(fn, *args, **kwargs)
-        self._weights_key = None
+        self._native.invalidate_weights()
         return r
