@@ -128,7 +128,7 @@ int wunet_profile_read(wunet_ctx *ctx, float *ms, int capacity, int *count);
 /* Number of kernel launches the last wunet_forward()/wunet_forward_host() enqueued. */
 int wunet_last_launch_count(const wunet_ctx *ctx);
 
-/* ---- training step (fp32; correctness-first kernels, opt-in from the host mirror) --------------------
+/* ---- training step (fp32 CUDA-core kernels; the host mirror's default in .train() mode) -----------------
  * Replaces, together, what autograd records and replays for trainer/trainer.py:35-37 (enhanced = model(mixture) in .train()
  * mode; loss.backward()). Parameters are read in the reference's layouts straight from the caller's tensors.
  * wunet_train_forward: y = model(x) with BatchNorm1d (model/unet_basic.py:12,25,55) using batch statistics; updates the
@@ -144,6 +144,15 @@ int wunet_train_backward(wunet_ctx *ctx, const float *x, const float *y, const f
                          const float *const *conv_w, const float *const *bn_weight, const float *const *bn_bias, const float *out_w,
                          float *const *g_conv_w, float *const *g_conv_b, float *const *g_bn_weight, float *const *g_bn_bias,
                          float *g_out_w, float *g_out_b, void *workspace, size_t workspace_bytes, void *stream);
+/* The same backward in two parts, for data-parallel training (one process per GPU replaces the nn.DataParallel
+ * of trainer/base_trainer.py:26-27): part 0 = head + decoder blocks — their parameter gradients are final when it has run, so
+ * the caller starts the all-reduce of that half of the flat gradient bucket on another stream; part 1 = middle + encoder
+ * blocks, enqueued after part 0 on the same stream, overlaps that all-reduce. part -1 = both (= wunet_train_backward). */
+int wunet_train_backward_part(wunet_ctx *ctx, const float *x, const float *y, const float *dy, int B, int T,
+                              const float *const *conv_w, const float *const *bn_weight, const float *const *bn_bias,
+                              const float *out_w, float *const *g_conv_w, float *const *g_conv_b, float *const *g_bn_weight,
+                              float *const *g_bn_bias, float *g_out_w, float *g_out_b, void *workspace, size_t workspace_bytes,
+                              void *stream, int part);
 
 /* Introspection for tests and tuning, host-only (needs no GPU, no context): the tiling the bf16 path would use for conv
  * block `block` (1 .. 2*n_layers; block 0 = first encoder runs on CUDA cores) at batch B, frame length T, on a device with

@@ -81,11 +81,14 @@ def test_eval_forward_has_no_cpu_fallback():
         m(torch.zeros(1, 1, 16384))
 
 
-def test_train_mode_raises_unless_opted_in():
-    m = Model(n_layers=2, channels_interval=4)
+def test_train_mode_backends():
+    m = Model(n_layers=2, channels_interval=4)               # default: the native training step, CUDA only
     m.train()
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
         m(torch.zeros(1, 1, 16))
+    m0 = Model(n_layers=2, channels_interval=4, train_backend="none").train()
+    with pytest.raises(NotImplementedError):
+        m0(torch.zeros(1, 1, 16))
     m2 = Model(n_layers=2, channels_interval=4, train_backend="torch").train()
     assert m2(torch.zeros(2, 1, 16)).shape == (2, 1, 16)
 

@@ -142,12 +142,14 @@ def test_forward_host_matches_device_path(state_full):
 # ---- bf16 / tcgen05 path (BASELINE.json configs[2]) -------------------------------------------------------
 # Every activation is stored in bf16 (8 mantissa bits: relative rounding 2^-9 = 0.2 %) and every conv uses bf16
 # operands with fp32 accumulation, so the per-level bound is relative to the level's dynamic range:
-BF16_LEVEL_REL = 1.5e-2     # max-abs(level error) / max-abs(level) ; measured 0.3-0.5 %
-BF16_OUT_TOL = 5e-3         # max-abs on the tanh output (|y| <= 0.35 here); measured 6e-4
+BF16_LEVEL_REL = 8e-3       # max-abs(level error) / max-abs(level) ; measured 0.3-0.5 %
+BF16_OUT_TOL = 2e-3         # max-abs on the tanh output (|y| <= 0.35 here); measured 6e-4 (~2e-3 for bf16 operands)
 
 
-def bf16_model(n, ci, st):
-    os.environ["WUNET_TC_STORE_LAST"] = "1"      # also materialise the last decoder block (normally fused with the head)
+def bf16_model(n, ci, st, store_last=False):
+    """store_last=False is the benchmarked variant (last decoder block fused with the head, never stored); True also
+    materialises that block so that read_level(2n) works (the flag is read when the library creates the model's context)."""
+    os.environ["WUNET_TC_STORE_LAST"] = "1" if store_last else "0"
     return make_model(n, ci, st, "bf16")
 
 
@@ -156,27 +158,38 @@ def test_bf16_small_config_all_levels(golden_dir):
     n, ci, T, B = int(g["n_layers"]), int(g["channels_interval"]), int(g["T"]), int(g["B"])
     st = wo.make_state(n, ci, seed=int(g["state_seed"]))
     x = wo.make_input(B, T, seed=int(g["input_seed"]))
-    m = bf16_model(n, ci, st)
+    m = bf16_model(n, ci, st, store_last=True)
     y = run(m, x)
     for i in range(2 * n + 1):
         lv = m.read_level(i, B, T).cpu().numpy()
         ref = g[f"level_{i}"]
         assert np.abs(lv - ref).max() <= BF16_LEVEL_REL * np.abs(ref).max(), f"level {i}"
     assert np.abs(y - g["y"]).max() <= BF16_OUT_TOL
+    y_fused = run(bf16_model(n, ci, st), x)                  # the variant that is benchmarked: head fused, no store
+    assert np.array_equal(y_fused, y)
 
 
 def test_bf16_full_config_all_levels_vs_oracle(full, state_full):
     x = wo.make_input(2, 16384, seed=int(full["input_seed"]))
     want, levels = wo.COracle(12, 24).forward(state_full, x, return_levels=True)
-    m = bf16_model(12, 24, state_full)
+    m = bf16_model(12, 24, state_full, store_last=True)
     y = run(m, x)
+    rels = []
     for i in range(25):
         lv = m.read_level(i, 2, 16384).cpu().numpy()
         err = np.abs(lv - levels[i]).max()
+        rels.append(float(err / np.abs(levels[i]).max()))
         assert err <= BF16_LEVEL_REL * np.abs(levels[i]).max(), f"level {i}: {err}"
+    print("bf16 per-level relative errors: " + " ".join("%.4f" % r for r in rels))
+    print("bf16 output max-abs error vs oracle: %.3e" % np.abs(y - want).max())
     assert np.abs(y - full["y"]).max() <= BF16_OUT_TOL
     assert np.abs(y - want).max() <= BF16_OUT_TOL
     assert m.last_launch_count() == 25          # enc0 + 24 fused conv blocks (head fused into the last one)
+    m2 = bf16_model(12, 24, state_full)         # benchmarked variant: no store of the last block
+    y2 = run(m2, x)
+    assert np.array_equal(y2, y)
+    with pytest.raises(_lib.WunetError, match="not materialised"):
+        m2.read_level(24, 2, 16384)
 
 
 def test_bf16_odd_shapes_vs_oracle(state_full):
@@ -189,19 +202,22 @@ def test_bf16_odd_shapes_vs_oracle(state_full):
 
 
 def test_bf16_config3_batch256_properties(state_full):
-    """BASELINE.json configs[2] size (B=256): oracle-checked frames + batch-permutation invariance (bit exact)."""
+    """BASELINE.json configs[2] size (B=256), the benchmarked kernel variant (head fused, last block not stored):
+    16 oracle-checked frames spread over the batch + batch-permutation invariance (bit exact)."""
     B = 256
     x = wo.make_input(B, 16384, seed=2468)
     m = bf16_model(12, 24, state_full)
     y = run(m, x)
-    pick = [0, 100, 255]
+    pick = [0, 1, 17, 31, 64, 100, 127, 128, 129, 150, 177, 200, 222, 240, 254, 255]
     want = wo.COracle(12, 24).forward(state_full, x[pick])
-    assert np.abs(y[pick] - want).max() <= BF16_OUT_TOL
+    err = float(np.abs(y[pick] - want).max())
+    print("bf16 B=256 (benchmarked variant): max-abs error over 16 frames %.3e" % err)
+    assert err <= BF16_OUT_TOL
     perm = np.random.default_rng(1).permutation(B)
     assert np.array_equal(run(m, x[perm]), y[perm])
     # batches >= 128 take the tuned tilings of wunet_tc.cu (kTuned), small batches the generic rules: the K-loop order,
     # hence every output bit, must not depend on the tiling
-    assert np.array_equal(run(m, x[pick]), y[pick])
+    assert np.array_equal(run(m, x[pick[:3]]), y[pick[:3]])
     assert np.isfinite(y).all() and np.abs(y).max() < 1.0
 
 

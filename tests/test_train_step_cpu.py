@@ -39,6 +39,25 @@ flat = torch.cat([p.detach().reshape(-1) for p in params])
 gathered = [torch.zeros_like(flat) for _ in range(world)]
 dist.all_gather(gathered, flat)
 assert torch.equal(gathered[0], gathered[1]), "ranks diverged after the optimizer step"
+# the same through the public step (trainer/trainer.py:34-38 + all-reduce) with the composite backend of the drop-in model
+from wave_u_net_for_speech_enhancement_b200 import Model
+from wave_u_net_for_speech_enhancement_b200.train_step import train_step, GradientBucket
+m = Model(n, ci, train_backend="torch")
+m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in st.items()})
+m.train()
+assert not m.reduces_gradients                               # only the native backend reduces inside backward()
+opt = torch.optim.Adam(m.parameters(), lr=1e-3, betas=(0.9, 0.999))
+loss = train_step(m, opt, lambda c, e: torch.nn.functional.mse_loss(e, c), torch.from_numpy(noisy[sl]), torch.from_numpy(clean[sl]))
+flat = torch.cat([p.detach().reshape(-1) for p in m.parameters()])
+gathered = [torch.zeros_like(flat) for _ in range(world)]
+dist.all_gather(gathered, flat)
+assert torch.equal(gathered[0], gathered[1]), "model replicas diverged after train_step"
+# bucket layout: backward-completion order, two parts, every view aligned
+b = GradientBucket([p.shape for p in m.parameters()], 2 * n + 1, "cpu")
+names = [k for k, _ in m.named_parameters()]
+first = [names[i] for i, v in enumerate(b.views) if v.storage_offset() < b.split]
+assert all(k.startswith(("out.", "decoder.")) for k in first) and len(first) == 2 + 4 * n
+assert all(v.storage_offset() % 4 == 0 for v in b.views) and b.split % 128 == 0
 if rank == 0:
     print("ALLREDUCE_OK")
 dist.destroy_process_group()

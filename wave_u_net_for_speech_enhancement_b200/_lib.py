@@ -52,6 +52,7 @@ def load() -> ctypes.CDLL:
     lib.wunet_train_workspace_bytes.restype = cs
     lib.wunet_train_forward.argtypes = [vp, vp, vp, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_float, vp, cs, vp]
     lib.wunet_train_backward.argtypes = [vp, vp, vp, vp, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, cs, vp]
+    lib.wunet_train_backward_part.argtypes = [vp, vp, vp, vp, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, cs, vp, ci]
     _lib = lib
     return lib
 
@@ -65,7 +66,7 @@ EXPORTED_SYMBOLS = [
     "wunet_version", "wunet_last_error", "wunet_create", "wunet_destroy", "wunet_num_blocks", "wunet_block_shape",
     "wunet_set_weights", "wunet_workspace_bytes", "wunet_forward", "wunet_forward_host", "wunet_stream_submit", "wunet_stream_wait", "wunet_read_level",
     "wunet_last_launch_count", "wunet_profile_enable", "wunet_profile_read", "wunet_debug_plan",
-    "wunet_train_workspace_bytes", "wunet_train_forward", "wunet_train_backward",
+    "wunet_train_workspace_bytes", "wunet_train_forward", "wunet_train_backward", "wunet_train_backward_part",
 ]
 
 PLAN_FIELDS = ["L", "Cin0", "Cin1", "Cout", "Npad", "Nh", "nsplit", "Nstride", "MT", "nacc", "packed", "FR", "S", "m_tiles",

@@ -474,6 +474,16 @@ int wunet_train_backward(wunet_ctx *c, const float *x, const float *y, const flo
                          float *const *g_conv_w, float *const *g_conv_b, float *const *g_bn_weight, float *const *g_bn_bias,
                          float *g_out_w, float *g_out_b, void *workspace, size_t workspace_bytes, void *stream)
 {
+    return wunet_train_backward_part(c, x, y, dy, B, T, conv_w, bn_weight, bn_bias, out_w, g_conv_w, g_conv_b, g_bn_weight,
+                                     g_bn_bias, g_out_w, g_out_b, workspace, workspace_bytes, stream, -1);
+}
+
+int wunet_train_backward_part(wunet_ctx *c, const float *x, const float *y, const float *dy, int B, int T,
+                              const float *const *conv_w, const float *const *bn_weight, const float *const *bn_bias,
+                              const float *out_w, float *const *g_conv_w, float *const *g_conv_b, float *const *g_bn_weight,
+                              float *const *g_bn_bias, float *g_out_w, float *g_out_b, void *workspace, size_t workspace_bytes,
+                              void *stream, int part)
+{
     int rc = check_shape(c, B, T);
     if (rc != WUNET_OK) return rc;
     if (!x || !y || !dy || !workspace || !conv_w || !bn_weight || !bn_bias || !out_w || !g_conv_w || !g_conv_b || !g_bn_weight ||
@@ -484,7 +494,7 @@ int wunet_train_backward(wunet_ctx *c, const float *x, const float *y, const flo
     CUDA_TRY(cudaSetDevice(c->device));
     const TrainParams P{conv_w, nullptr, bn_weight, bn_bias, nullptr, nullptr, out_w, nullptr};
     const TrainGrads G{g_conv_w, g_conv_b, g_bn_weight, g_bn_bias, g_out_w, g_out_b};
-    if (train_backward(c->n, c->ci, x, y, dy, B, T, P, G, workspace, static_cast<cudaStream_t>(stream)))
+    if (train_backward(c->n, c->ci, x, y, dy, B, T, P, G, workspace, static_cast<cudaStream_t>(stream), part))
         return fail(WUNET_ECUDA, "%s", train_error());
     return WUNET_OK;
 }

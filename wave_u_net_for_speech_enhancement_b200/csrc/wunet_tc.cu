@@ -233,8 +233,8 @@ struct TcParams {
     const float *head_w;       // [C+1]
     const float *head_b;       // [1]
     long long *trace;          // WUNET_TC_TRACE builds: per-role clock64 stamps of CTA 0 (development)
-    int exp;                   // experimental code paths of the X = 1 kernel instantiations (WUNET_TC_EXP bit mask); 0 otherwise
-    // experimental (exp bit 1): the last K chunk of a decoder block is [skip tail (TMA) | upsampled tail (producers)] in ONE stage
+    // merged tail chunk (MG = 1 instantiations): the last K chunk of a decoder block is [skip tail (TMA) | upsampled tail
+    // (producers)] in ONE stage - one K chunk fewer for dec6 / dec9 / dec10 of the reference architecture
     int mg;                    // 1: chunk_map's last entry (0x40) is such a merged chunk
     int mg_vo, mg_nvec;        // first 16-byte vector / number of vectors the producers write in it
     int mg_nk, mg_kslot;       // its K16 steps, its 64-wide slot in the packed weights
@@ -260,12 +260,12 @@ inline size_t smem_total(const TcParams &p) { return smem_map(p).bars + 8 * (8 +
 
 // K-loop position c -> (segment, chunk index inside the segment, K16 steps, 64-wide slot in the packed weights)
 struct ChunkInfo { bool up; int idx, nk, kslot; bool merged; int vo, nvec; };
-template <bool UPCAT, int X>
+template <bool UPCAT, int MG>
 __device__ __forceinline__ ChunkInfo chunk_info(const TcParams &p, int c)
 {
     ChunkInfo ci;
     const int m = p.chunk_map[c];
-    if (X != 0 && UPCAT && (m & 0x40)) {          // merged tail chunk: TMA fills the leading vectors, the producers the next ones
+    if (MG != 0 && UPCAT && (m & 0x40)) {          // merged tail chunk: TMA fills the leading vectors, the producers the next ones
         ci.up = true; ci.merged = true;
         ci.idx = p.mg_up_idx; ci.nk = p.mg_nk; ci.kslot = p.mg_kslot; ci.vo = p.mg_vo; ci.nvec = p.mg_nvec;
         return ci;
@@ -283,9 +283,9 @@ __device__ __forceinline__ ChunkInfo chunk_info(const TcParams &p, int c)
 // -------------------------------------------------------------------------------------------------
 // the conv kernel
 // -------------------------------------------------------------------------------------------------
-// X = 0: the validated kernel. X = 1: the same kernel plus experimental paths selected at run time by p.exp (kept in separate
+// MG = 1: decoder instantiations whose K loop ends in a merged tail chunk (p.mg); MG = 0 everything else (kept in separate
 // instantiations so that the code of the validated ones does not change while they are being developed).
-template <int KS, bool UPCAT, int EW, int PW, int X>
+template <int KS, bool UPCAT, int EW, int PW, int MG>
 __global__ void __launch_bounds__(64 + 32 * (EW + PW), EW == kEpiWarpsSmall ? 2 : 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmO, const TcParams p)
@@ -303,7 +303,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t a_full = bars, a_empty = bars + 32, b_full = bars + 64, b_empty = bars + 64 + 8 * kMaxBStages;
     const uint32_t acc_full = bars + 64 + 16 * kMaxBStages, acc_empty = acc_full + 16;
     const uint32_t tmem_slot = acc_empty + 16;
-    const uint32_t a_tma = tmem_slot + 16;            // [4], X = 1 kernels with a merged chunk only (smem_total reserves them)
+    const uint32_t a_tma = tmem_slot + 16;            // [4], MG = 1 kernels (merged tail chunk) only (smem_total reserves them)
     volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(base_ptr + sm.bars + 64 + 16 * kMaxBStages + 32);
 
     // Programmatic dependent launch: let the next block's kernel be scheduled as our CTAs retire, so its prologue (barrier
@@ -331,7 +331,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_init(acc_empty + 8 * s, kEpilogueWarps);
         }
         for (int s = 0; s < min(p.nb, kMaxBStages); ++s) { mbar_init(b_full + 8 * s, 1); mbar_init(b_empty + 8 * s, 1); }
-        if (X != 0 && p.mg)
+        if (MG != 0 && p.mg)
             for (int s = 0; s < 4; ++s) mbar_init(a_tma + 8 * s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -376,7 +376,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (!blocking && !mbar_test(a_empty + 8 * sa, pa ^ 1)) return false;
                 int b0, l0, n0;
                 tile_coords(a_tile, b0, l0, n0);
-                const ChunkInfo aci = chunk_info<UPCAT, X>(p, a_c);
+                const ChunkInfo aci = chunk_info<UPCAT, MG>(p, a_c);
                 const bool from_tma = !aci.up;
                 TRACE(0, tr0);
                 mbar_wait(a_empty + 8 * sa, pa ^ 1);
@@ -388,7 +388,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int op = 0; op < p.nops; ++op)
                         tma_load_3d(base + sm.a + sa * p.a_stage_bytes + op * p.R1 * 128, &tmA, a_full + 8 * sa, cc * 64,
                                     lcoord + op * p.R1, b0);
-                } else if (X != 0 && aci.merged) {
+                } else if (MG != 0 && aci.merged) {
                     // skip tail by TMA into the leading vectors of the stage (zero fill behind it), completion on a_tma: the
                     // producers add the upsampled tail once it has landed and complete a_full
                     const int lcoord = l0 - PAD;
@@ -408,7 +408,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 // the whole packed weight set of this block (nchunks x KS tiles of [Nh x 64]) is loaded once per CTA
                 mbar_expect_tx(b_full, (uint32_t)p.nchunks * p.ngroups * p.tg * p.Nh * 128);
                 for (int c = 0; c < p.nchunks; ++c) {
-                    const int kslot = chunk_info<UPCAT, X>(p, c).kslot;
+                    const int kslot = chunk_info<UPCAT, MG>(p, c).kslot;
                     for (int g = 0; g < p.ngroups; ++g)
                         tma_load_3d(base + sm.b + (uint32_t)(c * p.ngroups + g) * p.b_stage_bytes, &tmW, b_full, kslot * 64, 0, g * p.tg);
                 }
@@ -423,7 +423,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     // the weight groups of this chunk go out as soon as their ring slots free up; the A tile of the NEXT
                     // chunk is slipped in between them the moment its stage is released (it never blocks the weights)
                     bool a_done = false;
-                    const int kslot = chunk_info<UPCAT, X>(p, c).kslot;
+                    const int kslot = chunk_info<UPCAT, MG>(p, c).kslot;
                     for (int g = 0; g < (p.resident ? 0 : p.ngroups); ++g) {
                         if (!a_done) a_done = issue_a(false);
                         mbar_wait(b_empty + 8 * sb, pb ^ 1);
@@ -440,106 +440,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ======================= MMA issuer =======================
         // One elected lane runs the whole role (barrier waits included): every warp-level reconvergence between two weight
         // stages costs tensor-pipe idle time, because the asynchronous MMA queue is only a few instructions deep.
-        if (X != 0 && (p.exp & 1)) {
-            // ---- experimental issue loop (WUNET_TC_EXP bit 0): the barriers of the NEXT weight stage are tested and its
-            // descriptors built before the LAST tap of the current stage is issued, so that the boundary bookkeeping
-            // (chunk lookup, two barrier tests, fences, descriptor words) overlaps MMAs that are still queued; a failed
-            // test falls back to the blocking wait after the tap. Trace of dec10: ~900 cycles per K-chunk boundary.
-            if (elect_one()) {
-                int sa = 0, pa = 0, sb = 0, pb = 0, it = 0;
-                const uint32_t b_step = ((uint32_t)p.Nh * 128) >> 4;
-                const uint32_t hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
-                auto desc_lo = [](uint32_t addr) { return ((addr >> 4) & 0x3FFFu) | (1u << 16); };
-                if (p.resident) { mbar_wait(b_full, 0); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-                const int nstages = p.nchunks * p.ngroups;
-                int nk = 0, nnk = 0;
-                uint32_t a_lo = 0, b_lo = 0, na_lo = 0, nb_lo = 0;
-                bool have = false;                                   // the next stage's barriers passed and its descriptors are built
-                bool acc_ready = false;                              // ... including, across a tile boundary, the accumulator buffer
-                for (int tile = first_tile; tile < total_tiles; tile += gridDim.x, ++it) {
-                    int b0, l0, n0;
-                    tile_coords(tile, b0, l0, n0);
-                    const int Nthis = min(p.Nh, p.Npad - n0);
-                    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Nthis >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-                    const int buf = (p.nacc == 2) ? (it & 1) : 0;
-                    const uint32_t use = (p.nacc == 2) ? (uint32_t)(it >> 1) : (uint32_t)it;
-                    if (!acc_ready) {
-                        mbar_wait(acc_empty + 8 * buf, (use & 1) ^ 1);
-                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    }
-                    acc_ready = false;
-                    const uint32_t acc_col = tmem_base + buf * p.MT * p.Nstride;
-                    int c = 0, g = 0;
-                    for (int s = 0; s < nstages; ++s) {
-                        if (!have) {
-                            if (g == 0) {
-                                nk = chunk_info<UPCAT, X>(p, c).nk;
-                                mbar_wait(a_full + 8 * sa, pa);
-                                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                                a_lo = desc_lo(base + sm.a + sa * p.a_stage_bytes);
-                            }
-                            uint32_t b_base;
-                            if (p.resident) {
-                                b_base = base + sm.b + (uint32_t)(c * p.ngroups + g) * p.b_stage_bytes;
-                            } else {
-                                mbar_wait(b_full + 8 * sb, pb);
-                                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                                b_base = base + sm.b + sb * p.b_stage_bytes;
-                            }
-                            b_lo = desc_lo(b_base);
-                        } else {
-                            a_lo = na_lo; b_lo = nb_lo; nk = nnk;
-                        }
-                        const int t_end = min(KS, (g + 1) * p.tg);
-#pragma unroll 1
-                        for (int t = g * p.tg; t < t_end - 1; ++t) {
-                            issue_tap(acc_col, p.MT, p.Nstride, nk, a_lo, b_lo, hi, idesc, (c | t) ? 1u : 0u);
-                            a_lo += 8;
-                            b_lo += b_step;
-                        }
-                        // peek at the next stage of this tile
-                        have = false;
-                        int c2 = c, g2 = g + 1;
-                        if (g2 == p.ngroups) { g2 = 0; ++c2; }
-                        const bool next_tile = c2 == p.nchunks;              // the next stage is the first one of this CTA's next tile
-                        if (!next_tile || tile + (int)gridDim.x < total_tiles) {
-                            const int cn = next_tile ? 0 : c2;
-                            int sa2 = sa, pa2 = pa, sb2 = sb, pb2 = pb;
-                            if (g2 == 0 && ++sa2 == p.na) { sa2 = 0; pa2 ^= 1; }
-                            if (++sb2 == p.nb) { sb2 = 0; pb2 ^= 1; }
-                            bool ok = true;
-                            if (next_tile) {
-                                const int it2 = it + 1;
-                                const int buf2 = (p.nacc == 2) ? (it2 & 1) : 0;
-                                const uint32_t use2 = (p.nacc == 2) ? (uint32_t)(it2 >> 1) : (uint32_t)it2;
-                                ok = mbar_test(acc_empty + 8 * buf2, (use2 & 1) ^ 1);
-                            }
-                            if (ok && g2 == 0) ok = mbar_test(a_full + 8 * sa2, pa2);
-                            if (ok && !p.resident) ok = mbar_test(b_full + 8 * sb2, pb2);
-                            if (ok) {
-                                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                                nnk = (g2 == 0) ? chunk_info<UPCAT, X>(p, cn).nk : nk;
-                                na_lo = (g2 == 0) ? desc_lo(base + sm.a + sa2 * p.a_stage_bytes) : a_lo + 8;   // + 8: past the tap issued below
-                                nb_lo = desc_lo(p.resident ? base + sm.b + (uint32_t)(cn * p.ngroups + g2) * p.b_stage_bytes
-                                                           : base + sm.b + sb2 * p.b_stage_bytes);
-                                have = true;
-                                acc_ready = next_tile;
-                            }
-                        }
-                        issue_tap(acc_col, p.MT, p.Nstride, nk, a_lo, b_lo, hi, idesc, (c | (t_end - 1)) ? 1u : 0u);
-                        a_lo += 8;
-                        if (!p.resident) umma_commit(b_empty + 8 * sb);
-                        if (++sb == p.nb) { sb = 0; pb ^= 1; }
-                        if (g == p.ngroups - 1) {
-                            umma_commit(a_empty + 8 * sa);
-                            if (++sa == p.na) { sa = 0; pa ^= 1; }
-                        }
-                        c = c2; g = g2;
-                    }
-                    umma_commit(acc_full + 8 * buf);
-                }
-            }
-        } else
         if (elect_one()) {
             int sa = 0, pa = 0, sb = 0, pb = 0, it = 0;
             int tr1 = 0; (void)tr1;
@@ -563,7 +463,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t acc_col = tmem_base + buf * p.MT * p.Nstride;
                 for (int c = 0; c < p.nchunks; ++c) {
-                    const int nk = chunk_info<UPCAT, X>(p, c).nk;
+                    const int nk = chunk_info<UPCAT, MG>(p, c).nk;
                     mbar_wait(a_full + 8 * sa, pa);
                     TRACE(1, tr1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -708,72 +608,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (lane == 0) mbar_arrive(acc_empty + 8 * buf);
         }
         if (p.bulk_store && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    } else if (UPCAT && KS == 1) {
-        // ======================= Toeplitz producers (experimental: first encoder block on the tensor cores) ============
-        // Conv1d(1 -> C, k=15) (model/unet_basic.py:10, first DownSamplingLayer) as a K = 48 GEMM per position:
-        // A[l][t] = x[l + t - 7], split into bf16 high and low parts, laid out [hi | lo | hi] (16 columns each, column 15 = 0),
-        // against B[co] = [w_hi | w_hi | w_lo]: D = x_hi w_hi + x_lo w_hi + x_hi w_lo, relative error ~2^-16 (the dropped
-        // x_lo w_lo term), i.e. fp32-grade before the bf16 store. A work item is (16 rows) x (one 16-column part): 32 aligned
-        // floats of x, the 31 bf16 pairs of both alignments, 32 16-byte stores. The loads for the next tile are issued after
-        // the stage hand-off (the fence before the arrive is a MEMBAR and would wait for them).
-        const int pt = (warp - kFirstProducer) * 32 + lane;
-        int sa = 0, pa = 0;
-        const int nitems = (p.rows_used >> 4) * 3;                     // rows_used = 128 * MT
-        float v[32];
-        auto load_x = [&](int tile, int item) {
-            int tb0, tl0, tn0;
-            tile_coords(tile, tb0, tl0, tn0);
-            const int run = item / 3;
-            const int first = tl0 + 16 * run - 8;                      // v[i] = x[first + i]; multiple of 8
-            const float *xp = p.x + (size_t)tb0 * p.T;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int i0 = first + 4 * q;
-                float4 f = make_float4(0.f, 0.f, 0.f, 0.f);                // Conv1d zero padding at the frame ends
-                if (tb0 < p.B && i0 >= 0 && i0 + 3 < p.T) f = __ldg(reinterpret_cast<const float4 *>(xp + i0));
-                v[4 * q] = f.x; v[4 * q + 1] = f.y; v[4 * q + 2] = f.z; v[4 * q + 3] = f.w;
-            }
-        };
-        if (first_tile < total_tiles && pt < nitems) load_x(first_tile, pt);
-        for (int tile = first_tile; tile < total_tiles; tile += gridDim.x) {
-            mbar_wait(a_empty + 8 * sa, pa ^ 1);
-            const uint32_t stage = base + sm.a + sa * p.a_stage_bytes;
-#pragma unroll 1
-            for (int item = pt; item < nitems; item += NPROD) {
-                if (item != pt) load_x(tile, item);                    // later rounds (fewer producer threads than items)
-                const int run = item / 3, part = item - run * 3;
-                const bool low = part == 1;
-                float sv[32];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) sv[i] = low ? v[i] - __bfloat162float(__float2bfloat16_rn(v[i])) : v[i];
-                uint32_t wo[15], we[16];
-#pragma unroll
-                for (int k = 0; k < 15; ++k) wo[k] = pack_bf16(sv[2 * k + 1], sv[2 * k + 2]);
-#pragma unroll
-                for (int k = 0; k < 16; ++k) we[k] = pack_bf16(sv[2 * k], sv[2 * k + 1]);
-#pragma unroll
-                for (int r = 0; r < 16; ++r) {
-                    // column t of row r is s[r + t + 1]; column 15 (high half of the last word) is forced to zero
-                    const int m = r >> 1;
-                    uint4 o0, o1;
-                    if (r & 1) {
-                        o0 = make_uint4(we[m + 1], we[m + 2], we[m + 3], we[m + 4]);
-                        o1 = make_uint4(we[m + 5], we[m + 6], we[m + 7], we[m + 8] & 0x0000ffffu);
-                    } else {
-                        o0 = make_uint4(wo[m], wo[m + 1], wo[m + 2], wo[m + 3]);
-                        o1 = make_uint4(wo[m + 4], wo[m + 5], wo[m + 6], wo[m + 7] & 0x0000ffffu);
-                    }
-                    const uint32_t rowaddr = stage + (uint32_t)(16 * run + r) * 128u;
-                    st_shared_v4_if(rowaddr + (uint32_t)(((2 * part) ^ (r & 7)) << 4), o0, true);
-                    st_shared_v4_if(rowaddr + (uint32_t)(((2 * part + 1) ^ (r & 7)) << 4), o1, true);
-                }
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor core reads
-            __syncwarp();
-            if (lane == 0) mbar_arrive(a_full + 8 * sa);
-            if (++sa == p.na) { sa = 0; pa ^= 1; }
-            if (tile + (int)gridDim.x < total_tiles && pt < nitems) load_x(tile + gridDim.x, pt);
-        }
     } else if (UPCAT) {
         // ======================= upsample producers (decoder) =======================
         // F.interpolate(scale_factor=2, mode="linear", align_corners=True) of the previous block's output, written straight
@@ -789,10 +623,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         bool pref = false;
         const int nruns = (p.rows_used + 15) >> 4;
         // a chunk whose first-round items can be prefetched into the register window one work unit ahead
-        auto unit_fast = [&](int c) { return !p.packed && chunk_info<UPCAT, X>(p, c).up; };
+        auto unit_fast = [&](int c) { return !p.packed && chunk_info<UPCAT, MG>(p, c).up; };
         // loads of item `item` of unit (frame ub0, first row ul0, K-loop position c) into the window
         auto fetch = [&](int ub0, int ul0, int c, int item) {
-            const ChunkInfo u = chunk_info<UPCAT, X>(p, c);
+            const ChunkInfo u = chunk_info<UPCAT, MG>(p, c);
             const int nvec = u.nvec;
             if (item >= nruns * nvec) return;
             const int run = item / nvec, vec = item - run * nvec;
@@ -811,7 +645,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // store instead of branches): the 16 rows are independent, and a branch per row serialises their dependent chains
         // (trace: ~3600 cycles per item with branches, the stage hand-off was waiting on it).
         auto emit = [&](uint8_t *dst, int l0, int c, int item, const uint4 (&w)[10]) {
-            const ChunkInfo u = chunk_info<UPCAT, X>(p, c);
+            const ChunkInfo u = chunk_info<UPCAT, MG>(p, c);
             const int nvec = u.nvec;
             const int run = item / nvec, vec = item - run * nvec;
             const int ch = u.idx * 64 + vec * 8;
@@ -849,10 +683,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (pt == 0) TRACE(4, tr4);
                 mbar_wait(a_empty + 8 * sa, pa ^ 1);
                 if (pt == 0) TRACE(4, tr4);
-                const ChunkInfo cu = chunk_info<UPCAT, X>(p, c);
+                const ChunkInfo cu = chunk_info<UPCAT, MG>(p, c);
                 bool emitted_fast = false;
                 if (cu.up) {
-                    if (X != 0 && cu.merged) {                               // the TMA part of this stage must have landed
+                    if (MG != 0 && cu.merged) {                               // the TMA part of this stage must have landed
                         mbar_wait(a_tma + 8 * sa, (tma_par >> sa) & 1u);
                         tma_par ^= 1u << sa;
                     }
@@ -909,7 +743,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     int nt = tile, nc = c + 1;
                     for (int hop = 0; hop < p.nchunks; ++hop) {
                         if (nc >= p.nchunks) { nc = 0; nt += gridDim.x; }
-                        if (chunk_info<UPCAT, X>(p, nc).up) break;
+                        if (chunk_info<UPCAT, MG>(p, nc).up) break;
                         ++nc;
                     }
                     if (nt < total_tiles && unit_fast(nc)) {
@@ -1039,26 +873,6 @@ __global__ void pack_tc_merged_kernel(const float *__restrict__ w, __nv_bfloat16
     wp[((size_t)t * Npad + co) * Ktot + (Ktot - 64) + j] = __float2bfloat16(v);
 }
 
-// experimental (WUNET_TC_EXP bit 2): first encoder block on the tensor cores. Weights [C][1][15] fp32 -> one [Npad][64] bf16 tile,
-// columns [w_hi(15) 0 | w_hi(15) 0 | w_lo(15) 0 | 0 x 16] matching the [x_hi | x_lo | x_hi] columns the Toeplitz producers write
-__global__ void pack_enc0_tc_kernel(const float *__restrict__ w, const float *__restrict__ scale, const float *__restrict__ shift,
-                                    __nv_bfloat16 *__restrict__ wp, float2 *__restrict__ ss, int C, int Npad)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < Npad * 64) {
-        const int co = i / 64, j = i - co * 64;
-        const int grp = j >> 4, t = j & 15;
-        float v = 0.f;
-        if (co < C && t < 15 && grp < 3) {
-            const float wf = w[co * 15 + t];
-            const float hi = __bfloat162float(__float2bfloat16_rn(wf));
-            v = (grp == 2) ? wf - hi : hi;
-        }
-        wp[i] = __float2bfloat16_rn(v);
-    }
-    if (i < Npad) ss[i] = (i < C) ? make_float2(scale[i], shift[i]) : make_float2(0.f, 0.f);
-}
-
 __global__ void nlc_bf16_to_ncl_f32_kernel(const __nv_bfloat16 *__restrict__ src, float *__restrict__ dst, int B, int L, int C)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;       // index into dst [B][C][L]
@@ -1080,7 +894,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
 struct TcLevel {
     int cin0, cin1, cout, k;
     int Npad, Ktot;
-    int mg_s = 0, mg_u = 0;            // experimental (WUNET_TC_EXP bit 1): channel tails of the skip / upsampled segment that share
+    int mg_s = 0, mg_u = 0;            // merged tail chunk: channel tails of the skip / upsampled segment that share
                                        // one extra 64-wide K slot at the end of the packed weights (0 = not merged)
     __nv_bfloat16 *wp = nullptr;
     float2 *ss = nullptr;
@@ -1098,7 +912,6 @@ struct TcPlanLevel {
     size_t smem;
     bool upcat;
     bool small;                        // two-CTAs-per-SM kernel flavour
-    bool ks1;                          // experimental first-encoder block on the tensor cores (KS = 1 instantiation, Toeplitz producers)
 };
 
 // Per-block tiling overrides for tuning sweeps: WUNET_TC_OVR="<block>:key=val,key=val;<block>:..." with keys
@@ -1165,7 +978,7 @@ struct TcState {
     bool store_last = false;           // WUNET_TC_STORE_LAST=1: also materialise the last decoder block (tests)
     bool attr_set = false;
     bool pdl = false;                  // programmatic dependent launch between the blocks (WUNET_TC_PDL=1); measured slower, off
-    int exp = 0;                       // WUNET_TC_EXP bit mask: experimental kernel paths (X = 1 instantiations), default 0
+    bool merge = true;                 // merged tail chunks (WUNET_TC_MERGE=0 switches them off for A/B measurements)
     int num_sms = 148;
     cudaStream_t copy_in = nullptr, copy_out = nullptr;     // host pipeline: H2D / D2H streams
     cudaEvent_t ev_in[8] = {}, ev_out[8] = {};
@@ -1205,7 +1018,7 @@ size_t tc_workspace_bytes(int n, int ci, int B, int T)
 
 // K segments and padded sizes of every block: encoders have one input segment, decoder block i concatenates the previous
 // block's (upsampled) output with the skip of encoder 2n - i (model/unet_basic.py:93-95)
-static void derive_levels(std::vector<TcLevel> &levels, const TcBlockSrc *blocks, int nblocks, int n, int exp = 0)
+static void derive_levels(std::vector<TcLevel> &levels, const TcBlockSrc *blocks, int nblocks, int n, bool merge = true)
 {
     for (int i = 0; i < nblocks; ++i) {
         TcLevel &lv = levels[i];
@@ -1217,7 +1030,7 @@ static void derive_levels(std::vector<TcLevel> &levels, const TcBlockSrc *blocks
         lv.w_src = blocks[i].w; lv.scale = blocks[i].scale; lv.shift = blocks[i].shift;
         lv.mg_s = lv.mg_u = 0;
         const int u = lv.cin0 % 64, sk = lv.cin1 % 64;
-        if ((exp & 2) && i > n && u > 0 && sk > 0 && u + sk <= 64 && u % 8 == 0 && sk % 8 == 0) {
+        if (merge && i > n && u > 0 && sk > 0 && u + sk <= 64 && u % 8 == 0 && sk % 8 == 0) {
             lv.mg_s = sk; lv.mg_u = u;
             lv.Ktot += 64;                                  // slot [skip tail | upsampled tail | 0] after the regular slots
         }
@@ -1244,7 +1057,7 @@ int tc_set_weights(TcState **pst, int n, int ci, const TcBlockSrc *blocks, int n
         st->store_last = e && e[0] == '1';
         const char *pe = getenv("WUNET_TC_PDL");
         st->pdl = pe && pe[0] == '1';
-        if (const char *xe = getenv("WUNET_TC_EXP")) st->exp = atoi(xe);
+        if (const char *xe = getenv("WUNET_TC_MERGE")) st->merge = xe[0] != '0';
 #ifdef WUNET_TC_TRACE
         if (const char *tl = getenv("WUNET_TC_TRACE_LEVEL")) {
             st->trace_level = atoi(tl);
@@ -1256,7 +1069,7 @@ int tc_set_weights(TcState **pst, int n, int ci, const TcBlockSrc *blocks, int n
     }
     st->out_w = out_w; st->out_b = out_b;
     st->plan_ws = nullptr;                               // weights moved: rebuild maps lazily
-    derive_levels(st->levels, blocks, nblocks, n, st->exp);
+    derive_levels(st->levels, blocks, nblocks, n, st->merge);
     if (ci % 8 != 0 || ci > 32) return 0;                // tensor-core path unsupported for this plan; forward reports it
     {
         // enc0 runs on CUDA cores from fp32 weights: keep a library-owned copy (include/wunet_b200.h: the caller's tensors are
@@ -1267,16 +1080,6 @@ int tc_set_weights(TcState **pst, int n, int ci, const TcBlockSrc *blocks, int n
         if (cudaMemcpyAsync(l0.w_own, blocks[0].w, wn, cudaMemcpyDeviceToDevice, stream) != cudaSuccess)
             return tc_fail("enc0 weight copy failed");
         l0.w_src = l0.w_own;
-    }
-    if (st->exp & 4) {
-        TcLevel &l0 = st->levels[0];
-        if (!l0.wp) {
-            if (cudaMalloc(&l0.wp, (size_t)l0.Npad * 64 * sizeof(__nv_bfloat16)) != cudaSuccess) return tc_fail("cudaMalloc(wp0) failed");
-            if (cudaMalloc(&l0.ss, l0.Npad * sizeof(float2)) != cudaSuccess) return tc_fail("cudaMalloc(ss0) failed");
-        }
-        pack_enc0_tc_kernel<<<(l0.Npad * 64 + 255) / 256, 256, 0, stream>>>(blocks[0].w, blocks[0].scale, blocks[0].shift, l0.wp, l0.ss,
-                                                                            l0.cout, l0.Npad);
-        if (cudaGetLastError() != cudaSuccess) return tc_fail("pack_enc0_tc_kernel launch failed");
     }
     for (int i = 1; i < nblocks; ++i) {                  // enc0 runs on CUDA cores from the fp32 weights
         TcLevel &lv = st->levels[i];
@@ -1530,37 +1333,6 @@ static int plan_block(const TcLevel &lv, int i, int n, int B, int T, int num_sms
     return 0;
 }
 
-// experimental: the first encoder block as an implicit GEMM with K = 48 (see the Toeplitz producers of conv_tc_kernel<1, ...>)
-static void plan_enc0_tc(int C, int B, int T, int num_sms, TcPlanLevel &P)
-{
-    TcParams &p = P.p;
-    memset(&p, 0, sizeof(p));
-    P.upcat = true; P.small = false; P.ks1 = true;
-    p.B = B; p.L = T; p.T = T; p.Cout = C;
-    p.Cin0 = 48; p.Cin1 = 0; p.nchunks0 = 1; p.nchunks = 1; p.chunk_map[0] = (unsigned char)0x80;
-    p.Npad = round_up(C, 16); p.Nh = p.Npad; p.Nstride = round_up(p.Nh, 32); p.nsplit = 1;
-    int MT = 4;
-    while (MT > 1 && 128 * MT > T) --MT;
-    p.MT = MT; p.packed = 0; p.S = 0; p.FR = 1;
-    p.tiles_per_frame = (T + 128 * MT - 1) / (128 * MT);
-    p.m_tiles = B * p.tiles_per_frame;
-    p.nacc = 2;
-    uint32_t cols = 32;
-    while ((int)cols < 2 * MT * p.Nstride) cols <<= 1;
-    p.tmem_cols = cols;
-    p.rows_used = 128 * MT; p.nops = 1; p.R1 = 128 * MT; p.a_tx_bytes = 0;
-    p.a_stage_bytes = (uint32_t)(128 * MT * 128);
-    p.b_stage_bytes = (uint32_t)round_up(p.Nh * 128, 1024);
-    p.resident = 1; p.nb = 1; p.tg = 1; p.ngroups = 1; p.na = 3;
-    p.n_epi = kEpiWarpsLarge;
-    p.bulk_store = (T % (128 * MT) == 0 && (long long)B * T < (1LL << 31)) ? 1 : 0;
-    p.tile_begin = 0; p.tile_end = p.m_tiles;
-    P.threads = 64 + 32 * (kEpiWarpsLarge + kProducerWarpsLarge);
-    P.per_sm = 1;
-    P.smem = smem_total(p);
-    P.grid = dim3((unsigned)std::min(p.m_tiles, num_sms), 1, 1);
-}
-
 static int build_plan(TcState *st, const float *x, float *y, int B, int T, void *ws)
 {
     const int n = st->n;
@@ -1570,16 +1342,6 @@ static int build_plan(TcState *st, const float *x, float *y, int B, int T, void 
     pl.lv.assign(2 * n + 1, TcPlanLevel{});
     char *base = static_cast<char *>(ws);
     auto lvl = [&](int i) { return reinterpret_cast<__nv_bfloat16 *>(base + pl.off[i]); };
-    if (st->exp & 4) {
-        const TcLevel &lv = st->levels[0];
-        TcPlanLevel &P = pl.lv[0];
-        plan_enc0_tc(lv.cout, B, T, st->num_sms, P);
-        TcParams &p = P.p;
-        p.ss = lv.ss; p.out = lvl(0);
-        if (make_map(st, &P.tmW, lv.wp, 64, (uint64_t)lv.Npad, 1, 128, (uint64_t)lv.Npad * 128, 64, (uint32_t)p.Nh, 1)) return -1;
-        P.tmA = P.tmW;                                   // no TMA input chunks: the producers build the whole operand
-        if (make_map_out(st, &P.tmO, p.out, (uint64_t)lv.cout, (uint64_t)B * T)) return -1;
-    }
     for (int i = 1; i < 2 * n + 1; ++i) {
         const TcLevel &lv = st->levels[i];
         TcPlanLevel &P = pl.lv[i];
@@ -1632,7 +1394,8 @@ int tc_debug_plan(int n, int ci, const TcBlockSrc *blocks, int nblocks, int B, i
     if (ci % 8 != 0 || ci > 32) return tc_fail("bf16 tcgen05 path needs channels_interval %% 8 == 0 and <= 32 (got %d)", ci);
     if (cap < 32 || !f) return tc_fail("need room for 32 fields");
     std::vector<TcLevel> levels(nblocks);
-    derive_levels(levels, blocks, nblocks, n);
+    const char *mge = getenv("WUNET_TC_MERGE");
+    derive_levels(levels, blocks, nblocks, n, !(mge && mge[0] == '0'));
     const char *ovr = getenv("WUNET_TC_OVR");
     TcPlanLevel P{};
     if (plan_block(levels[block], block, n, B, T, num_sms, ovr ? ovr : "", P)) return -1;
@@ -1655,11 +1418,8 @@ static int tc_prepare(TcState *st, const float *x, float *y, int B, int T, void 
         cudaFuncSetAttribute(conv_tc_kernel<5, true, kEpiWarpsLarge, kProducerWarpsLarge, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         cudaFuncSetAttribute(conv_tc_kernel<15, false, kEpiWarpsSmall, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         cudaFuncSetAttribute(conv_tc_kernel<5, true, kEpiWarpsSmall, kProducerWarpsSmall, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
-        cudaFuncSetAttribute(conv_tc_kernel<15, false, kEpiWarpsLarge, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         cudaFuncSetAttribute(conv_tc_kernel<5, true, kEpiWarpsLarge, kProducerWarpsLarge, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
-        cudaFuncSetAttribute(conv_tc_kernel<15, false, kEpiWarpsSmall, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         cudaFuncSetAttribute(conv_tc_kernel<5, true, kEpiWarpsSmall, kProducerWarpsSmall, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
-        cudaFuncSetAttribute(conv_tc_kernel<1, true, kEpiWarpsLarge, kProducerWarpsLarge, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         cudaFuncSetAttribute(enc0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
         int dev = 0, sms = 0;
         if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
@@ -1712,20 +1472,13 @@ static int launch_block(TcState *st, int i, int t0, int t1, cudaStream_t stream,
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = st->pdl ? 1 : 0;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    p.exp = st->exp;
-    if (st->exp == 0) {
-        if (P.upcat && !P.small) cudaLaunchKernelEx(&cfg, conv_tc_kernel<5, true, kEpiWarpsLarge, kProducerWarpsLarge, 0>, P.tmA, P.tmW, P.tmO, p);
-        else if (P.upcat) cudaLaunchKernelEx(&cfg, conv_tc_kernel<5, true, kEpiWarpsSmall, kProducerWarpsSmall, 0>, P.tmA, P.tmW, P.tmO, p);
-        else if (!P.small) cudaLaunchKernelEx(&cfg, conv_tc_kernel<15, false, kEpiWarpsLarge, 0, 0>, P.tmA, P.tmW, P.tmO, p);
-        else cudaLaunchKernelEx(&cfg, conv_tc_kernel<15, false, kEpiWarpsSmall, 0, 0>, P.tmA, P.tmW, P.tmO, p);
-    } else if (P.ks1) {
-        cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, true, kEpiWarpsLarge, kProducerWarpsLarge, 1>, P.tmA, P.tmW, P.tmO, p);
-    } else {
-        if (P.upcat && !P.small) cudaLaunchKernelEx(&cfg, conv_tc_kernel<5, true, kEpiWarpsLarge, kProducerWarpsLarge, 1>, P.tmA, P.tmW, P.tmO, p);
-        else if (P.upcat) cudaLaunchKernelEx(&cfg, conv_tc_kernel<5, true, kEpiWarpsSmall, kProducerWarpsSmall, 1>, P.tmA, P.tmW, P.tmO, p);
-        else if (!P.small) cudaLaunchKernelEx(&cfg, conv_tc_kernel<15, false, kEpiWarpsLarge, 0, 1>, P.tmA, P.tmW, P.tmO, p);
-        else cudaLaunchKernelEx(&cfg, conv_tc_kernel<15, false, kEpiWarpsSmall, 0, 1>, P.tmA, P.tmW, P.tmO, p);
-    }
+    if (P.upcat && p.mg) {
+        if (!P.small) cudaLaunchKernelEx(&cfg, conv_tc_kernel<5, true, kEpiWarpsLarge, kProducerWarpsLarge, 1>, P.tmA, P.tmW, P.tmO, p);
+        else cudaLaunchKernelEx(&cfg, conv_tc_kernel<5, true, kEpiWarpsSmall, kProducerWarpsSmall, 1>, P.tmA, P.tmW, P.tmO, p);
+    } else if (P.upcat && !P.small) cudaLaunchKernelEx(&cfg, conv_tc_kernel<5, true, kEpiWarpsLarge, kProducerWarpsLarge, 0>, P.tmA, P.tmW, P.tmO, p);
+    else if (P.upcat) cudaLaunchKernelEx(&cfg, conv_tc_kernel<5, true, kEpiWarpsSmall, kProducerWarpsSmall, 0>, P.tmA, P.tmW, P.tmO, p);
+    else if (!P.small) cudaLaunchKernelEx(&cfg, conv_tc_kernel<15, false, kEpiWarpsLarge, 0, 0>, P.tmA, P.tmW, P.tmO, p);
+    else cudaLaunchKernelEx(&cfg, conv_tc_kernel<15, false, kEpiWarpsSmall, 0, 0>, P.tmA, P.tmW, P.tmO, p);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return tc_fail("conv_tc level %d launch failed: %s", i, cudaGetErrorString(e));
     return 0;
@@ -1738,8 +1491,7 @@ int tc_forward(TcState *st, const float *x, float *y, int B, int T, void *ws, cu
     const int n = st->n;
     int nl = 0;
     if (ev) cudaEventRecord(ev[0], stream);
-    if (st->exp & 4) { if (launch_block(st, 0, 0, -1, stream, x, y)) return -1; }
-    else if (launch_enc0(st, x, 0, B, T, ws, stream)) return -1;
+    if (launch_enc0(st, x, 0, B, T, ws, stream)) return -1;
     ++nl;
     if (ev) cudaEventRecord(ev[1], stream);
     for (int i = 1; i < 2 * n + 1; ++i) {
@@ -1781,10 +1533,7 @@ int tc_forward_host(TcState *st, const float *x_host, float *y_host, float *x_de
         cudaMemcpyAsync(x_dev + c * chunk, x_host + c * chunk, chunk * sizeof(float), cudaMemcpyHostToDevice, st->copy_in);
         cudaEventRecord(st->ev_in[c], st->copy_in);
         cudaStreamWaitEvent(stream, st->ev_in[c], 0);
-        if (st->exp & 4) {
-            const int tpf = st->plan.lv[0].p.tiles_per_frame;
-            if (launch_block(st, 0, c * bc * tpf, (c + 1) * bc * tpf, stream, x_dev, y_dev)) return -1;
-        } else if (launch_enc0(st, x_dev, c * bc, bc, T, ws, stream)) return -1;
+        if (launch_enc0(st, x_dev, c * bc, bc, T, ws, stream)) return -1;
         ++nl;
     }
     for (int i = 1; i < 2 * n; ++i) {

@@ -1,6 +1,6 @@
 // wunet_train.cu — training step of the Wave-U-Net: forward with BatchNorm1d in training mode and the
 // backward pass, fp32, NCL layout, straight CUDA-core kernels written for correctness first (one formula per kernel, in the
-// order autograd would replay them). NOT YET RUN ON A GPU: reached only through Model(train_backend="native").
+// order autograd would replay them); validated on a B200 against float64 golden steps (tests/test_train_gpu.py).
 //
 // Reference: trainer/trainer.py:34-38 (forward, loss.backward()), model/unet_basic.py:77-100 with the BatchNorm1d of
 // :12, :25, :55 in .train() mode (batch statistics; running statistics updated with momentum 0.1 and the unbiased variance).
@@ -441,7 +441,7 @@ int train_forward(int n, int ci, const float *x, float *y, int B, int T, const T
 }
 
 int train_backward(int n, int ci, const float *x, const float *y, const float *dy, int B, int T, const TrainParams &P,
-                   const TrainGrads &G, void *workspace, cudaStream_t st)
+                   const TrainGrads &G, void *workspace, cudaStream_t st, int part)
 {
     std::vector<Shape> sh;
     shapes_of(n, ci, T, sh);
@@ -449,11 +449,15 @@ int train_backward(int n, int ci, const float *x, const float *y, const float *d
     layout_of(sh, B, lo);
     float *ws = static_cast<float *>(workspace);
     const int last = 2 * n, C = sh[last].cout;
-    cudaMemsetAsync(G.out_w, 0, (C + 1) * sizeof(float), st);
-    cudaMemsetAsync(G.out_b, 0, sizeof(float), st);
-    train_head_bwd_kernel<<<blocks_for((long long)B * T, 256), 256, 0, st>>>(dy, y, ws + lo.act[last], x, P.out_w, ws + lo.ga[last],
-                                                                             G.out_w, G.out_b, B, C, T);
-    for (int i = last; i >= 0; --i) {
+    if (part < -1 || part > 1) return train_fail("training backward: part must be -1, 0 or 1 (got %d)", part);
+    if (part != 1) {
+        cudaMemsetAsync(G.out_w, 0, (C + 1) * sizeof(float), st);
+        cudaMemsetAsync(G.out_b, 0, sizeof(float), st);
+        train_head_bwd_kernel<<<blocks_for((long long)B * T, 256), 256, 0, st>>>(dy, y, ws + lo.act[last], x, P.out_w, ws + lo.ga[last],
+                                                                                 G.out_w, G.out_b, B, C, T);
+    }
+    const int i_hi = (part == 1) ? n : last, i_lo = (part == 0) ? n + 1 : 0;
+    for (int i = i_hi; i >= i_lo; --i) {
         const Shape &s = sh[i];
         float *ga = ws + lo.ga[i];                               // gradient of the activation; becomes dz in place
         const float *z = ws + lo.z[i];

@@ -27,8 +27,10 @@ size_t train_workspace_bytes(int n_layers, int ci, int B, int T);
 // y = model(x) with BatchNorm in training mode; keeps every pre-BN output and activation in `workspace` for the backward
 int train_forward(int n_layers, int ci, const float *x, float *y, int B, int T, const TrainParams &P, float momentum,
                   void *workspace, cudaStream_t stream);
-// gradients of every parameter for the upstream gradient dy of the output; `workspace` as left by train_forward
+// gradients of every parameter for the upstream gradient dy of the output; `workspace` as left by train_forward.
+// part: -1 = the whole backward; 0 = head + decoder blocks (their gradients are complete afterwards: a data-parallel caller
+// starts reducing them while part 1 runs); 1 = middle + encoder blocks (must follow part 0 on the same stream).
 int train_backward(int n_layers, int ci, const float *x, const float *y, const float *dy, int B, int T, const TrainParams &P,
-                   const TrainGrads &G, void *workspace, cudaStream_t stream);
+                   const TrainGrads &G, void *workspace, cudaStream_t stream, int part = -1);
 
 }  // namespace wunet

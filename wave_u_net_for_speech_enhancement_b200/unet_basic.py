@@ -170,22 +170,33 @@ class _NativeTrainStep(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gy):
+        from .train_step import GradientBucket, data_parallel_world
         lib = _lib.load()
         x, y, *params = ctx.saved_tensors
         nb = ctx.nb
         B, _, T = x.shape
         gy = gy.contiguous()
-        grads = [torch.empty_like(p) for p in params]
+        # all gradients live in ONE flat buffer laid out in backward-completion order (train_step.GradientBucket); autograd
+        # hands the views to .grad, so the all-reduce below needs no gather / scatter copies
+        bucket = GradientBucket([p.shape for p in params], nb, x.device)
+        grads = bucket.views
+        reduce = ctx.model.data_parallel != "off" and data_parallel_world() > 1
         with torch.cuda.device(x.device):
             c = ctx.model._context(x.device)
             stream = torch.cuda.current_stream(x.device).cuda_stream
             P = _NativeTrainStep._ptr_array
             sel = lambda ts, k: [ts[4 * i + k] for i in range(nb)]          # noqa: E731
-            _lib.check(lib.wunet_train_backward(c, x.data_ptr(), y.data_ptr(), gy.data_ptr(), B, T, P(sel(params, 0)),
-                                                P(sel(params, 2)), P(sel(params, 3)), params[-2].data_ptr(),
-                                                P(sel(grads, 0)), P(sel(grads, 1)), P(sel(grads, 2)), P(sel(grads, 3)),
-                                                grads[-2].data_ptr(), grads[-1].data_ptr(), ctx.ws.data_ptr(), ctx.ws.numel(),
-                                                stream))
+            for part in ((0, 1) if reduce else (-1,)):
+                _lib.check(lib.wunet_train_backward_part(c, x.data_ptr(), y.data_ptr(), gy.data_ptr(), B, T, P(sel(params, 0)),
+                                                         P(sel(params, 2)), P(sel(params, 3)), params[-2].data_ptr(),
+                                                         P(sel(grads, 0)), P(sel(grads, 1)), P(sel(grads, 2)), P(sel(grads, 3)),
+                                                         grads[-2].data_ptr(), grads[-1].data_ptr(), ctx.ws.data_ptr(),
+                                                         ctx.ws.numel(), stream, part))
+                if reduce:
+                    # head + decoder gradients are final after part 0: their all-reduce overlaps part 1 (middle + encoders)
+                    bucket.reduce_part(part)
+            if reduce:
+                bucket.finish()
         ctx.ws = None
         return (None, None, *grads)                          # no gradient for the model handle and for the input
 
@@ -196,15 +207,20 @@ class Model(nn.Module):
     Extra keyword arguments (not in the reference; configs pass ``"args": {}`` so defaults apply):
 
     precision      "fp32" (default; FFMA path, <=1e-4 vs the reference) or "bf16" (tcgen05 path).
-    train_backend  "none" (default): a forward in training mode raises
-                   NotImplementedError — the training step is SURVEY §8(f) row N1, not built yet.
-                   "torch": opt-in composite of torch ops with the reference's semantics so that the
-                   unchanged ``trainer/trainer.py`` loop can be driven for boundary tests; it is not
-                   part of the measured hot path.
+    train_backend  "native" (default): a forward in training mode runs ``wunet_train_forward`` (BatchNorm with batch
+                   statistics, running buffers updated) behind a ``torch.autograd.Function`` whose backward is
+                   ``wunet_train_backward_part``; the reference's loss, ``loss.backward()`` and optimizer run unchanged
+                   (trainer/trainer.py:34-38). fp32, validated against float64 golden steps on a B200.
+                   "torch": opt-in composite of torch ops with the reference's semantics (runs on CPU too), used by the
+                   CPU boundary tests that drive the unchanged ``trainer/trainer.py`` loop; not a measured hot path.
+                   "none": a forward in training mode raises NotImplementedError.
+    data_parallel  "auto" (default): when ``torch.distributed`` is initialised with more than one rank (one process per
+                   GPU) the native backward averages the gradients over the ranks — one flat bucket,
+                   all-reduced in two parts so that the first overlaps the rest of the backward. "off": never.
     """
 
     def __init__(self, n_layers: int = 12, channels_interval: int = 24, precision: str = "fp32",
-                 train_backend: str = "none"):
+                 train_backend: str = "native", data_parallel: str = "auto"):
         super().__init__()
         if precision not in _lib.PRECISIONS:
             raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}, got {precision!r}")
@@ -212,8 +228,11 @@ class Model(nn.Module):
             raise ValueError("train_backend must be 'none', 'torch' or 'native'")
         self.n_layers = n_layers
         self.channels_interval = channels_interval
+        if data_parallel not in ("auto", "off"):
+            raise ValueError("data_parallel must be 'auto' or 'off'")
         self.precision = precision
         self.train_backend = train_backend
+        self.data_parallel = data_parallel
         n, ci = n_layers, channels_interval
 
         enc_in = [1] + [i * ci for i in range(1, n)]
@@ -298,12 +317,18 @@ class Model(nn.Module):
             if self.train_backend == "native":
                 return self._forward_train_native(input)
             raise NotImplementedError(
-                "libwunet_b200 implements the eval-mode forward (SURVEY §8 rows a–e). Training-mode BatchNorm / "
-                "autograd (row N1) is not built yet: call model.eval(), or construct the model with "
-                "train_backend='torch' to opt into the composite PyTorch training path.")
+                "this model was built with train_backend='none': call model.eval(), or construct it with "
+                "train_backend='native' (default; sm_100a kernels) or 'torch' (composite PyTorch path).")
         # eval mode: like enhancement.py:66 (`model(chunk).detach().cpu()`, no torch.no_grad()) the result is
         # returned detached — the native path records no autograd graph.
         return self._forward_native(input)
+
+    @property
+    def reduces_gradients(self) -> bool:
+        """True when ``loss.backward()`` through this model already averages the gradients over the data-parallel ranks."""
+        from .train_step import data_parallel_world
+        return (self.training and self.train_backend == "native" and self.data_parallel != "off"
+                and data_parallel_world() > 1)
 
     def _forward_train_native(self, x: torch.Tensor) -> torch.Tensor:
         """Training-mode forward through libwunet_b200 (wunet_train_forward / wunet_train_backward behind a
