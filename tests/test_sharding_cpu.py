@@ -25,6 +25,25 @@ t = torch.tensor([float(10 + rank)])                        # per-rank "elapsed 
 dist.all_reduce(t, op=dist.ReduceOp.MAX)
 gathered = [torch.zeros_like(torch.from_numpy(y_local)) for _ in range(world)]
 dist.all_gather(gathered, torch.from_numpy(y_local))        # test-only gather to compare with the unsharded result
+# config 4 (enhancement.py:49-74 over several GPUs): clips dealt to the ranks by frame count, results gathered on rank 0
+from wave_u_net_for_speech_enhancement_b200 import enhance
+rng = np.random.default_rng(5)
+lengths = [130, 64, 1, 700, 65, 333, 64, 250, 90]
+clips = [rng.standard_normal(k).astype(np.float32) for k in lengths]
+def fake_stream(batches, outs):
+    for b_, o_ in zip(batches, outs):
+        o_.copy_(b_ * 2.0 + torch.arange(b_.shape[-1], dtype=torch.float32) / b_.shape[-1])
+        yield o_
+shards = enhance.shard_clips(lengths, world, sample_length=64)
+assert sorted(i for s_ in shards for i in s_) == list(range(len(lengths)))
+fr = [sum(max(1, -(-lengths[i] // 64)) for i in s_) for s_ in shards]
+assert max(fr) - min(fr) <= max(max(1, -(-k // 64)) for k in lengths), fr          # balanced to within one clip
+res = enhance.enhance_waveforms_sharded(None, clips, rank, world, sample_length=64, batch_frames=4, stream_fn=fake_stream, gather=True)
+if rank == 0:
+    single = enhance.enhance_waveforms(None, clips, sample_length=64, batch_frames=4, stream_fn=fake_stream)
+    assert len(res) == len(single) and all(np.array_equal(a, b_) for a, b_ in zip(res, single))
+else:
+    assert res is None
 if rank == 0:
     y_full = wo.COracle(n, ci).forward(st, x)
     y_cat = torch.cat(gathered, 0).numpy()

@@ -26,13 +26,23 @@ def is_stale() -> bool:
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 
+def source_hash() -> str:
+    """sha1 over the CUDA sources and headers (12 hex digits): compiled into wunet_version() so that profiles/ captures can be
+    matched to the binary they were taken from (bench.py only quotes ncu traffic from a capture of the running build)."""
+    import hashlib
+    h = hashlib.sha1()
+    for s in SOURCES + HEADERS:
+        with open(os.path.join(CSRC, s), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:12]
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return SO
     objs = []
     common = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "--use_fast_math=false" if False else "-DWUNET_BUILD"]
-    common = [c for c in common if c]
+              "-Xcompiler", "-fPIC", "-DWUNET_BUILD", f'-DWUNET_SRC_HASH="{source_hash()}"']
     if verbose:
         common += ["-Xptxas", "-v"]
     if os.environ.get("WUNET_TC_TRACE"):

@@ -172,7 +172,10 @@ int forward_fp32(wunet_ctx *c, const float *x, float *y, int B, int T, void *ws,
 
 extern "C" {
 
-const char *wunet_version(void) { return "wunet_b200 0.1 (sm_100a; fp32 FFMA + bf16 tcgen05 paths)"; }
+#ifndef WUNET_SRC_HASH
+#define WUNET_SRC_HASH "unknown"
+#endif
+const char *wunet_version(void) { return "wunet_b200 0.2 (sm_100a; fp32 FFMA + bf16 tcgen05 paths; src " WUNET_SRC_HASH ")"; }
 
 const char *wunet_last_error(void) { return g_err; }
 

@@ -75,3 +75,44 @@ def enhance_waveforms(model, waveforms: Sequence[np.ndarray], sample_length: int
     if rem:
         out[nfull * B:] = tail_out[:rem]
     return unframe_clips(out, index)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# several GPUs (BASELINE.json configs[3]: batch 1024 sharded over 8 GPUs): one process per GPU, clips dealt to the ranks,
+# no collective on the data path (frames are independent in eval mode)
+# ---------------------------------------------------------------------------------------------------------------------------
+def shard_clips(lengths: Sequence[int], world: int, sample_length: int = 16384) -> List[List[int]]:
+    """Deal clips to ``world`` ranks so that every rank gets about the same number of 16384-sample frames: longest clip
+    first onto the least loaded rank (ties: lowest rank); every rank's list is returned in ascending clip order.
+    Deterministic, so every rank computes the same assignment without communicating."""
+    frames = [max(1, -(-int(n) // sample_length)) for n in lengths]
+    load = [0] * world
+    out: List[List[int]] = [[] for _ in range(world)]
+    for i in sorted(range(len(frames)), key=lambda i: (-frames[i], i)):
+        r = min(range(world), key=lambda r: (load[r], r))
+        out[r].append(i)
+        load[r] += frames[i]
+    return [sorted(ix) for ix in out]
+
+
+def enhance_waveforms_sharded(model, waveforms: Sequence[np.ndarray], rank: int, world: int, sample_length: int = 16384,
+                              batch_frames: int = 256, stream_fn=None, gather: bool = False):
+    """This rank's share of :func:`enhance_waveforms` over ``world`` ranks (``enhancement.py:49-74`` sharded by clip).
+
+    Returns ``{clip index: enhanced waveform}`` for the clips of this rank; with ``gather=True`` (needs an initialised
+    ``torch.distributed`` group) rank 0 gets the full list in clip order — the only communication, and only of results
+    (what a single writer of the output directory, ``enhancement.py:73-74``, needs) — and the other ranks get None."""
+    mine = shard_clips([int(np.asarray(w).shape[-1]) for w in waveforms], world, sample_length)[rank]
+    local = enhance_waveforms(model, [waveforms[i] for i in mine], sample_length, batch_frames, stream_fn) if mine else []
+    result = dict(zip(mine, local))
+    if not gather:
+        return result
+    import torch.distributed as dist
+    parts = [None] * world if rank == 0 else None
+    dist.gather_object(result, parts, dst=0)
+    if rank != 0:
+        return None
+    merged = {}
+    for p in parts:
+        merged.update(p)
+    return [merged[i] for i in range(len(waveforms))]
