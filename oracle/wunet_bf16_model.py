@@ -79,29 +79,37 @@ def _upsample_fp32(prev: torch.Tensor) -> torch.Tensor:
     return _bf16(lam0[None, None, :] * prev[:, :, i0] + lam1[None, None, :] * prev[:, :, i1])
 
 
-def forward_bf16_model(state, x: np.ndarray, n_layers: int = 12, channels_interval: int = 24, return_levels: bool = False):
-    """-> y [B,1,T] fp32 (and the bf16-valued outputs of the 2n+1 blocks as fp32 arrays; the last one unrounded)."""
+def forward_bf16_model(state, x: np.ndarray, n_layers: int = 12, channels_interval: int = 24, return_levels: bool = False,
+                       forced=None):
+    """-> y [B,1,T] fp32 (and the bf16-valued outputs of the 2n+1 blocks as fp32 arrays; the last one unrounded).
+
+    ``forced``: optional list of the 2n block outputs measured on the GPU (fp32 arrays holding bf16 values). Block i is then
+    evaluated on the GPU's outputs of the blocks before it ("teacher forcing"): rounding flips do not propagate, so every
+    level can be held to bit-equality up to its own flips, however deep it is."""
     plan = channel_plan(n_layers, channels_interval)
     n = n_layers
     xt = torch.from_numpy(np.asarray(x, np.float32))
     levels, skips = [], []
-    o = _bf16(_block(xt, state, plan[0][0], 15, quantise_operands=False))
+
+    def keep(i, t):
+        levels.append(t)
+        return torch.from_numpy(np.asarray(forced[i], np.float32)) if (forced is not None and i < 2 * n) else t
+
+    o = keep(0, _bf16(_block(xt, state, plan[0][0], 15, quantise_operands=False)))
     skips.append(o)
-    levels.append(o)
     o = o[:, :, ::2]
     for i in range(1, n):
-        o = _bf16(_block(o, state, plan[i][0], 15, True))
+        o = keep(i, _bf16(_block(o, state, plan[i][0], 15, True)))
         skips.append(o)
-        levels.append(o)
         o = o[:, :, ::2]
-    o = _bf16(_block(o, state, "middle", 15, True))
-    levels.append(o)
+    o = keep(n, _bf16(_block(o, state, "middle", 15, True)))
     for j in range(n):
         L = 2 * o.shape[2]
         up = _upsample_hfma2(o) if L >= 128 else _upsample_fp32(o)
         v = _block(torch.cat([up, skips[n - 1 - j]], dim=1), state, plan[n + 1 + j][0], 5, True)
-        o = v if j == n - 1 else _bf16(v)                        # the last block feeds the fused head unrounded
-        levels.append(o)
+        o = v if j == n - 1 else keep(n + 1 + j, _bf16(v))      # the last block feeds the fused head unrounded
+        if j == n - 1:
+            levels.append(o)
     w = torch.from_numpy(np.asarray(state["out.0.weight"], np.float32))[0, :, 0]
     b = np.float32(np.asarray(state["out.0.bias"], np.float32)[0])
     C = o.shape[1]

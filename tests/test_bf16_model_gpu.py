@@ -30,28 +30,29 @@ def test_levels_match_the_arithmetic_model(n, ci, B, T, seed, monkeypatch):
     monkeypatch.setenv("WUNET_TC_STORE_LAST", "1")               # materialise the last decoder block too
     st = wo.make_state(n, ci, seed=seed)
     x = wo.make_input(B, T, seed=seed + 100)
-    want_y, want = wb.forward_bf16_model(st, x, n, ci, return_levels=True)
     m = Model(n, ci, precision="bf16")
     m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in st.items()})
     m = m.to("cuda:0").eval()
     with torch.no_grad():
         y = m(torch.from_numpy(x).cuda()).cpu().numpy()
+    got_levels = [m.read_level(i, B, T).cpu().numpy() for i in range(2 * n + 1)]
+    # every block of the model is evaluated on the GPU's own outputs of the blocks before it: a rounding flip stays local
+    want_y, want = wb.forward_bf16_model(st, x, n, ci, return_levels=True, forced=got_levels[:2 * n])
     report = []
     for i in range(2 * n + 1):
-        got = m.read_level(i, B, T).cpu().numpy()
+        got = got_levels[i]
         ref = want[i] if i < 2 * n else want[i].astype(np.float32)
         if i == 2 * n:                                           # the stored copy of the last block is rounded to bf16
             ref = torch.from_numpy(ref).to(torch.bfloat16).float().numpy()
         diff = np.abs(got - ref)
         frac_equal = float((diff == 0).mean())
-        worst_ulps = float((diff / ulp_bf16(ref)).max())
         excess = float((diff - np.maximum(2.0 * ulp_bf16(ref), ABS_FLOOR * np.abs(ref).max())).max())
-        report.append((i, round(frac_equal, 5), worst_ulps, float(diff.max()), excess))
+        report.append((i, round(frac_equal, 5), float(diff.max()), excess))
     yerr = float(np.abs(y - want_y).max())
-    print("bf16 model vs kernels (block, fraction bit-equal, worst ulps, max abs diff, excess over bound):")
+    print("bf16 model (teacher-forced) vs kernels: (block, fraction bit-equal, max abs diff, excess over bound)")
     for r in report:
         print("   ", r)
     print("    output max-abs diff", yerr)
-    assert all(r[1] >= 0.97 for r in report), report
-    assert all(r[4] <= 0.0 for r in report), report
-    assert yerr <= 2e-3, (yerr, report)
+    assert all(r[1] >= 0.995 for r in report), report
+    assert all(r[3] <= 0.0 for r in report), report
+    assert yerr <= 2e-5, (yerr, report)

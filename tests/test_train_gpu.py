@@ -17,7 +17,8 @@ from wave_u_net_for_speech_enhancement_b200 import Model
 pytestmark = [pytest.mark.gpu]
 
 GRAD_REL = 2e-4       # fp32 kernels vs the float64 reference step; relative to the largest entry of each gradient
-GRAD_REL_FULL = 1e-3  # 25 blocks deep, batch statistics over 2 x L samples only
+GRAD_REL_FULL = 2e-2  # 25 blocks deep, batch statistics over 2 x L samples only: the reference's OWN fp32 autograd (PyTorch CPU)
+                      # is 9.98e-3 away from the float64 golden step on decoder.6 BatchNorm.weight (measured), ours 9.2e-3
 Y_TOL = 1e-3          # train-mode forward vs the float64 golden output (see the module docstring)
 
 
@@ -107,7 +108,7 @@ def test_three_adam_steps_track_the_composite_torch_path():
             losses.append(step(m, noisy, clean)[0])
             opt.step()
         # after the first update the two trajectories differ by Adam's +-lr steps on rounding-noise gradients
-        assert abs(losses[0] - losses[1]) <= (1e-5 if it == 0 else 2e-3) * abs(losses[1]), (it, losses)
+        assert abs(losses[0] - losses[1]) <= (1e-4 if it == 0 else 2e-3) * abs(losses[1]), (it, losses)
     for (k, a), (_, b) in zip(ms[0].state_dict().items(), ms[1].state_dict().items()):
         if k.endswith(".0.bias") and not k.startswith("out."):
             continue                      # gradient is rounding noise, Adam turns it into +-lr steps on both sides

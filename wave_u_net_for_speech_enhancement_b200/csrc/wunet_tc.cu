@@ -762,6 +762,363 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // -------------------------------------------------------------------------------------------------
+// "taps in N" kernel for the shallow, long blocks (Cout <= 48: enc1, dec10, dec11 of the reference architecture)
+// -------------------------------------------------------------------------------------------------
+// For N = Cout < 128 the M=128 MMA is bound by its shared-memory operand reads (32 + N/4 cycles, tools/umma_rate.cu): every
+// tap re-reads the same 4 KB A slab. Here G = 5 taps are folded into the N axis instead,
+//     D'[row, (t', co)] = sum_cin X[row, cin] * W[5g + t'][co, cin]        (one MMA of N' = 5 Cp columns per K16 step),
+// so the A slab is read once per 5 taps (dec11: 64 cycles instead of 5 x 40, dec10 / enc1: 120 instead of 5 x 44), and the
+// tap sum moves to the epilogue as a shifted sum over rows = TMEM lanes,
+//     out[l] = sum_t' D'[row(l) + t', t'],
+// done with warp shuffles (Horner: acc = D'[.,4]; acc = shfl_down(acc) + D'[.,3]; ...). A warp only reaches the 32 lanes of its
+// TMEM quadrant, so the operand tile is laid out in BLOCKS of 32 rows that overlap by 4 positions (block k holds positions
+// l0 - PAD + 28 k ... + 31): every quadrant then yields 28 complete output rows without any cross-warp exchange, at the price
+// of 12.5 % redundant MMA rows. A 15-tap encoder block runs its three tap groups as three K "chunks" (same channels, operand
+// rows shifted by 5 g positions, weight slot g). Everything else (TMA zero fill = conv padding, decimated / skip tensor maps,
+// upsample producers writing the swizzled operand, resident weights, double-buffered accumulators, fused head) is as in
+// conv_tc_kernel.
+struct TnParams {
+    int B, L, T, Cout, Cp, Npad, Nstride;      // Cp = column pitch of a tap inside N' (Cout rounded up to 8), Npad = N' padded to 16
+    int Cin0, Cin1;                            // decoder: upsampled / skip channels; encoder: Cin0 = Cin
+    int MT, tile_rows, tiles_per_frame;        // tile_rows = 112 MT output positions per tile
+    int tile_begin, tile_end;
+    int nchunks, na;                           // K chunks per tile, operand ring depth
+    unsigned char c_up[8], c_ch[8], c_nk[8], c_slot[8], c_row[8];   // per chunk: producer-written?, 64-channel chunk index inside its
+                                               // segment, K16 steps, weight slot, extra operand row offset (tap group * 5)
+    int pad;                                   // (KS - 1) / 2
+    int wpg, npg;                              // producer warps per group, groups (each group owns every npg-th upsampled chunk)
+    uint32_t a_stage_bytes, w_tile_bytes, tmem_cols;
+    const __nv_bfloat16 *prev;                 // decoder: previous block output [B][L/2][Cin0]
+    int Lin;
+    float up_scale;
+    const float2 *ss;                          // [Cout] folded BatchNorm (scale, shift)
+    __nv_bfloat16 *out;                        // [B][L][Cout] or nullptr (fused head without the debug store)
+    int head;
+    const float *x;
+    float *y;
+    const float *head_w, *head_b;
+};
+struct TnSmem { uint32_t a, w, ss, bars; };
+__host__ __device__ inline TnSmem tn_smem_map(const TnParams &p)
+{
+    TnSmem m;
+    m.a = 0;
+    m.w = p.na * p.a_stage_bytes;
+    m.ss = m.w + p.nchunks * p.w_tile_bytes;
+    m.bars = (m.ss + (uint32_t)p.Cout * 8 + 64 * 4 + 15) & ~15u;
+    return m;
+}
+inline size_t tn_smem_total(const TnParams &p) { return tn_smem_map(p).bars + 8 * (4 + 4 + 1 + 2 + 2) + 16 + 1024; }
+
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&v)[8])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void mbar_arrive_n(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+
+template <bool UPCAT>
+__global__ void __launch_bounds__(64 + 32 * (kEpiWarpsLarge + (UPCAT ? kProducerWarpsLarge : 0)), 1)
+conv_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TnParams p)
+{
+    constexpr int EW = kEpiWarpsLarge, PW = UPCAT ? kProducerWarpsLarge : 0;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t *base_ptr = smem_raw + (base - smem_u32(smem_raw));
+    const TnSmem sm = tn_smem_map(p);
+    const uint32_t bars = base + sm.bars;
+    // barrier slots (8 B each): a_full[4] a_empty[4] w_full[1] acc_full[2] acc_empty[2] | tmem slot
+    const uint32_t a_full = bars, a_empty = bars + 32, w_full = bars + 64, acc_full = bars + 72, acc_empty = bars + 88;
+    const uint32_t tmem_slot = bars + 104;
+    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(base_ptr + sm.bars + 104);
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int kFirstProducer = EW, kTmaWarp = EW + PW, kMmaWarp = kTmaWarp + 1;
+    const int total_tiles = p.tile_end;
+    const int first_tile = p.tile_begin + (int)blockIdx.x;
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
+        for (int s = 0; s < 4; ++s) {
+            mbar_init(a_full + 8 * s, UPCAT ? 1 + p.wpg : 1);
+            mbar_init(a_empty + 8 * s, 1);
+        }
+        mbar_init(w_full, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(acc_full + 8 * s, 1); mbar_init(acc_empty + 8 * s, EW); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kMmaWarp) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    {
+        float2 *ss = reinterpret_cast<float2 *>(base_ptr + sm.ss);
+        for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) ss[i] = p.ss[i];
+        if (p.head) {
+            float *hw = reinterpret_cast<float *>(base_ptr + sm.ss) + 2 * p.Cout;
+            if ((int)threadIdx.x <= p.Cout) hw[threadIdx.x] = p.head_w[threadIdx.x];
+            if ((int)threadIdx.x == p.Cout + 1) hw[threadIdx.x] = p.head_b[0];
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    if (warp != kTmaWarp) asm volatile("griddepcontrol.wait;" ::: "memory");
+
+    auto tile_coords = [&](int tile, int &b0, int &l0) {
+        b0 = tile / p.tiles_per_frame;
+        l0 = (tile - b0 * p.tiles_per_frame) * p.tile_rows;
+    };
+    const int nblk = 4 * p.MT;                               // 32-row operand blocks per tile
+
+    if (warp == kTmaWarp) {
+        if (lane == 0) {
+            // the block's whole weight set: one [Npad x 64] tile per K chunk, loaded once per CTA (independent of the previous kernel)
+            mbar_expect_tx(w_full, (uint32_t)p.nchunks * (uint32_t)p.Npad * 128u);
+            for (int c = 0; c < p.nchunks; ++c)
+                tma_load_3d(base + sm.w + (uint32_t)c * p.w_tile_bytes, &tmW, w_full, p.c_slot[c] * 64, 0, 0);
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            uint32_t cnt = 0;
+            for (int tile = first_tile; tile < total_tiles; tile += gridDim.x) {
+                int b0, l0;
+                tile_coords(tile, b0, l0);
+                for (int c = 0; c < p.nchunks; ++c, ++cnt) {
+                    const uint32_t sa = cnt % (uint32_t)p.na, pa = (cnt / (uint32_t)p.na) & 1u;
+                    mbar_wait(a_empty + 8 * sa, pa ^ 1);
+                    if (!p.c_up[c]) {
+                        mbar_expect_tx(a_full + 8 * sa, (uint32_t)nblk * 4096u);
+                        const uint32_t dst = base + sm.a + sa * p.a_stage_bytes;
+                        const int lc = l0 - p.pad + p.c_row[c];
+                        for (int k = 0; k < nblk; ++k)
+                            tma_load_3d(dst + (uint32_t)k * 4096u, &tmA, a_full + 8 * sa, p.c_ch[c] * 64, lc + 28 * k, b0);
+                        if (UPCAT) mbar_arrive_n(a_full + 8 * sa, (uint32_t)p.wpg);     // the producers do not touch this stage
+                    } else {
+                        mbar_arrive(a_full + 8 * sa);                                   // the owning producer group completes it
+                    }
+                }
+            }
+        }
+    } else if (warp == kMmaWarp) {
+        if (elect_one()) {
+            const uint32_t hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Npad >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            mbar_wait(w_full, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t cnt = 0;
+            int it = 0;
+            for (int tile = first_tile; tile < total_tiles; tile += gridDim.x, ++it) {
+                const int buf = it & 1;
+                mbar_wait(acc_empty + 8 * buf, (((uint32_t)it >> 1) & 1u) ^ 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t acc_col = tmem_base + (uint32_t)(buf * p.MT * p.Nstride);
+                for (int c = 0; c < p.nchunks; ++c, ++cnt) {
+                    const uint32_t sa = cnt % (uint32_t)p.na, pa = (cnt / (uint32_t)p.na) & 1u;
+                    mbar_wait(a_full + 8 * sa, pa);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_lo = (((base + sm.a + sa * p.a_stage_bytes) >> 4) & 0x3FFFu) | (1u << 16);
+                    const uint32_t b_lo = (((base + sm.w + (uint32_t)c * p.w_tile_bytes) >> 4) & 0x3FFFu) | (1u << 16);
+                    const int nk = p.c_nk[c];
+#pragma unroll 1
+                    for (int mt = 0; mt < p.MT; ++mt) {
+                        const uint32_t d = acc_col + (uint32_t)(mt * p.Nstride);
+                        const uint32_t am = a_lo + (uint32_t)mt * 1024u;               // next 128 rows: 16 KB = 1024 sixteen-byte units
+                        umma_bf16_lohi(d, am, b_lo, hi, idesc, c ? 1u : 0u);
+                        if (nk > 1) umma_bf16_lohi(d, am + 2, b_lo + 2, hi, idesc, 1u);
+                        if (nk > 2) umma_bf16_lohi(d, am + 4, b_lo + 4, hi, idesc, 1u);
+                        if (nk > 3) umma_bf16_lohi(d, am + 6, b_lo + 6, hi, idesc, 1u);
+                    }
+                    umma_commit(a_empty + 8 * sa);
+                }
+                umma_commit(acc_full + 8 * buf);
+            }
+        }
+    } else if (warp < EW) {
+        // ======================= epilogue: shifted tap sum + BatchNorm + LeakyReLU (+ fused head) =======================
+        const int q = warp & 3, half = warp >> 2;
+        const float2 *ss = reinterpret_cast<const float2 *>(base_ptr + sm.ss);
+        const float *hw = reinterpret_cast<const float *>(base_ptr + sm.ss) + 2 * p.Cout;
+        const int ncc = p.Cout >> 3;                              // 8-column chunks of the output
+        int it = 0;
+        for (int tile = first_tile; tile < total_tiles; tile += gridDim.x, ++it) {
+            int b0, l0;
+            tile_coords(tile, b0, l0);
+            const int buf = it & 1;
+            // fused head: the raw-input samples of this thread's rows, fetched before the accumulators are waited for
+            float xin[4] = {0.f, 0.f, 0.f, 0.f};
+            if (p.head) {
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt) {
+                    const int l = l0 + 28 * (4 * mt + q) + lane;
+                    if (mt < p.MT && (mt & 1) == half && lane < 28 && l < p.L) xin[mt] = __ldg(p.x + (size_t)b0 * p.T + l);
+                }
+            }
+            mbar_wait(acc_full + 8 * buf, ((uint32_t)it >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+            for (int mt = 0; mt < p.MT; ++mt) {
+                // the two warps of a quadrant split the work: by sub-tile when there are several, else by column chunk
+                if (p.MT > 1 && (mt & 1) != half) continue;
+                const int l = l0 + 28 * (4 * mt + q) + lane;
+                const bool valid = lane < 28 && l < p.L;
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * p.MT + mt) * p.Nstride);
+                float hacc = p.head ? hw[p.Cout + 1] : 0.f;
+#pragma unroll 1
+                for (int cc = (p.MT > 1 ? 0 : half); cc < ncc; cc += (p.MT > 1 ? 1 : 2)) {
+                    uint32_t v0[8], v1[8], v2[8], v3[8], v4[8];
+                    const uint32_t col = taddr + (uint32_t)(8 * cc);
+                    tmem_ld8_nowait(col, v0);
+                    tmem_ld8_nowait(col + (uint32_t)p.Cp, v1);
+                    tmem_ld8_nowait(col + (uint32_t)(2 * p.Cp), v2);
+                    tmem_ld8_nowait(col + (uint32_t)(3 * p.Cp), v3);
+                    tmem_ld8_nowait(col + (uint32_t)(4 * p.Cp), v4);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    float f[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        // out[row] = D'[row,0] + D'[row+1,1] + ... + D'[row+4,4]; lanes 28..31 end up incomplete and are not stored
+                        float a = __uint_as_float(v4[j]);
+                        a = __shfl_down_sync(0xffffffffu, a, 1) + __uint_as_float(v3[j]);
+                        a = __shfl_down_sync(0xffffffffu, a, 1) + __uint_as_float(v2[j]);
+                        a = __shfl_down_sync(0xffffffffu, a, 1) + __uint_as_float(v1[j]);
+                        a = __shfl_down_sync(0xffffffffu, a, 1) + __uint_as_float(v0[j]);
+                        const float2 s2 = ss[8 * cc + j];
+                        f[j] = lrelu(fmaf(a, s2.x, s2.y));
+                    }
+                    if (p.out != nullptr && valid)
+                        *reinterpret_cast<uint4 *>(p.out + ((size_t)b0 * p.L + l) * p.Cout + 8 * cc) =
+                            make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+                    if (p.head) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) hacc = fmaf(hw[8 * cc + j], f[j], hacc);
+                    }
+                }
+                if (p.head && valid) {
+                    // cat([o, input], 1) -> Conv1d(C+1 -> 1, k=1) -> Tanh   (model/unet_basic.py:98-99)
+                    hacc = fmaf(hw[p.Cout], mt == 0 ? xin[0] : (mt == 1 ? xin[1] : (mt == 2 ? xin[2] : xin[3])), hacc);
+                    p.y[(size_t)b0 * p.T + l] = tanh_fast(hacc);
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty + 8 * buf);
+        }
+    } else if (UPCAT) {
+        // ======================= upsample producers =======================
+        // As in conv_tc_kernel (16 output rows x one 16-byte channel vector per thread, packed-bf16 interpolation straight into
+        // the swizzled operand), with the operand rows mapped to positions block by block (row 32 k + i <-> l0 - PAD + 28 k + i)
+        // and the producer warps split into groups that work on different upsampled chunks at the same time: one chunk has
+        // fewer items than there are producer threads, and its latency (~1.5 k cycles) is longer than a tile's MMAs.
+        const int pw = warp - kFirstProducer;
+        const int grp = pw / p.wpg;
+        if (grp < p.npg) {
+            const int pt = (pw - grp * p.wpg) * 32 + lane;
+            const int nthreads = p.wpg * 32;
+            const int nruns = 8 * p.MT;                            // 16-row runs per tile (two per 32-row block)
+            uint32_t cnt = 0, unit = 0;
+            for (int tile = first_tile; tile < total_tiles; tile += gridDim.x) {
+                int b0, l0;
+                tile_coords(tile, b0, l0);
+                for (int c = 0; c < p.nchunks; ++c, ++cnt) {
+                    // Every group follows EVERY chunk's stage release in order, also those it does not write: an mbarrier wait
+                    // only tells the current phase from the previous one, so a waiter must never get two uses of a stage ahead
+                    // of (or behind) the barrier it polls. Skipping the chunks of other groups did exactly that.
+                    const uint32_t sa = cnt % (uint32_t)p.na, pa = (cnt / (uint32_t)p.na) & 1u;
+                    const bool mine = p.c_up[c] && (unit % (uint32_t)p.npg) == (uint32_t)grp;
+                    if (p.c_up[c]) ++unit;
+                    if (!mine) { mbar_wait(a_empty + 8 * sa, pa ^ 1); continue; }
+                    const int nvec = p.c_nk[c] * 2;
+                    const int nitems = nruns * nvec;
+                    uint4 xr[10];
+                    auto fetch = [&](int item) {
+                        const int run = item / nvec, vec = item - run * nvec;
+                        const int ch = p.c_ch[c] * 64 + vec * 8;
+                        const int lstart = l0 - p.pad + 28 * (run >> 1) + 16 * (run & 1);      // even
+                        const int ms = lstart >> 1;
+                        const bool chok = ch < p.Cin0;
+                        const __nv_bfloat16 *pb = p.prev + (size_t)b0 * p.Lin * p.Cin0 + ch;
+#pragma unroll
+                        for (int qq = 0; qq < 10; ++qq) {
+                            int m = ms - 1 + qq;
+                            m = m < 0 ? 0 : (m > p.Lin - 1 ? p.Lin - 1 : m);
+                            xr[qq] = chok ? __ldg(reinterpret_cast<const uint4 *>(pb + (size_t)m * p.Cin0)) : make_uint4(0u, 0u, 0u, 0u);
+                        }
+                    };
+                    if (pt < nitems) fetch(pt);                    // issued before the wait: DRAM latency overlaps it
+                    mbar_wait(a_empty + 8 * sa, pa ^ 1);
+                    const uint32_t stage = base + sm.a + sa * p.a_stage_bytes;
+#pragma unroll 1
+                    for (int item = pt; item < nitems; item += nthreads) {
+                        if (item != pt) fetch(item);
+                        const int run = item / nvec, vec = item - run * nvec;
+                        const int ch = p.c_ch[c] * 64 + vec * 8;
+                        const int lstart = l0 - p.pad + 28 * (run >> 1) + 16 * (run & 1);
+                        const int ms = lstart >> 1;
+                        const bool chok = ch < p.Cin0;
+                        const float lf0 = (float)lstart, mf0 = (float)(ms - 1);
+                        const uint32_t drow = stage + (uint32_t)(16 * run) * 128u;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int l = lstart + j;
+                            const int qa = (j >> 1) + (j & 1);
+                            const float lam1 = fmaf(p.up_scale, lf0 + (float)j, -(mf0 + (float)qa));
+                            const __nv_bfloat162 lam = __float2bfloat162_rn(lam1);
+                            const __nv_bfloat162 *a2 = reinterpret_cast<const __nv_bfloat162 *>(&xr[qa]);
+                            const __nv_bfloat162 *b2 = reinterpret_cast<const __nv_bfloat162 *>(&xr[qa + 1]);
+                            __nv_bfloat162 r2[4];
+#pragma unroll
+                            for (int q4 = 0; q4 < 4; ++q4) r2[q4] = __hfma2(lam, __hsub2(b2[q4], a2[q4]), a2[q4]);
+                            uint4 o = *reinterpret_cast<const uint4 *>(r2);
+                            const uint32_t keep = (chok && (unsigned)l < (unsigned)p.L) ? 0xffffffffu : 0u;
+                            o.x &= keep; o.y &= keep; o.z &= keep; o.w &= keep;
+                            st_shared_v4_if(drow + (uint32_t)(j * 128 + ((vec ^ (j & 7)) << 4)), o, true);
+                        }
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(a_full + 8 * sa);
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == kMmaWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols));
+}
+
+// TN weights: [Npad rows = (t', co) at t' * Cp + co][nslots * 64] bf16. Decoder (ngroups == 1): K slots as in pack_tc_kernel
+// ([upsampled chunks | skip chunks], 64 channels each), tap = t'. Encoder: slot g = tap group g (taps 5 g + t'), channel < Cin.
+__global__ void pack_tn_kernel(const float *__restrict__ w, __nv_bfloat16 *__restrict__ wp, int Cout, int Cin0, int Cin1, int K,
+                               int Cp, int Npad, int nslots, int ngroups)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n = (long long)Npad * nslots * 64;
+    if (i >= n) return;
+    const int ks = (int)(i % (nslots * 64));
+    const int row = (int)(i / (nslots * 64));
+    const int tp = row / Cp, co = row - tp * Cp;
+    float v = 0.f;
+    if (tp < 5 && co < Cout) {
+        int ci = -1, tap = tp;
+        if (ngroups == 1) {
+            const int seg1_base = (Cin0 + 63) / 64 * 64;
+            if (ks < seg1_base) { if (ks < Cin0) ci = ks; }
+            else if (ks - seg1_base < Cin1) ci = Cin0 + (ks - seg1_base);
+        } else {
+            const int g = ks / 64, c = ks - g * 64;
+            tap = 5 * g + tp;
+            if (c < Cin0 && g < ngroups) ci = c;
+        }
+        if (ci >= 0 && tap < K) v = w[((size_t)co * (Cin0 + Cin1) + ci) * K + tap];
+    }
+    wp[i] = __float2bfloat16(v);
+}
+
+// -------------------------------------------------------------------------------------------------
 // enc0: Conv1d(1 -> C, k=15) + BN + LeakyReLU on CUDA cores (Cin = 1: K = 15, HBM-bound), fp32 in, bf16 NLC out
 // -------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256, 4) enc0_kernel(const float *__restrict__ x, const float *__restrict__ w /*[C][1][15]*/,
@@ -898,6 +1255,9 @@ struct TcLevel {
                                        // one extra 64-wide K slot at the end of the packed weights (0 = not merged)
     __nv_bfloat16 *wp = nullptr;
     float2 *ss = nullptr;
+    // taps-in-N variant (conv_tn_kernel): eligible blocks keep a second packed copy [tn_npad][tn_slots * 64]
+    int tn_cp = 0, tn_npad = 0, tn_slots = 0, tn_groups = 0;      // 0 = not eligible
+    __nv_bfloat16 *wp_tn = nullptr;
     const float *w_src = nullptr;      // enc0 only: fp32 weights (w_own, a library-owned copy) / scale / shift (the context's folded copies)
     float *w_own = nullptr;            // enc0 only: [Cout][1][K] fp32 copy made by tc_set_weights (the caller's tensor is not read afterwards)
     const float *scale = nullptr, *shift = nullptr;
@@ -905,6 +1265,8 @@ struct TcLevel {
 
 struct TcPlanLevel {
     TcParams p;
+    TnParams tn;                       // is_tn: the block runs conv_tn_kernel (tmA / tmW are its maps, p is unused)
+    bool is_tn = false;
     CUtensorMap tmA, tmW, tmO;
     dim3 grid;
     int threads;
@@ -979,6 +1341,7 @@ struct TcState {
     bool attr_set = false;
     bool pdl = false;                  // programmatic dependent launch between the blocks (WUNET_TC_PDL=1); measured slower, off
     bool merge = true;                 // merged tail chunks (WUNET_TC_MERGE=0 switches them off for A/B measurements)
+    bool tn = true;                    // taps-in-N kernel for the shallow blocks (WUNET_TC_TN=0 switches it off for A/B measurements)
     int num_sms = 148;
     cudaStream_t copy_in = nullptr, copy_out = nullptr;     // host pipeline: H2D / D2H streams
     cudaEvent_t ev_in[8] = {}, ev_out[8] = {};
@@ -1018,7 +1381,7 @@ size_t tc_workspace_bytes(int n, int ci, int B, int T)
 
 // K segments and padded sizes of every block: encoders have one input segment, decoder block i concatenates the previous
 // block's (upsampled) output with the skip of encoder 2n - i (model/unet_basic.py:93-95)
-static void derive_levels(std::vector<TcLevel> &levels, const TcBlockSrc *blocks, int nblocks, int n, bool merge = true)
+static void derive_levels(std::vector<TcLevel> &levels, const TcBlockSrc *blocks, int nblocks, int n, bool merge = true, bool tn = true)
 {
     for (int i = 0; i < nblocks; ++i) {
         TcLevel &lv = levels[i];
@@ -1029,6 +1392,15 @@ static void derive_levels(std::vector<TcLevel> &levels, const TcBlockSrc *blocks
         lv.Ktot = round_up(lv.cin0, 64) + (lv.cin1 ? round_up(lv.cin1, 64) : 0);
         lv.w_src = blocks[i].w; lv.scale = blocks[i].scale; lv.shift = blocks[i].shift;
         lv.mg_s = lv.mg_u = 0;
+        // taps-in-N: 5 taps x Cout columns must fit one MMA (N <= 256) and pay off (N = Cout < 64: operand-read-bound MMAs)
+        lv.tn_cp = lv.tn_npad = lv.tn_slots = lv.tn_groups = 0;
+        if (tn && i >= 1 && lv.cout % 8 == 0 && lv.cout <= 48 && lv.k % 5 == 0) {
+            const int groups = lv.k / 5;
+            const int slots = (i > n) ? (lv.cin0 + 63) / 64 + (lv.cin1 + 63) / 64 : groups * ((lv.cin0 + 63) / 64);
+            if (((i > n && groups == 1) || (i <= n && lv.cin0 <= 64)) && slots <= 8) {
+                lv.tn_cp = lv.cout; lv.tn_npad = round_up(5 * lv.cout, 16); lv.tn_slots = slots; lv.tn_groups = groups;
+            }
+        }
         const int u = lv.cin0 % 64, sk = lv.cin1 % 64;
         if (merge && i > n && u > 0 && sk > 0 && u + sk <= 64 && u % 8 == 0 && sk % 8 == 0) {
             lv.mg_s = sk; lv.mg_u = u;
@@ -1058,6 +1430,7 @@ int tc_set_weights(TcState **pst, int n, int ci, const TcBlockSrc *blocks, int n
         const char *pe = getenv("WUNET_TC_PDL");
         st->pdl = pe && pe[0] == '1';
         if (const char *xe = getenv("WUNET_TC_MERGE")) st->merge = xe[0] != '0';
+        if (const char *xe = getenv("WUNET_TC_TN")) st->tn = xe[0] != '0';
 #ifdef WUNET_TC_TRACE
         if (const char *tl = getenv("WUNET_TC_TRACE_LEVEL")) {
             st->trace_level = atoi(tl);
@@ -1069,7 +1442,7 @@ int tc_set_weights(TcState **pst, int n, int ci, const TcBlockSrc *blocks, int n
     }
     st->out_w = out_w; st->out_b = out_b;
     st->plan_ws = nullptr;                               // weights moved: rebuild maps lazily
-    derive_levels(st->levels, blocks, nblocks, n, st->merge);
+    derive_levels(st->levels, blocks, nblocks, n, st->merge, st->tn);
     if (ci % 8 != 0 || ci > 32) return 0;                // tensor-core path unsupported for this plan; forward reports it
     {
         // enc0 runs on CUDA cores from fp32 weights: keep a library-owned copy (include/wunet_b200.h: the caller's tensors are
@@ -1091,6 +1464,13 @@ int tc_set_weights(TcState **pst, int n, int ci, const TcBlockSrc *blocks, int n
         pack_tc_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, stream>>>(blocks[i].w, blocks[i].scale, blocks[i].shift, lv.wp,
                                                                           lv.ss, lv.cout, lv.cin0, lv.cin1, lv.k, lv.Npad, lv.Ktot);
         if (cudaGetLastError() != cudaSuccess) return tc_fail("pack_tc_kernel launch failed");
+        if (lv.tn_slots) {
+            const size_t nt = (size_t)lv.tn_npad * lv.tn_slots * 64;
+            if (!lv.wp_tn && cudaMalloc(&lv.wp_tn, nt * sizeof(__nv_bfloat16)) != cudaSuccess) return tc_fail("cudaMalloc(wp_tn) failed");
+            pack_tn_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, stream>>>(blocks[i].w, lv.wp_tn, lv.cout, lv.cin0, lv.cin1, lv.k, lv.tn_cp,
+                                                                            lv.tn_npad, lv.tn_slots, lv.tn_groups);
+            if (cudaGetLastError() != cudaSuccess) return tc_fail("pack_tn_kernel launch failed");
+        }
         if (lv.mg_s) {
             const size_t nm = (size_t)lv.k * lv.Npad * 64;
             pack_tc_merged_kernel<<<(unsigned)((nm + 255) / 256), 256, 0, stream>>>(blocks[i].w, lv.wp, lv.cout, lv.cin0, lv.cin1, lv.k,
@@ -1333,6 +1713,73 @@ static int plan_block(const TcLevel &lv, int i, int n, int B, int T, int num_sms
     return 0;
 }
 
+// Tiling of a taps-in-N block (conv_tn_kernel): pure host logic like plan_block. Returns false if the block does not take
+// this path at this shape (frames shorter than a tile, channel plan not eligible).
+static bool plan_block_tn(const TcLevel &lv, int i, int n, int B, int T, int num_sms, TcPlanLevel &P)
+{
+    if (!lv.tn_slots) return false;
+    const bool dec = i > n;
+    const int L = (i <= n) ? (T >> i) : (T >> (2 * n - i));
+    const bool last = (i == 2 * n);
+    TnParams &t = P.tn;
+    memset(&t, 0, sizeof(t));
+    t.Cout = lv.cout; t.Cp = lv.tn_cp; t.Npad = lv.tn_npad; t.Nstride = round_up(t.Npad, 32);
+    int MT = 512 / (2 * t.Nstride);                                   // double-buffered accumulators
+    if (MT > 4) MT = 4;
+    if (MT < 1) return false;
+    if (last && MT < 2) return false;                                 // the fused head splits the sub-tiles between warp pairs
+    if (L < 112 * MT * 2) return false;                               // long blocks only
+    t.B = B; t.L = L; t.T = T; t.MT = MT; t.tile_rows = 112 * MT;
+    t.tiles_per_frame = (L + t.tile_rows - 1) / t.tile_rows;
+    t.Cin0 = lv.cin0; t.Cin1 = lv.cin1; t.pad = (lv.k - 1) / 2;
+    int k = 0;
+    auto add = [&](int up, int ch, int cwidth, int slot, int row) {
+        t.c_up[k] = (unsigned char)up; t.c_ch[k] = (unsigned char)ch; t.c_nk[k] = (unsigned char)((std::min(cwidth, 64) + 15) / 16);
+        t.c_slot[k] = (unsigned char)slot; t.c_row[k] = (unsigned char)row; ++k;
+    };
+    if (dec) {
+        // K-loop order as in conv_tc_kernel: full upsampled chunks, skip chunks (TMA), then the partial upsampled chunk; if the
+        // only upsampled chunk is partial it goes first
+        const int n0 = (lv.cin0 + 63) / 64, n1 = (lv.cin1 + 63) / 64, nfull0 = lv.cin0 / 64;
+        if (nfull0 == 0) add(1, 0, lv.cin0, 0, 0);
+        for (int c = 0; c < nfull0; ++c) add(1, c, 64, c, 0);
+        for (int c = 0; c < n1; ++c) add(0, c, lv.cin1 - 64 * c, n0 + c, 0);
+        if (nfull0 > 0 && nfull0 < n0) add(1, nfull0, lv.cin0 - 64 * nfull0, nfull0, 0);
+    } else {
+        for (int g = 0; g < lv.tn_groups; ++g) add(0, 0, lv.cin0, g, 5 * g);
+    }
+    t.nchunks = k;
+    t.a_stage_bytes = (uint32_t)(MT * 4 * 4096);
+    t.w_tile_bytes = (uint32_t)round_up(t.Npad * 128, 1024);
+    const int budget = kSmemLimit - 2048 - t.Cout * 8 - 512 - t.nchunks * (int)t.w_tile_bytes;
+    int na = budget / (int)t.a_stage_bytes;
+    if (na > 4) na = 4;
+    if (na < 2) return false;
+    t.na = na;
+    t.tmem_cols = 512;
+    // producer groups: enough warps per group to give every thread at most one item of the widest upsampled chunk
+    int items = 0;
+    for (int c = 0; c < t.nchunks; ++c) if (t.c_up[c]) items = std::max(items, 8 * MT * 2 * (int)t.c_nk[c]);
+    t.wpg = std::max(1, std::min(kProducerWarpsLarge, (items + 31) / 32));
+    t.npg = std::max(1, kProducerWarpsLarge / t.wpg);
+    t.head = last ? 1 : 0;
+    const int total_tiles = B * t.tiles_per_frame;
+    t.tile_begin = 0; t.tile_end = total_tiles;
+    P.is_tn = true; P.upcat = dec; P.small = false; P.per_sm = 1;
+    P.threads = 64 + 32 * (kEpiWarpsLarge + (dec ? kProducerWarpsLarge : 0));
+    P.smem = tn_smem_total(t);
+    P.grid = dim3((unsigned)std::min(total_tiles, num_sms), 1, 1);
+    // mirror the fields tests / tools read from TcParams
+    TcParams &p = P.p;
+    memset(&p, 0, sizeof(p));
+    p.B = B; p.L = L; p.T = T; p.Cout = lv.cout; p.Cin0 = lv.cin0; p.Cin1 = lv.cin1; p.Npad = t.Npad; p.Nh = t.Npad; p.nsplit = 1;
+    p.Nstride = t.Nstride; p.MT = MT; p.nacc = 2; p.FR = 1; p.m_tiles = total_tiles; p.nchunks = t.nchunks; p.resident = 1;
+    p.na = na; p.nb = t.nchunks; p.tg = 5; p.ngroups = 1; p.a_stage_bytes = t.a_stage_bytes; p.b_stage_bytes = t.w_tile_bytes;
+    p.a_tx_bytes = (int)t.a_stage_bytes; p.rows_used = 128 * MT; p.tmem_cols = 512; p.tiles_per_frame = t.tiles_per_frame;
+    p.tile_begin = 0; p.tile_end = total_tiles; p.n_epi = kEpiWarpsLarge;
+    return true;
+}
+
 static int build_plan(TcState *st, const float *x, float *y, int B, int T, void *ws)
 {
     const int n = st->n;
@@ -1345,6 +1792,29 @@ static int build_plan(TcState *st, const float *x, float *y, int B, int T, void 
     for (int i = 1; i < 2 * n + 1; ++i) {
         const TcLevel &lv = st->levels[i];
         TcPlanLevel &P = pl.lv[i];
+        if (parse_override(st->plan_ovr, i).any == false && plan_block_tn(lv, i, n, B, T, st->num_sms, P)) {
+            TnParams &t = P.tn;
+            const bool dec = i > n;
+            const bool last = (i == 2 * n);
+            t.ss = lv.ss;
+            t.out = (last && !st->store_last) ? nullptr : lvl(i);
+            t.head_w = st->out_w; t.head_b = st->out_b;
+            if (!dec) {
+                const int Cp = lv.cin0, Lp = 2 * t.L;           // decimated view of the previous encoder output (o[:, :, ::2])
+                if (make_map(st, &P.tmA, lvl(i - 1), Cp, t.L, B, (uint64_t)2 * Cp * 2, (uint64_t)Lp * Cp * 2, 64, 32, 1)) return -1;
+            } else {
+                const int e = 2 * n - i, Cs = lv.cin1;
+                if (make_map(st, &P.tmA, lvl(e), Cs, t.L, B, (uint64_t)Cs * 2, (uint64_t)t.L * Cs * 2, 64, 32, 1)) return -1;
+                t.prev = lvl(i - 1);
+                t.Lin = t.L / 2;
+                t.up_scale = (t.L > 1) ? (float)(t.Lin - 1) / (float)(t.L - 1) : 0.f;
+            }
+            if (make_map(st, &P.tmW, lv.wp_tn, (uint64_t)lv.tn_slots * 64, (uint64_t)lv.tn_npad, 1, (uint64_t)lv.tn_slots * 128,
+                         (uint64_t)lv.tn_npad * lv.tn_slots * 128, 64, (uint32_t)lv.tn_npad, 1))
+                return -1;
+            P.tmO = P.tmA;
+            continue;
+        }
         if (plan_block(lv, i, n, B, T, st->num_sms, st->plan_ovr, P)) return -1;
         TcParams &p = P.p;
         const bool dec = i > n;
@@ -1379,6 +1849,12 @@ static int build_plan(TcState *st, const float *x, float *y, int B, int T, void 
     if (getenv("WUNET_TC_DEBUG")) {
         for (int i = 1; i < 2 * n + 1; ++i) {
             const TcParams &p = pl.lv[i].p;
+            if (pl.lv[i].is_tn) {
+                const TnParams &t = pl.lv[i].tn;
+                fprintf(stderr, "[wunet tn] blk %2d L=%5d Cin=%3d+%3d Cout=%3d N'=%3d MT=%d chunks=%d na=%d wpg=%d npg=%d smem=%zu tiles=%d grid=%u\n", i, t.L,
+                        t.Cin0, t.Cin1, t.Cout, t.Npad, t.MT, t.nchunks, t.na, t.wpg, t.npg, pl.lv[i].smem, t.tile_end, pl.lv[i].grid.x);
+                continue;
+            }
             fprintf(stderr, "[wunet tc] blk %2d L=%5d Cin=%3d+%3d Cout=%3d Nh=%3d x%d MT=%d nacc=%d packed=%d FR=%d res=%d bulk=%d na=%d nb=%d tg=%d smem=%zu tmem=%u tiles=%d grid=%u small=%d per_sm=%d\n",
                     i, p.L, p.Cin0, p.Cin1, p.Cout, p.Nh, p.nsplit, p.MT, p.nacc, p.packed, p.FR, p.resident, p.bulk_store, p.na, p.nb, p.tg, pl.lv[i].smem, p.tmem_cols,
                     p.m_tiles * p.nsplit, pl.lv[i].grid.x, (int)pl.lv[i].small, pl.lv[i].per_sm);
@@ -1395,10 +1871,13 @@ int tc_debug_plan(int n, int ci, const TcBlockSrc *blocks, int nblocks, int B, i
     if (cap < 32 || !f) return tc_fail("need room for 32 fields");
     std::vector<TcLevel> levels(nblocks);
     const char *mge = getenv("WUNET_TC_MERGE");
-    derive_levels(levels, blocks, nblocks, n, !(mge && mge[0] == '0'));
+    const char *tne = getenv("WUNET_TC_TN");
+    derive_levels(levels, blocks, nblocks, n, !(mge && mge[0] == '0'), !(tne && tne[0] == '0'));
     const char *ovr = getenv("WUNET_TC_OVR");
     TcPlanLevel P{};
-    if (plan_block(levels[block], block, n, B, T, num_sms, ovr ? ovr : "", P)) return -1;
+    const std::string ovr_s = ovr ? ovr : "";
+    if (!(parse_override(ovr_s, block).any == false && plan_block_tn(levels[block], block, n, B, T, num_sms, P)))
+        if (plan_block(levels[block], block, n, B, T, num_sms, ovr_s, P)) return -1;
     const TcParams &p = P.p;
     const int v[32] = {p.L, p.Cin0, p.Cin1, p.Cout, p.Npad, p.Nh, p.nsplit, p.Nstride, p.MT, p.nacc, p.packed, p.FR, p.S, p.m_tiles,
                        p.nchunks, p.resident, p.bulk_store, p.na, p.nb, p.tg, p.ngroups, (int)p.a_stage_bytes, (int)p.b_stage_bytes,
@@ -1420,6 +1899,8 @@ static int tc_prepare(TcState *st, const float *x, float *y, int B, int T, void 
         cudaFuncSetAttribute(conv_tc_kernel<5, true, kEpiWarpsSmall, kProducerWarpsSmall, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         cudaFuncSetAttribute(conv_tc_kernel<5, true, kEpiWarpsLarge, kProducerWarpsLarge, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         cudaFuncSetAttribute(conv_tc_kernel<5, true, kEpiWarpsSmall, kProducerWarpsSmall, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+        cudaFuncSetAttribute(conv_tn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+        cudaFuncSetAttribute(conv_tn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         cudaFuncSetAttribute(enc0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
         int dev = 0, sms = 0;
         if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
@@ -1461,6 +1942,24 @@ static int launch_enc0(TcState *st, const float *x, int f0, int nf, int T, void 
 static int launch_block(TcState *st, int i, int t0, int t1, cudaStream_t stream, const float *x = nullptr, float *y = nullptr)
 {
     TcPlanLevel &P = st->plan.lv[i];
+    if (P.is_tn) {
+        TnParams t = P.tn;
+        t.x = x; t.y = y;
+        if (t1 >= 0) { t.tile_begin = t0; t.tile_end = t1; }
+        const int ntiles = t.tile_end - t.tile_begin;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)std::min(ntiles, st->num_sms), 1, 1);
+        cfg.blockDim = dim3(P.threads); cfg.dynamicSmemBytes = P.smem; cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = st->pdl ? 1 : 0;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        if (P.upcat) cudaLaunchKernelEx(&cfg, conv_tn_kernel<true>, P.tmA, P.tmW, t);
+        else cudaLaunchKernelEx(&cfg, conv_tn_kernel<false>, P.tmA, P.tmW, t);
+        const cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return tc_fail("conv_tn level %d launch failed: %s", i, cudaGetErrorString(e));
+        return 0;
+    }
     TcParams p = P.p;
     p.x = x; p.y = y;                                    // only the fused head (last block) reads x / writes y
     if (t1 >= 0) { p.tile_begin = t0; p.tile_end = t1; }
@@ -1590,7 +2089,7 @@ void tc_destroy(TcState *st)
         }
         cudaFree(st->trace);
     }
-    for (auto &lv : st->levels) { cudaFree(lv.wp); cudaFree(lv.ss); cudaFree(lv.w_own); }
+    for (auto &lv : st->levels) { cudaFree(lv.wp); cudaFree(lv.ss); cudaFree(lv.w_own); cudaFree(lv.wp_tn); }
     delete st;
 }
 

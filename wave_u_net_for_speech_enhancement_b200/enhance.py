@@ -14,11 +14,32 @@ import numpy as np
 import torch
 
 
+class _PinnedPool:
+    """Grow-only pinned staging buffers, reused across calls: allocating page-locked memory costs milliseconds, a forward of
+    a few hundred frames costs one. Single-threaded use (every result is copied out of the pool before the call returns)."""
+
+    def __init__(self):
+        self._buf = {}
+
+    def get(self, name: str, frames: int, sample_length: int, pin: bool) -> torch.Tensor:
+        key = (name, sample_length, pin)
+        t = self._buf.get(key)
+        if t is None or t.shape[0] < frames:
+            t = torch.empty(max(frames, 1), 1, sample_length, dtype=torch.float32)
+            if pin:
+                t = t.pin_memory()
+            self._buf[key] = t
+        return t[:frames]
+
+
+_POOL = _PinnedPool()
+
+
 def frame_clips(waveforms: Sequence[np.ndarray], sample_length: int = 16384, pin: bool = True
                 ) -> Tuple[torch.Tensor, List[Tuple[int, int, int]]]:
     """Zero-pad each 1-D waveform to a multiple of ``sample_length`` (enhancement.py:57-59) and split it into chunks
-    (enhancement.py:62). Returns the stacked chunks ``[N,1,sample_length]`` (float32, pinned if requested) and, per clip,
-    ``(first_frame, n_frames, original_length)``."""
+    (enhancement.py:62). Returns the stacked chunks ``[N,1,sample_length]`` (float32; a view of a pooled pinned staging
+    buffer if requested, valid until the next call) and, per clip, ``(first_frame, n_frames, original_length)``."""
     index, total = [], 0
     for w in waveforms:
         n = int(np.asarray(w).shape[-1])
@@ -27,13 +48,12 @@ def frame_clips(waveforms: Sequence[np.ndarray], sample_length: int = 16384, pin
         nf = max(1, -(-n // sample_length))
         index.append((total, nf, n))
         total += nf
-    frames = torch.zeros(total, 1, sample_length, dtype=torch.float32)
-    if pin and torch.cuda.is_available():
-        frames = frames.pin_memory()
+    frames = _POOL.get("in", total, sample_length, pin and torch.cuda.is_available())
     flat = frames.view(total, sample_length)
     for (f0, nf, n), w in zip(index, waveforms):
         dst = flat[f0:f0 + nf].reshape(-1)
         dst[:n] = torch.from_numpy(np.ascontiguousarray(w, dtype=np.float32))
+        dst[n:] = 0.0                                          # the padding of enhancement.py:58 (the buffer is reused)
     return frames, index
 
 
@@ -52,9 +72,8 @@ def enhance_waveforms(model, waveforms: Sequence[np.ndarray], sample_length: int
     only) replaces ``model.forward_host_stream``."""
     frames, index = frame_clips(waveforms, sample_length)
     total = frames.shape[0]
-    out = torch.empty_like(frames)
-    if frames.is_pinned():
-        out = out.pin_memory()
+    pinned = frames.is_pinned()
+    out = _POOL.get("out", total, sample_length, pinned)
     B = min(batch_frames, total)
     nfull, rem = divmod(total, B)
     batches = [frames[i * B:(i + 1) * B] for i in range(nfull)]
@@ -62,11 +81,10 @@ def enhance_waveforms(model, waveforms: Sequence[np.ndarray], sample_length: int
     tail_in = tail_out = None
     if rem:
         # keep the batch size constant (one plan / workspace): the last batch is filled up with silent frames
-        tail_in = torch.zeros(B, 1, sample_length, dtype=torch.float32)
-        tail_out = torch.empty_like(tail_in)
-        if frames.is_pinned():
-            tail_in, tail_out = tail_in.pin_memory(), tail_out.pin_memory()
+        tail_in = _POOL.get("tail_in", B, sample_length, pinned)
+        tail_out = _POOL.get("tail_out", B, sample_length, pinned)
         tail_in[:rem] = frames[nfull * B:]
+        tail_in[rem:] = 0.0
         batches.append(tail_in)
         outs.append(tail_out)
     fn = stream_fn if stream_fn is not None else model.forward_host_stream
