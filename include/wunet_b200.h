@@ -36,6 +36,8 @@ extern "C" {
 /* arithmetic of the convolution path */
 #define WUNET_PREC_FP32 0   /* fp32 operands, fp32 FFMA accumulate: parity <= 1e-4 vs reference (config 2) */
 #define WUNET_PREC_BF16 1   /* bf16 operands/activations, fp32 accumulate on tcgen05 tensor cores (config 3) */
+#define WUNET_PREC_FP32_TC 2 /* fp32-grade on the tensor cores: activations and weights split into bf16 high + low parts, three tcgen05
+                               MMAs per product (hi*hi + lo*hi + hi*lo, fp32 accumulate): <= 1e-4 vs the reference like WUNET_PREC_FP32 */
 
 typedef struct wunet_ctx wunet_ctx;
 

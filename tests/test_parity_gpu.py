@@ -233,3 +233,63 @@ def test_bf16_forward_host_matches_device_path(state_full):
     x = wo.make_input(8, 16384, seed=8)
     yh = m.forward_host(torch.from_numpy(x).pin_memory())
     assert np.array_equal(yh.numpy(), run(m, x))
+
+
+# ---- fp32_tc: fp32-grade results on the tensor cores (bf16 hi + lo split, three MMAs per product) -----------------------
+# BASELINE.json north_star asks for tcgen05 AND <= 1e-4 on the same path: every fp32 parity case again, same tolerance.
+def test_fp32_tc_small_config_all_levels(golden_dir):
+    g = np.load(os.path.join(golden_dir, "small_n4_c8.npz"))
+    n, ci, T, B = int(g["n_layers"]), int(g["channels_interval"]), int(g["T"]), int(g["B"])
+    st = wo.make_state(n, ci, seed=int(g["state_seed"]))
+    x = wo.make_input(B, T, seed=int(g["input_seed"]))
+    os.environ["WUNET_TC_STORE_LAST"] = "1"
+    m = make_model(n, ci, st, "fp32_tc")
+    y = run(m, x)
+    errs = []
+    for i in range(2 * n + 1):
+        lv = m.read_level(i, B, T).cpu().numpy()
+        errs.append(float(np.abs(lv - g[f"level_{i}"]).max()))
+    print("fp32_tc small config: per-level max-abs errors " + " ".join("%.1e" % e for e in errs) + " | output %.2e" % np.abs(y - g["y"]).max())
+    assert max(errs) <= FP32_TOL, errs
+    assert np.abs(y - g["y"]).max() <= FP32_TOL
+
+
+def test_fp32_tc_full_config_vs_golden_and_oracle(full, state_full):
+    x = wo.make_input(2, 16384, seed=int(full["input_seed"]))
+    os.environ["WUNET_TC_STORE_LAST"] = "1"
+    m = make_model(12, 24, state_full, "fp32_tc")
+    y = run(m, x)
+    errs = []
+    for i in range(25):
+        lv = m.read_level(i, 2, 16384).cpu().numpy()
+        idx = full[f"probe_idx_{i}"]
+        errs.append(float(np.abs(lv[0][:, idx] - full[f"probe_{i}"]).max()))
+    err = float(np.abs(y - full["y"]).max())
+    print("fp32_tc full config: per-level probe errors " + " ".join("%.1e" % e for e in errs) + " | output %.2e" % err)
+    assert max(errs) <= FP32_TOL, errs
+    assert err <= FP32_TOL, err
+    assert m.last_launch_count() == 25
+    os.environ["WUNET_TC_STORE_LAST"] = "0"
+    assert np.array_equal(run(make_model(12, 24, state_full, "fp32_tc"), x), y)       # head fused, last block not stored
+
+
+def test_fp32_tc_config2_batch64_edges_and_odd_lengths(golden_dir, state_full):
+    os.environ["WUNET_TC_STORE_LAST"] = "0"
+    m = make_model(12, 24, state_full, "fp32_tc")
+    B = 64
+    x = wo.make_input(B, 16384, seed=4321)
+    y = run(m, x)
+    pick = [0, 17, 42, 63]
+    want = wo.COracle(12, 24).forward(state_full, x[pick])
+    err = float(np.abs(y[pick] - want).max())
+    print("fp32_tc B=64: max-abs error over 4 frames %.2e" % err)
+    assert err <= FP32_TOL
+    perm = np.random.default_rng(0).permutation(B)
+    assert np.array_equal(run(m, x[perm]), y[perm])
+    g = np.load(os.path.join(golden_dir, "edges_n12_c24.npz"))
+    for name, xe in wo.edge_inputs(16384).items():
+        assert np.abs(run(m, xe) - g[name]).max() <= FP32_TOL, name
+    for Tx in (4096, 20480):
+        assert np.abs(run(m, wo.make_input(1, Tx, seed=77 + Tx)) - g[f"T{Tx}"]).max() <= FP32_TOL, Tx
+    yh = m.forward_host(torch.from_numpy(x[:8]).pin_memory())
+    assert np.array_equal(yh.numpy(), run(m, x[:8]))

@@ -113,3 +113,29 @@ def test_three_adam_steps_track_the_composite_torch_path():
         if k.endswith(".0.bias") and not k.startswith("out."):
             continue                      # gradient is rounding noise, Adam turns it into +-lr steps on both sides
         assert rel_err(a.float().cpu().numpy(), b.float().cpu().numpy()) <= 5e-3, k
+
+
+def test_tuned_training_kernels_match_the_one_thread_per_output_ones(monkeypatch):
+    """csrc/wunet_train.cu: forward conv / input gradient through the tuned fp32 conv kernels and the tiled weight-gradient
+    kernel against the naive kernels they replaced (WUNET_TRAIN_NAIVE=1), same step, reference architecture at T=4096."""
+    n, ci, B, T = 12, 24, 3, 4096
+    st = wo.make_state(n, ci, seed=5)
+    noisy, clean = make_pair(B, T, 77)
+    out = {}
+    for naive in ("1", "0"):
+        monkeypatch.setenv("WUNET_TRAIN_NAIVE", naive)
+        m = make_model(n, ci, st, "native")
+        loss, y = step(m, noisy, clean)
+        out[naive] = (loss, y, {k: p.grad.detach().cpu().numpy() for k, p in m.named_parameters()},
+                      {k: v.detach().cpu().numpy() for k, v in m.state_dict().items() if "running" in k})
+    assert abs(out["0"][0] - out["1"][0]) <= 1e-6 * abs(out["1"][0])
+    assert np.abs(out["0"][1] - out["1"][1]).max() <= 1e-5
+    worst = (0.0, "")
+    for k, g1 in out["1"][2].items():
+        if k.endswith(".0.bias") and not k.startswith("out."):
+            continue
+        worst = max(worst, (rel_err(out["0"][2][k], g1), k))
+    print(f"tuned vs naive training kernels: worst gradient rel diff {worst[0]:.2e} ({worst[1]})")
+    assert worst[0] <= 2e-3, worst               # different summation orders of an ill-conditioned fp32 sum (see GRAD_REL_FULL)
+    for k, v in out["1"][3].items():
+        assert rel_err(out["0"][3][k], v) <= 1e-5, k

@@ -9,7 +9,8 @@ SO_PATH = os.environ.get("WUNET_LIB_PATH") or os.path.join(_HERE, "libwunet_b200
 
 PREC_FP32 = 0
 PREC_BF16 = 1
-PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16}
+PREC_FP32_TC = 2
+PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "fp32_tc": PREC_FP32_TC}
 
 _lib = None
 

@@ -47,6 +47,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         common += ["-Xptxas", "-v"]
     if os.environ.get("WUNET_TC_TRACE"):
         common += ["-DWUNET_TC_TRACE"]
+    if os.environ.get("WUNET_TN_DEBUG"):
+        common += ["-DWUNET_TN_DEBUG"]                  # development: conv_tn_kernel instantiations with one role switched off
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     procs = []
     for s in SOURCES:

@@ -286,7 +286,8 @@ size_t wunet_workspace_bytes(const wunet_ctx *c, int B, int T, int precision)
         fp32_layout(c, B, T, off, total);
         return total;
     }
-    if (precision == WUNET_PREC_BF16) return tc_workspace_bytes(c->n, c->ci, B, T);
+    if (precision == WUNET_PREC_BF16) return tc_workspace_bytes(c->n, c->ci, B, T, 0);
+    if (precision == WUNET_PREC_FP32_TC) return tc_workspace_bytes(c->n, c->ci, B, T, 1);
     fail(WUNET_EINVAL, "unknown precision %d", precision);
     return 0;
 }
@@ -306,7 +307,8 @@ int wunet_forward(wunet_ctx *c, const float *x, float *y, int B, int T, int prec
     if (precision == WUNET_PREC_FP32) return forward_fp32(c, x, y, B, T, workspace, st);
     int launches = 0;
     cudaEvent_t *ev = prof_events(c);
-    const int r = tc_forward(c->tc, x, y, B, T, workspace, st, &launches, ev);
+    if (precision != WUNET_PREC_BF16 && precision != WUNET_PREC_FP32_TC) return fail(WUNET_EINVAL, "unknown precision %d", precision);
+    const int r = tc_forward(c->tc, x, y, B, T, workspace, st, &launches, ev, precision == WUNET_PREC_FP32_TC ? 1 : 0);
     if (ev && r == 0) c->ev_recorded = 2 * c->n + 3;
     if (r != 0) return fail(WUNET_ECUDA, "tcgen05 forward failed: %s", tc_error());
     c->last_launches = launches;
@@ -336,11 +338,11 @@ int wunet_forward_host(wunet_ctx *c, const float *x_host, float *y_host, int B, 
         CUDA_TRY(cudaMalloc(&c->hws, need));
         c->hws_cap = need;
     }
-    if (precision == WUNET_PREC_BF16) {
+    if (precision == WUNET_PREC_BF16 || precision == WUNET_PREC_FP32_TC) {
         // chunked pipeline: H2D, first/last kernels and D2H overlap per batch chunk (see tc_forward_host)
         if (!c->have_weights) return fail(WUNET_ESTATE, "wunet_forward_host called before wunet_set_weights");
         int launches = 0;
-        if (tc_forward_host(c->tc, x_host, y_host, c->hx, c->hy, B, T, c->hws, c->hstream, &launches) != 0)
+        if (tc_forward_host(c->tc, x_host, y_host, c->hx, c->hy, B, T, c->hws, c->hstream, &launches, precision == WUNET_PREC_FP32_TC ? 1 : 0) != 0)
             return fail(WUNET_ECUDA, "tcgen05 host pipeline failed: %s", tc_error());
         c->last_launches = launches;
         return WUNET_OK;
@@ -438,8 +440,8 @@ int wunet_read_level(wunet_ctx *c, int block, const void *workspace, int B, int 
                                  (size_t)B * c->blocks[block].cout * L * sizeof(float), cudaMemcpyDeviceToDevice, st));
         return WUNET_OK;
     }
-    if (precision == WUNET_PREC_BF16) {
-        const int r = tc_read_level(c->tc, block, workspace, B, T, out_dev, st);
+    if (precision == WUNET_PREC_BF16 || precision == WUNET_PREC_FP32_TC) {
+        const int r = tc_read_level(c->tc, block, workspace, B, T, out_dev, st, precision == WUNET_PREC_FP32_TC ? 1 : 0);
         if (r != 0) return fail(WUNET_ECUDA, "tc_read_level failed: %s", tc_error());
         return WUNET_OK;
     }

@@ -29,6 +29,8 @@ struct ConvArgs {
     int Cin, Cin0, Cin1; // Cin = Cin0 + Cin1 (Cin1 = 0 unless UPCAT)
     int Cout;
     float up_scale;      // UPCAT: (L/2 - 1) / (L - 1) in fp32, like ATen's area_pixel_compute_scale
+    int linear;          // 0: LeakyReLU(0.1) epilogue (the forward blocks); 1: out = acc * scale + shift (training: pre-BatchNorm
+                         // conv output, input gradients)
 };
 
 // x -> NCL element fetch with zero padding outside [0, L)  (Conv1d padding, per frame)
@@ -57,10 +59,10 @@ __device__ __forceinline__ float fetch_src(const ConvArgs &a, int b, int ci, int
     }
 }
 
-__device__ __forceinline__ float bn_lrelu(float acc, float scale, float shift)
+__device__ __forceinline__ float bn_lrelu(float acc, float scale, float shift, int linear = 0)
 {
     const float v = fmaf(acc, scale, shift);
-    return v >= 0.f ? v : kLreluSlope * v;
+    return (v >= 0.f || linear) ? v : kLreluSlope * v;
 }
 
 // ---- launchers implemented in wunet_fp32.cu -------------------------------------------------

@@ -97,10 +97,10 @@ __global__ void __launch_bounds__(96 * LW) conv_slide_kernel(const ConvArgs a)
         const int co = co0 + wc * 8 + m;
         const float s = __ldg(a.scale + co), t = __ldg(a.shift + co);
         float4 v0, v1;
-        v0.x = bn_lrelu(acc[m][0], s, t); v0.y = bn_lrelu(acc[m][1], s, t);
-        v0.z = bn_lrelu(acc[m][2], s, t); v0.w = bn_lrelu(acc[m][3], s, t);
-        v1.x = bn_lrelu(acc[m][4], s, t); v1.y = bn_lrelu(acc[m][5], s, t);
-        v1.z = bn_lrelu(acc[m][6], s, t); v1.w = bn_lrelu(acc[m][7], s, t);
+        v0.x = bn_lrelu(acc[m][0], s, t, a.linear); v0.y = bn_lrelu(acc[m][1], s, t, a.linear);
+        v0.z = bn_lrelu(acc[m][2], s, t, a.linear); v0.w = bn_lrelu(acc[m][3], s, t, a.linear);
+        v1.x = bn_lrelu(acc[m][4], s, t, a.linear); v1.y = bn_lrelu(acc[m][5], s, t, a.linear);
+        v1.z = bn_lrelu(acc[m][6], s, t, a.linear); v1.w = bn_lrelu(acc[m][7], s, t, a.linear);
         float4 *dst = reinterpret_cast<float4 *>(a.out + ((size_t)b * a.Cout + co) * a.L + l0 + lbase);
         dst[0] = v0;
         dst[1] = v1;
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(128) conv_gen_kernel(const ConvArgs a)
         for (int m = 0; m < 6; ++m) {
             const int co = co0 + m0 + m;
             if (co < a.Cout)
-                a.out[((size_t)b * a.Cout + co) * a.L + l] = bn_lrelu(acc[m][n], __ldg(a.scale + co), __ldg(a.shift + co));
+                a.out[((size_t)b * a.Cout + co) * a.L + l] = bn_lrelu(acc[m][n], __ldg(a.scale + co), __ldg(a.shift + co), a.linear);
         }
     }
 }
@@ -266,6 +266,7 @@ int launch_conv_fp32(const ConvArgs &a, int ksize, int mode, cudaStream_t st)
         if (mode == SRC_DECIM) return launch_conv_mode<15, SRC_DECIM>(a, st);
     } else if (ksize == 5) {
         if (mode == SRC_UPCAT) return launch_conv_mode<5, SRC_UPCAT>(a, st);
+        if (mode == SRC_DIRECT) return launch_conv_mode<5, SRC_DIRECT>(a, st);      // training: input gradient of a decoder block
     }
     return -1;
 }

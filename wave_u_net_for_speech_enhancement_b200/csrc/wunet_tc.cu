@@ -203,7 +203,8 @@ struct TcParams {
     int B, L, Cout, T;
     int Cin0, Cin1;            // K segments: ENC: Cin0 = Cin, Cin1 = 0; DEC: Cin0 = upsampled prev, Cin1 = skip
     int nchunks0, nchunks;     // 64-channel chunks in segment 0 / in total
-    unsigned char chunk_map[16]; // K-loop order: bit 7 = chunk of the upsampled segment, bits 0-6 = chunk index inside its segment
+    unsigned char chunk_map[48]; // K-loop order: bit 7 = chunk of the upsampled segment, bits 0-5 = chunk index inside its segment;
+                                 // bit 6: merged tail chunk (MG kernels) / low-part data (split-precision kernels)
     // N tiling
     int Npad, Nh, Nstride;     // padded Cout, columns per CTA, TMEM column stride between sub-tile accumulators
     // M tiling
@@ -235,6 +236,8 @@ struct TcParams {
     long long *trace;          // WUNET_TC_TRACE builds: per-role clock64 stamps of CTA 0 (development)
     // merged tail chunk (MG = 1 instantiations): the last K chunk of a decoder block is [skip tail (TMA) | upsampled tail
     // (producers)] in ONE stage - one K chunk fewer for dec6 / dec9 / dec10 of the reference architecture
+    int split;                 // split-precision mode (SP kernels): activations are stored as [hi | lo] bf16 channel halves (2 C channels per
+                               // row), the K loop runs [hi data x w_hi | lo data x w_hi | hi data x w_lo] and the epilogue stores hi and lo
     int mg;                    // 1: chunk_map's last entry (0x40) is such a merged chunk
     int mg_vo, mg_nvec;        // first 16-byte vector / number of vectors the producers write in it
     int mg_nk, mg_kslot;       // its K16 steps, its 64-wide slot in the packed weights
@@ -259,12 +262,24 @@ __host__ __device__ inline SmemMap smem_map(const TcParams &p)
 inline size_t smem_total(const TcParams &p) { return smem_map(p).bars + 8 * (8 + 2 * kMaxBStages + 4) + 16 + (p.mg ? 32 : 0) + 1024; }
 
 // K-loop position c -> (segment, chunk index inside the segment, K16 steps, 64-wide slot in the packed weights)
-struct ChunkInfo { bool up; int idx, nk, kslot; bool merged; int vo, nvec; };
-template <bool UPCAT, int MG>
+struct ChunkInfo { bool up; int idx, nk, kslot; bool merged; int vo, nvec; bool lo; };
+template <bool UPCAT, int MG, int SP = 0>
 __device__ __forceinline__ ChunkInfo chunk_info(const TcParams &p, int c)
 {
     ChunkInfo ci;
     const int m = p.chunk_map[c];
+    ci.lo = false;
+    if (SP != 0) {                                // split precision: the weight slot is the K-loop position itself
+        ci.merged = false;
+        ci.up = UPCAT && (m & 0x80);
+        ci.lo = (m & 0x40) != 0;
+        ci.idx = m & 0x3f;
+        const int seg = (ci.up || !UPCAT) ? p.Cin0 - 64 * ci.idx : p.Cin1 - 64 * ci.idx;
+        ci.nk = ((seg < 64 ? seg : 64) + 15) >> 4;
+        ci.kslot = c;
+        ci.vo = 0; ci.nvec = ci.nk * 2;
+        return ci;
+    }
     if (MG != 0 && UPCAT && (m & 0x40)) {          // merged tail chunk: TMA fills the leading vectors, the producers the next ones
         ci.up = true; ci.merged = true;
         ci.idx = p.mg_up_idx; ci.nk = p.mg_nk; ci.kslot = p.mg_kslot; ci.vo = p.mg_vo; ci.nvec = p.mg_nvec;
@@ -285,7 +300,7 @@ __device__ __forceinline__ ChunkInfo chunk_info(const TcParams &p, int c)
 // -------------------------------------------------------------------------------------------------
 // MG = 1: decoder instantiations whose K loop ends in a merged tail chunk (p.mg); MG = 0 everything else (kept in separate
 // instantiations so that the code of the validated ones does not change while they are being developed).
-template <int KS, bool UPCAT, int EW, int PW, int MG>
+template <int KS, bool UPCAT, int EW, int PW, int MG, int SP = 0>
 __global__ void __launch_bounds__(64 + 32 * (EW + PW), EW == kEpiWarpsSmall ? 2 : 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmO, const TcParams p)
@@ -376,7 +391,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (!blocking && !mbar_test(a_empty + 8 * sa, pa ^ 1)) return false;
                 int b0, l0, n0;
                 tile_coords(a_tile, b0, l0, n0);
-                const ChunkInfo aci = chunk_info<UPCAT, MG>(p, a_c);
+                const ChunkInfo aci = chunk_info<UPCAT, MG, SP>(p, a_c);
                 const bool from_tma = !aci.up;
                 TRACE(0, tr0);
                 mbar_wait(a_empty + 8 * sa, pa ^ 1);
@@ -386,7 +401,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int lcoord = p.packed ? -PAD : l0 - PAD;
                     mbar_expect_tx(a_full + 8 * sa, p.a_tx_bytes);
                     for (int op = 0; op < p.nops; ++op)
-                        tma_load_3d(base + sm.a + sa * p.a_stage_bytes + op * p.R1 * 128, &tmA, a_full + 8 * sa, cc * 64,
+                        tma_load_3d(base + sm.a + sa * p.a_stage_bytes + op * p.R1 * 128, &tmA, a_full + 8 * sa,
+                                    cc * 64 + ((SP != 0 && aci.lo) ? (UPCAT ? p.Cin1 : p.Cin0) : 0),      // low part: second channel half
                                     lcoord + op * p.R1, b0);
                 } else if (MG != 0 && aci.merged) {
                     // skip tail by TMA into the leading vectors of the stage (zero fill behind it), completion on a_tma: the
@@ -408,7 +424,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 // the whole packed weight set of this block (nchunks x KS tiles of [Nh x 64]) is loaded once per CTA
                 mbar_expect_tx(b_full, (uint32_t)p.nchunks * p.ngroups * p.tg * p.Nh * 128);
                 for (int c = 0; c < p.nchunks; ++c) {
-                    const int kslot = chunk_info<UPCAT, MG>(p, c).kslot;
+                    const int kslot = chunk_info<UPCAT, MG, SP>(p, c).kslot;
                     for (int g = 0; g < p.ngroups; ++g)
                         tma_load_3d(base + sm.b + (uint32_t)(c * p.ngroups + g) * p.b_stage_bytes, &tmW, b_full, kslot * 64, 0, g * p.tg);
                 }
@@ -423,7 +439,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     // the weight groups of this chunk go out as soon as their ring slots free up; the A tile of the NEXT
                     // chunk is slipped in between them the moment its stage is released (it never blocks the weights)
                     bool a_done = false;
-                    const int kslot = chunk_info<UPCAT, MG>(p, c).kslot;
+                    const int kslot = chunk_info<UPCAT, MG, SP>(p, c).kslot;
                     for (int g = 0; g < (p.resident ? 0 : p.ngroups); ++g) {
                         if (!a_done) a_done = issue_a(false);
                         mbar_wait(b_empty + 8 * sb, pb ^ 1);
@@ -463,7 +479,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t acc_col = tmem_base + buf * p.MT * p.Nstride;
                 for (int c = 0; c < p.nchunks; ++c) {
-                    const int nk = chunk_info<UPCAT, MG>(p, c).nk;
+                    const int nk = chunk_info<UPCAT, MG, SP>(p, c).nk;
                     mbar_wait(a_full + 8 * sa, pa);
                     TRACE(1, tr1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -575,7 +591,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             const bool col_ok = col < Nthis && n0 + col < p.Cout;
                             if (p.bulk_store) {
                                 if (col_ok) *reinterpret_cast<uint4 *>(srow + (((2 * h16 + g8) ^ sw) << 4)) = o;
-                            } else if (p.out != nullptr && valid && col_ok) {
+                            } else if (SP != 0 && p.out != nullptr && valid && col_ok) {
+                                // split precision: the row holds [hi(Cout) | lo(Cout)]; lo = bf16(v - hi)
+                                float g[8];
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) g[j] = f[j] - __bfloat162float(__float2bfloat16_rn(f[j]));
+                                __nv_bfloat16 *orow = p.out + ((size_t)bb * p.L + l) * (2 * p.Cout) + n0 + col;
+                                *reinterpret_cast<uint4 *>(orow) = o;
+                                *reinterpret_cast<uint4 *>(orow + p.Cout) =
+                                    make_uint4(pack_bf16(g[0], g[1]), pack_bf16(g[2], g[3]), pack_bf16(g[4], g[5]), pack_bf16(g[6], g[7]));
+                            } else if (SP == 0 && p.out != nullptr && valid && col_ok) {
                                 *reinterpret_cast<uint4 *>(p.out + ((size_t)bb * p.L + l) * p.Cout + n0 + col) = o;
                             }
                             if (p.head) {
@@ -623,10 +648,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         bool pref = false;
         const int nruns = (p.rows_used + 15) >> 4;
         // a chunk whose first-round items can be prefetched into the register window one work unit ahead
-        auto unit_fast = [&](int c) { return !p.packed && chunk_info<UPCAT, MG>(p, c).up; };
+        auto unit_fast = [&](int c) { return SP == 0 && !p.packed && chunk_info<UPCAT, MG, SP>(p, c).up; };
         // loads of item `item` of unit (frame ub0, first row ul0, K-loop position c) into the window
         auto fetch = [&](int ub0, int ul0, int c, int item) {
-            const ChunkInfo u = chunk_info<UPCAT, MG>(p, c);
+            const ChunkInfo u = chunk_info<UPCAT, MG, SP>(p, c);
             const int nvec = u.nvec;
             if (item >= nruns * nvec) return;
             const int run = item / nvec, vec = item - run * nvec;
@@ -645,7 +670,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // store instead of branches): the 16 rows are independent, and a branch per row serialises their dependent chains
         // (trace: ~3600 cycles per item with branches, the stage hand-off was waiting on it).
         auto emit = [&](uint8_t *dst, int l0, int c, int item, const uint4 (&w)[10]) {
-            const ChunkInfo u = chunk_info<UPCAT, MG>(p, c);
+            const ChunkInfo u = chunk_info<UPCAT, MG, SP>(p, c);
             const int nvec = u.nvec;
             const int run = item / nvec, vec = item - run * nvec;
             const int ch = u.idx * 64 + vec * 8;
@@ -683,7 +708,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (pt == 0) TRACE(4, tr4);
                 mbar_wait(a_empty + 8 * sa, pa ^ 1);
                 if (pt == 0) TRACE(4, tr4);
-                const ChunkInfo cu = chunk_info<UPCAT, MG>(p, c);
+                const ChunkInfo cu = chunk_info<UPCAT, MG, SP>(p, c);
                 bool emitted_fast = false;
                 if (cu.up) {
                     if (MG != 0 && cu.merged) {                               // the TMA part of this stage must have landed
@@ -702,15 +727,42 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         pref = false;
                         emitted_fast = true;
                     } else {
-                        // frames shorter than a tile (packed): generic per-(row, vector) path, ATen index math in fp32
+                        // frames shorter than a tile (packed), and every level in split-precision mode: generic per-(row, vector)
+                        // path, ATen index math in fp32
                         const int items = p.rows_used * nvec;
                         for (int itx = pt; itx < items; itx += NPROD) {
                             const int row = itx / nvec, vec = itx - row * nvec;
-                            const int f = row / p.S;
-                            const int bb = b0 + f, l = row - f * p.S - PAD;
+                            int bb = b0, l = l0 - PAD + row;                       // full-length frames (split-precision mode only)
+                            if (p.packed) { const int f = row / p.S; bb = b0 + f; l = row - f * p.S - PAD; }
                             const int ch = cu.idx * 64 + vec * 8;
                             uint4 o = make_uint4(0u, 0u, 0u, 0u);
-                            if (bb < p.B && l >= 0 && l < p.L && ch < p.Cin0) {
+                            if (SP != 0 && bb < p.B && l >= 0 && l < p.L && ch < p.Cin0) {
+                                // split precision: prev rows are [hi | lo] (2 Cin0 channels); interpolate hi + lo in fp32 with the
+                                // fp32 path's formula (lam0 a + lam1 b), emit the high or the low bf16 part of the result
+                                const float s = p.up_scale * (float)l;
+                                const int i0 = (int)s;
+                                const int i1 = i0 + (i0 < p.Lin - 1 ? 1 : 0);
+                                const float lam1 = s - (float)i0, lam0 = 1.f - lam1;
+                                const __nv_bfloat16 *r0 = p.prev + ((size_t)bb * p.Lin + i0) * (2 * p.Cin0) + ch;
+                                const __nv_bfloat16 *r1 = p.prev + ((size_t)bb * p.Lin + i1) * (2 * p.Cin0) + ch;
+                                const uint4 h0 = __ldg(reinterpret_cast<const uint4 *>(r0)), l0v = __ldg(reinterpret_cast<const uint4 *>(r0 + p.Cin0));
+                                const uint4 h1 = __ldg(reinterpret_cast<const uint4 *>(r1)), l1v = __ldg(reinterpret_cast<const uint4 *>(r1 + p.Cin0));
+                                const uint32_t ah[4] = {h0.x, h0.y, h0.z, h0.w}, al[4] = {l0v.x, l0v.y, l0v.z, l0v.w};
+                                const uint32_t bh[4] = {h1.x, h1.y, h1.z, h1.w}, bl[4] = {l1v.x, l1v.y, l1v.z, l1v.w};
+                                uint32_t r[4];
+#pragma unroll
+                                for (int q4 = 0; q4 < 4; ++q4) {
+                                    const float2 fah = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&ah[q4]));
+                                    const float2 fal = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&al[q4]));
+                                    const float2 fbh = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&bh[q4]));
+                                    const float2 fbl = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&bl[q4]));
+                                    const float vx = lam0 * (fah.x + fal.x) + lam1 * (fbh.x + fbl.x);
+                                    const float vy = lam0 * (fah.y + fal.y) + lam1 * (fbh.y + fbl.y);
+                                    const float hx = __bfloat162float(__float2bfloat16_rn(vx)), hy = __bfloat162float(__float2bfloat16_rn(vy));
+                                    r[q4] = cu.lo ? pack_bf16(vx - hx, vy - hy) : pack_bf16(vx, vy);
+                                }
+                                o = make_uint4(r[0], r[1], r[2], r[3]);
+                            } else if (SP == 0 && bb < p.B && l >= 0 && l < p.L && ch < p.Cin0) {
                                 const float s = p.up_scale * (float)l;
                                 const int i0 = (int)s;
                                 const int i1 = i0 + (i0 < p.Lin - 1 ? 1 : 0);
@@ -743,7 +795,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     int nt = tile, nc = c + 1;
                     for (int hop = 0; hop < p.nchunks; ++hop) {
                         if (nc >= p.nchunks) { nc = 0; nt += gridDim.x; }
-                        if (chunk_info<UPCAT, MG>(p, nc).up) break;
+                        if (chunk_info<UPCAT, MG, SP>(p, nc).up) break;
                         ++nc;
                     }
                     if (nt < total_tiles && unit_fast(nc)) {
@@ -797,6 +849,8 @@ struct TnParams {
     const float *x;
     float *y;
     const float *head_w, *head_b;
+    int dbg;                                   // development (WUNET_TN_DBG, -DWUNET_TN_DEBUG builds): selects a conv_tn_kernel<.., DBG> instantiation with one role
+                                               // switched off: 1 no tcgen05.ld, 2 no shuffles, 4 no stores, 8 no MMAs, 16 no TMA loads, 32 no producer work
 };
 struct TnSmem { uint32_t a, w, ss, bars; };
 __host__ __device__ inline TnSmem tn_smem_map(const TnParams &p)
@@ -808,7 +862,7 @@ __host__ __device__ inline TnSmem tn_smem_map(const TnParams &p)
     m.bars = (m.ss + (uint32_t)p.Cout * 8 + 64 * 4 + 15) & ~15u;
     return m;
 }
-inline size_t tn_smem_total(const TnParams &p) { return tn_smem_map(p).bars + 8 * (4 + 4 + 1 + 2 + 2) + 16 + 1024; }
+inline size_t tn_smem_total(const TnParams &p) { return tn_smem_map(p).bars + 8 * (8 + 8 + 1 + 2 + 2) + 16 + 1024; }
 
 __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&v)[8])
 {
@@ -821,7 +875,7 @@ __device__ __forceinline__ void mbar_arrive_n(uint32_t bar, uint32_t count)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
 
-template <bool UPCAT>
+template <bool UPCAT, int DBG>
 __global__ void __launch_bounds__(64 + 32 * (kEpiWarpsLarge + (UPCAT ? kProducerWarpsLarge : 0)), 1)
 conv_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TnParams p)
 {
@@ -831,10 +885,10 @@ conv_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint8_t *base_ptr = smem_raw + (base - smem_u32(smem_raw));
     const TnSmem sm = tn_smem_map(p);
     const uint32_t bars = base + sm.bars;
-    // barrier slots (8 B each): a_full[4] a_empty[4] w_full[1] acc_full[2] acc_empty[2] | tmem slot
-    const uint32_t a_full = bars, a_empty = bars + 32, w_full = bars + 64, acc_full = bars + 72, acc_empty = bars + 88;
-    const uint32_t tmem_slot = bars + 104;
-    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(base_ptr + sm.bars + 104);
+    // barrier slots (8 B each): a_full[8] a_empty[8] w_full[1] acc_full[2] acc_empty[2] | tmem slot
+    const uint32_t a_full = bars, a_empty = bars + 64, w_full = bars + 128, acc_full = bars + 136, acc_empty = bars + 152;
+    const uint32_t tmem_slot = bars + 168;
+    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(base_ptr + sm.bars + 168);
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int kFirstProducer = EW, kTmaWarp = EW + PW, kMmaWarp = kTmaWarp + 1;
@@ -843,7 +897,7 @@ conv_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
-        for (int s = 0; s < 4; ++s) {
+        for (int s = 0; s < 8; ++s) {
             mbar_init(a_full + 8 * s, UPCAT ? 1 + p.wpg : 1);
             mbar_init(a_empty + 8 * s, 1);
         }
@@ -891,11 +945,14 @@ conv_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint32_t sa = cnt % (uint32_t)p.na, pa = (cnt / (uint32_t)p.na) & 1u;
                     mbar_wait(a_empty + 8 * sa, pa ^ 1);
                     if (!p.c_up[c]) {
+                        if (DBG & 16) mbar_arrive(a_full + 8 * sa);
+                        else {
                         mbar_expect_tx(a_full + 8 * sa, (uint32_t)nblk * 4096u);
                         const uint32_t dst = base + sm.a + sa * p.a_stage_bytes;
                         const int lc = l0 - p.pad + p.c_row[c];
                         for (int k = 0; k < nblk; ++k)
                             tma_load_3d(dst + (uint32_t)k * 4096u, &tmA, a_full + 8 * sa, p.c_ch[c] * 64, lc + 28 * k, b0);
+                        }
                         if (UPCAT) mbar_arrive_n(a_full + 8 * sa, (uint32_t)p.wpg);     // the producers do not touch this stage
                     } else {
                         mbar_arrive(a_full + 8 * sa);                                   // the owning producer group completes it
@@ -924,7 +981,7 @@ conv_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint32_t b_lo = (((base + sm.w + (uint32_t)c * p.w_tile_bytes) >> 4) & 0x3FFFu) | (1u << 16);
                     const int nk = p.c_nk[c];
 #pragma unroll 1
-                    for (int mt = 0; mt < p.MT; ++mt) {
+                    for (int mt = 0; mt < ((DBG & 8) ? 0 : p.MT); ++mt) {
                         const uint32_t d = acc_col + (uint32_t)(mt * p.Nstride);
                         const uint32_t am = a_lo + (uint32_t)mt * 1024u;               // next 128 rows: 16 KB = 1024 sixteen-byte units
                         umma_bf16_lohi(d, am, b_lo, hi, idesc, c ? 1u : 0u);
@@ -971,25 +1028,34 @@ conv_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int cc = (p.MT > 1 ? 0 : half); cc < ncc; cc += (p.MT > 1 ? 1 : 2)) {
                     uint32_t v0[8], v1[8], v2[8], v3[8], v4[8];
                     const uint32_t col = taddr + (uint32_t)(8 * cc);
+                    if (DBG & 1) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) { v0[j] = col + j; v1[j] = col ^ j; v2[j] = col * j; v3[j] = col - j; v4[j] = j; }
+                    } else {
                     tmem_ld8_nowait(col, v0);
                     tmem_ld8_nowait(col + (uint32_t)p.Cp, v1);
                     tmem_ld8_nowait(col + (uint32_t)(2 * p.Cp), v2);
                     tmem_ld8_nowait(col + (uint32_t)(3 * p.Cp), v3);
                     tmem_ld8_nowait(col + (uint32_t)(4 * p.Cp), v4);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    }
                     float f[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         // out[row] = D'[row,0] + D'[row+1,1] + ... + D'[row+4,4]; lanes 28..31 end up incomplete and are not stored
                         float a = __uint_as_float(v4[j]);
+                        if (DBG & 2) {
+                            a = a + __uint_as_float(v3[j]) + __uint_as_float(v2[j]) + __uint_as_float(v1[j]) + __uint_as_float(v0[j]);
+                        } else {
                         a = __shfl_down_sync(0xffffffffu, a, 1) + __uint_as_float(v3[j]);
                         a = __shfl_down_sync(0xffffffffu, a, 1) + __uint_as_float(v2[j]);
                         a = __shfl_down_sync(0xffffffffu, a, 1) + __uint_as_float(v1[j]);
                         a = __shfl_down_sync(0xffffffffu, a, 1) + __uint_as_float(v0[j]);
+                        }
                         const float2 s2 = ss[8 * cc + j];
                         f[j] = lrelu(fmaf(a, s2.x, s2.y));
                     }
-                    if (p.out != nullptr && valid)
+                    if (p.out != nullptr && valid && !(DBG & 4))
                         *reinterpret_cast<uint4 *>(p.out + ((size_t)b0 * p.L + l) * p.Cout + 8 * cc) =
                             make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
                     if (p.head) {
@@ -997,7 +1063,7 @@ conv_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         for (int j = 0; j < 8; ++j) hacc = fmaf(hw[8 * cc + j], f[j], hacc);
                     }
                 }
-                if (p.head && valid) {
+                if (p.head && valid && !(DBG & 4)) {
                     // cat([o, input], 1) -> Conv1d(C+1 -> 1, k=1) -> Tanh   (model/unet_basic.py:98-99)
                     hacc = fmaf(hw[p.Cout], mt == 0 ? xin[0] : (mt == 1 ? xin[1] : (mt == 2 ? xin[2] : xin[3])), hacc);
                     p.y[(size_t)b0 * p.T + l] = tanh_fast(hacc);
@@ -1048,6 +1114,12 @@ conv_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             xr[qq] = chok ? __ldg(reinterpret_cast<const uint4 *>(pb + (size_t)m * p.Cin0)) : make_uint4(0u, 0u, 0u, 0u);
                         }
                     };
+                    if (DBG & 32) {
+                        mbar_wait(a_empty + 8 * sa, pa ^ 1);
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(a_full + 8 * sa);
+                        continue;
+                    }
                     if (pt < nitems) fetch(pt);                    // issued before the wait: DRAM latency overlaps it
                     mbar_wait(a_empty + 8 * sa, pa ^ 1);
                     const uint32_t stage = base + sm.a + sa * p.a_stage_bytes;
@@ -1123,7 +1195,7 @@ __global__ void pack_tn_kernel(const float *__restrict__ w, __nv_bfloat16 *__res
 // -------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256, 4) enc0_kernel(const float *__restrict__ x, const float *__restrict__ w /*[C][1][15]*/,
                                                       const float *__restrict__ scale, const float *__restrict__ shift,
-                                                      __nv_bfloat16 *__restrict__ out, int B, int T, int C)
+                                                      __nv_bfloat16 *__restrict__ out, int B, int T, int C, int split)
 {
     // A block owns 1024 consecutive positions of one frame; a thread owns 4 consecutive positions and sweeps the channels
     // 8 at a time (32 accumulators, 15 taps: 480 FFMA per 2x15 broadcast LDS.128 of weights). The bf16 rows are staged in
@@ -1134,7 +1206,8 @@ __global__ void __launch_bounds__(256, 4) enc0_kernel(const float *__restrict__ 
     float *ws = reinterpret_cast<float *>(smem_raw);          // [15][C]
     float *sc = ws + KS * C, *sh = sc + C;
     float *xs = sh + C + ((4 - ((KS * C + 2 * C) & 3)) & 3);  // keep xs 16-byte aligned
-    uint8_t *stage = reinterpret_cast<uint8_t *>(xs + TILE + 16);   // [TILE][C] bf16, 16-byte aligned
+    uint8_t *stage = reinterpret_cast<uint8_t *>(xs + TILE + 16);   // [TILE][C] bf16 ([TILE][2 C] = [hi | lo] in split-precision mode)
+    const int RC = split ? 2 * C : C;                                // channels per stored row
     const int b = blockIdx.y;
     const int l0 = blockIdx.x * TILE;
     for (int i = threadIdx.x; i < KS * C; i += 256) { const int k = i / C, c = i - k * C; ws[i] = w[c * KS + k]; }
@@ -1174,8 +1247,16 @@ __global__ void __launch_bounds__(256, 4) enc0_kernel(const float *__restrict__ 
             float f[8];
 #pragma unroll
             for (int m = 0; m < 8; ++m) f[m] = lrelu(fmaf(acc[j][m], sc[c0 + m], sh[c0 + m]));
-            *reinterpret_cast<uint4 *>(stage + (size_t)(4 * threadIdx.x + j) * (C * 2) + c0 * 2) =
+            uint8_t *srow = stage + (size_t)(4 * threadIdx.x + j) * (RC * 2) + c0 * 2;
+            *reinterpret_cast<uint4 *>(srow) =
                 make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+            if (split) {
+                float g[8];
+#pragma unroll
+                for (int m = 0; m < 8; ++m) g[m] = f[m] - __bfloat162float(__float2bfloat16_rn(f[m]));
+                *reinterpret_cast<uint4 *>(srow + C * 2) =
+                    make_uint4(pack_bf16(g[0], g[1]), pack_bf16(g[2], g[3]), pack_bf16(g[4], g[5]), pack_bf16(g[6], g[7]));
+            }
         }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -1183,7 +1264,7 @@ __global__ void __launch_bounds__(256, 4) enc0_kernel(const float *__restrict__ 
     if (threadIdx.x == 0) {
         const int rows = min(TILE, T - l0);
         asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                     ::"l"(out + ((size_t)b * T + l0) * C), "r"(smem_u32(stage)), "r"((uint32_t)(rows * C * 2)) : "memory");
+                     ::"l"(out + ((size_t)b * T + l0) * RC), "r"(smem_u32(stage)), "r"((uint32_t)(rows * RC * 2)) : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
@@ -1230,6 +1311,43 @@ __global__ void pack_tc_merged_kernel(const float *__restrict__ w, __nv_bfloat16
     wp[((size_t)t * Npad + co) * Ktot + (Ktot - 64) + j] = __float2bfloat16(v);
 }
 
+// split-precision ("fp32_tc") weights: K-loop position c of a block multiplies the data part (hi / lo) of one 64-channel chunk
+// with the high or the low bf16 part of the fp32 weights; SplitTable lists, per position, the first original input channel of
+// the chunk, its width and which weight part it takes. wp[t][co][c * 64 + j], zero beyond the chunk's width (the TMA box of a
+// chunk narrower than 64 channels reads on into the next channels of the row: they meet zero weights).
+struct SplitTable { short base[48]; unsigned char width[48], wlo[48]; int n; };
+__global__ void pack_tc_split_kernel(const float *__restrict__ w, __nv_bfloat16 *__restrict__ wp, int Cout, int Cin, int K, int Npad,
+                                     const SplitTable tab)
+{
+    const int Ktot = tab.n * 64;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)K * Npad * Ktot) return;
+    const int ks = (int)(i % Ktot);
+    const int co = (int)((i / Ktot) % Npad);
+    const int t = (int)(i / ((long long)Ktot * Npad));
+    const int c = ks >> 6, j = ks & 63;
+    float v = 0.f;
+    if (co < Cout && j < tab.width[c]) {
+        const float wf = w[((size_t)co * Cin + tab.base[c] + j) * K + t];
+        const float hi = __bfloat162float(__float2bfloat16_rn(wf));
+        v = tab.wlo[c] ? wf - hi : hi;
+    }
+    wp[i] = __float2bfloat16_rn(v);
+}
+
+// [B][L][2C] ([hi | lo] bf16 halves) -> [B][C][L] fp32 (read_level of the split-precision path)
+__global__ void nlc_split_to_ncl_f32_kernel(const __nv_bfloat16 *__restrict__ src, float *__restrict__ dst, int B, int L, int C)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n = (long long)B * C * L;
+    if (i >= n) return;
+    const int l = (int)(i % L);
+    const int c = (int)((i / L) % C);
+    const int b = (int)(i / ((long long)L * C));
+    const __nv_bfloat16 *row = src + ((size_t)b * L + l) * (2 * C);
+    dst[i] = __bfloat162float(row[c]) + __bfloat162float(row[C + c]);
+}
+
 __global__ void nlc_bf16_to_ncl_f32_kernel(const __nv_bfloat16 *__restrict__ src, float *__restrict__ dst, int B, int L, int C)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;       // index into dst [B][C][L]
@@ -1255,6 +1373,8 @@ struct TcLevel {
                                        // one extra 64-wide K slot at the end of the packed weights (0 = not merged)
     __nv_bfloat16 *wp = nullptr;
     float2 *ss = nullptr;
+    __nv_bfloat16 *wp_sp = nullptr;    // split-precision packing [K][Npad][sp_chunks * 64] (sp_chunk_order lists the K-loop positions)
+    int sp_chunks = 0;
     // taps-in-N variant (conv_tn_kernel): eligible blocks keep a second packed copy [tn_npad][tn_slots * 64]
     int tn_cp = 0, tn_npad = 0, tn_slots = 0, tn_groups = 0;      // 0 = not eligible
     __nv_bfloat16 *wp_tn = nullptr;
@@ -1262,6 +1382,8 @@ struct TcLevel {
     float *w_own = nullptr;            // enc0 only: [Cout][1][K] fp32 copy made by tc_set_weights (the caller's tensor is not read afterwards)
     const float *scale = nullptr, *shift = nullptr;
 };
+
+static int sp_chunk_order(const TcLevel &lv, bool dec, unsigned char *map, SplitTable *tab);
 
 struct TcPlanLevel {
     TcParams p;
@@ -1341,7 +1463,8 @@ struct TcState {
     bool attr_set = false;
     bool pdl = false;                  // programmatic dependent launch between the blocks (WUNET_TC_PDL=1); measured slower, off
     bool merge = true;                 // merged tail chunks (WUNET_TC_MERGE=0 switches them off for A/B measurements)
-    bool tn = true;                    // taps-in-N kernel for the shallow blocks (WUNET_TC_TN=0 switches it off for A/B measurements)
+    bool tn = false;                   // taps-in-N kernel for the shallow blocks: correct but not yet faster than conv_tc_kernel on a B200
+                                       // (profiles/r02_tn_*.txt), so opt-in: WUNET_TC_TN=1
     int num_sms = 148;
     cudaStream_t copy_in = nullptr, copy_out = nullptr;     // host pipeline: H2D / D2H streams
     cudaEvent_t ev_in[8] = {}, ev_out[8] = {};
@@ -1353,12 +1476,13 @@ struct TcState {
     const float *plan_x = nullptr;
     float *plan_y = nullptr;
     std::string plan_ovr;              // WUNET_TC_OVR value the cached plan was built with
+    int plan_mode = 0;                 // 0: bf16 plan, 1: split-precision (fp32_tc) plan
     TcPlan plan;
 };
 
 const char *tc_error() { return g_tc_err; }
 
-static void tc_layout(int n, int ci, int B, int T, std::vector<size_t> &off, size_t &total)
+static void tc_layout(int n, int ci, int B, int T, std::vector<size_t> &off, size_t &total, int mode = 0)
 {
     off.resize(2 * n + 1);
     size_t cur = 0;
@@ -1366,16 +1490,16 @@ static void tc_layout(int n, int ci, int B, int T, std::vector<size_t> &off, siz
         const int L = (i <= n) ? (T >> i) : (T >> (2 * n - i));
         const int cout = (i < n) ? (i + 1) * ci : (i == n ? n * ci : (2 * n - i + 1) * ci);
         off[i] = cur;
-        cur += round_up_sz((size_t)B * L * cout * sizeof(__nv_bfloat16), 1024);
+        cur += round_up_sz((size_t)B * L * cout * sizeof(__nv_bfloat16) * (mode ? 2 : 1), 1024);
     }
     total = cur + 1024;
 }
 
-size_t tc_workspace_bytes(int n, int ci, int B, int T)
+size_t tc_workspace_bytes(int n, int ci, int B, int T, int mode)
 {
     std::vector<size_t> off;
     size_t total;
-    tc_layout(n, ci, B, T, off, total);
+    tc_layout(n, ci, B, T, off, total, mode);
     return total;
 }
 
@@ -1430,7 +1554,7 @@ int tc_set_weights(TcState **pst, int n, int ci, const TcBlockSrc *blocks, int n
         const char *pe = getenv("WUNET_TC_PDL");
         st->pdl = pe && pe[0] == '1';
         if (const char *xe = getenv("WUNET_TC_MERGE")) st->merge = xe[0] != '0';
-        if (const char *xe = getenv("WUNET_TC_TN")) st->tn = xe[0] != '0';
+        if (const char *xe = getenv("WUNET_TC_TN")) st->tn = xe[0] == '1';
 #ifdef WUNET_TC_TRACE
         if (const char *tl = getenv("WUNET_TC_TRACE_LEVEL")) {
             st->trace_level = atoi(tl);
@@ -1464,6 +1588,16 @@ int tc_set_weights(TcState **pst, int n, int ci, const TcBlockSrc *blocks, int n
         pack_tc_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, stream>>>(blocks[i].w, blocks[i].scale, blocks[i].shift, lv.wp,
                                                                           lv.ss, lv.cout, lv.cin0, lv.cin1, lv.k, lv.Npad, lv.Ktot);
         if (cudaGetLastError() != cudaSuccess) return tc_fail("pack_tc_kernel launch failed");
+        {
+            // split-precision packing (fp32_tc): [K][Npad][positions * 64] in the split K-loop order
+            SplitTable tab;
+            lv.sp_chunks = sp_chunk_order(lv, i > n, nullptr, &tab);
+            const size_t ns = (size_t)lv.k * lv.Npad * lv.sp_chunks * 64;
+            if (!lv.wp_sp && cudaMalloc(&lv.wp_sp, ns * sizeof(__nv_bfloat16)) != cudaSuccess) return tc_fail("cudaMalloc(wp_sp) failed");
+            pack_tc_split_kernel<<<(unsigned)((ns + 255) / 256), 256, 0, stream>>>(blocks[i].w, lv.wp_sp, lv.cout, lv.cin0 + lv.cin1, lv.k,
+                                                                                  lv.Npad, tab);
+            if (cudaGetLastError() != cudaSuccess) return tc_fail("pack_tc_split_kernel launch failed");
+        }
         if (lv.tn_slots) {
             const size_t nt = (size_t)lv.tn_npad * lv.tn_slots * 64;
             if (!lv.wp_tn && cudaMalloc(&lv.wp_tn, nt * sizeof(__nv_bfloat16)) != cudaSuccess) return tc_fail("cudaMalloc(wp_tn) failed");
@@ -1511,9 +1645,44 @@ static int make_map(TcState *st, CUtensorMap *m, const void *base, uint64_t d0, 
     return 0;
 }
 
+// K-loop order of a block in split-precision mode: three passes over the single-precision order (encoders: natural; decoders:
+// full upsampled chunks, skip chunks, partial upsampled chunk - or the partial one first if it is the only one): hi data x
+// w_hi, lo data x w_hi, hi data x w_lo. Fills chunk_map bytes (bit 7 upsampled segment, bit 6 low data part, bits 0-5 chunk
+// index) and the table the weight packing follows. Returns the number of positions.
+static int sp_chunk_order(const TcLevel &lv, bool dec, unsigned char *map, SplitTable *tab)
+{
+    unsigned char one[16];
+    int k = 0;
+    const int n0 = (lv.cin0 + 63) / 64, n1 = (lv.cin1 + 63) / 64, nfull0 = lv.cin0 / 64;
+    if (!dec) { for (int c = 0; c < n0; ++c) one[k++] = (unsigned char)c; }
+    else if (nfull0 == 0) {
+        one[k++] = 0x80;
+        for (int c = 0; c < n1; ++c) one[k++] = (unsigned char)c;
+    } else {
+        for (int c = 0; c < nfull0; ++c) one[k++] = (unsigned char)(0x80 | c);
+        for (int c = 0; c < n1; ++c) one[k++] = (unsigned char)c;
+        if (nfull0 < n0) one[k++] = (unsigned char)(0x80 | nfull0);
+    }
+    int n = 0;
+    for (int pass = 0; pass < 3; ++pass)
+        for (int c = 0; c < k; ++c, ++n) {
+            const bool up = dec && (one[c] & 0x80);
+            const int idx = one[c] & 0x3f;
+            if (map) map[n] = (unsigned char)(one[c] | (pass == 1 ? 0x40 : 0));
+            if (tab) {
+                const int seg = (up || !dec) ? lv.cin0 : lv.cin1;
+                tab->base[n] = (short)(((up || !dec) ? 0 : lv.cin0) + 64 * idx);
+                tab->width[n] = (unsigned char)std::min(64, seg - 64 * idx);
+                tab->wlo[n] = (unsigned char)(pass == 2);
+            }
+        }
+    if (tab) tab->n = n;
+    return n;
+}
+
 // Tiling decision for conv block i: pure host logic (no CUDA calls), so that tests can exercise it without a GPU
 // (wunet_debug_plan). Fills every tiling field of P.p and the launch shape; pointers and tensor maps are added by build_plan.
-static int plan_block(const TcLevel &lv, int i, int n, int B, int T, int num_sms, const std::string &ovr, TcPlanLevel &P)
+static int plan_block(const TcLevel &lv, int i, int n, int B, int T, int num_sms, const std::string &ovr, TcPlanLevel &P, bool sp = false)
 {
     TcParams &p = P.p;
     memset(&p, 0, sizeof(p));
@@ -1530,7 +1699,10 @@ static int plan_block(const TcLevel &lv, int i, int n, int B, int T, int num_sms
         // K-loop order. Encoders: natural. Decoders: full upsampled chunks, then the skip chunks (TMA), then the partial
         // upsampled chunk: a TMA chunk is never preceded by a short chunk, so its load latency hides behind MMAs.
         int k = 0;
-        if (!dec) { for (int c = 0; c < p.nchunks; ++c) p.chunk_map[k++] = (unsigned char)c; }
+        if (sp) {
+            p.split = 1;
+            p.nchunks = sp_chunk_order(lv, dec, p.chunk_map, nullptr);
+        } else if (!dec) { for (int c = 0; c < p.nchunks; ++c) p.chunk_map[k++] = (unsigned char)c; }
         else if (lv.mg_s && L >= 128) {
             // experimental: [full upsampled chunks][full skip chunks][skip tail | upsampled tail] - one chunk fewer
             const int nfull0 = lv.cin0 / 64, nfull1 = lv.cin1 / 64;
@@ -1556,14 +1728,14 @@ static int plan_block(const TcLevel &lv, int i, int n, int B, int T, int num_sms
                 if (nfull0 < p.nchunks0) p.chunk_map[k++] = (unsigned char)(0x80 | nfull0);
             }
         }
-        if (p.nchunks > 16) return tc_fail("too many K chunks");
+        if (p.nchunks > 48) return tc_fail("too many K chunks");
     }
     // ---- tiling ---------------------------------------------------------------------------------
     TcOverride ov = parse_override(ovr, i);
-    if (!ov.any && B >= 128)
+    if (!ov.any && B >= 128 && !sp)
         for (const TunedTiling &t : kTuned)
             if (t.L == L && t.cin0 == lv.cin0 && t.cin1 == lv.cin1 && t.cout == lv.cout && t.k == KS) parse_kv(t.kv, ov);
-    const bool small = ov.small > 0;
+    const bool small = ov.small > 0 && !sp;
     const int smem_limit = small ? kSmemLimitSmall : kSmemLimit;
     const int tmem_limit = small ? 256 : 512;
     P.small = small;
@@ -1686,7 +1858,7 @@ static int plan_block(const TcLevel &lv, int i, int n, int B, int T, int num_sms
         if (!ok) return tc_fail("level %d does not fit in shared memory", i);
         if (ov.any && p.na < 2) return tc_fail("level %d: override leaves a single input stage", i);
     }
-    if (!packed && p.nsplit == 1 && ov.bulk != 0 && i != 2 * n && (L % (128 * p.MT) == 0) && (long long)B * L < (1LL << 31)) {
+    if (!sp && !packed && p.nsplit == 1 && ov.bulk != 0 && i != 2 * n && (L % (128 * p.MT) == 0) && (long long)B * L < (1LL << 31)) {
         // TMA-store epilogue if the slabs fit without giving up ring depth / residency / tile size
         const int need = p.n_epi * 2048 + 1024;
         const int min_nb = p.resident ? p.nb : (p.tg == 1 ? 4 : 2);
@@ -1753,7 +1925,8 @@ static bool plan_block_tn(const TcLevel &lv, int i, int n, int B, int T, int num
     t.w_tile_bytes = (uint32_t)round_up(t.Npad * 128, 1024);
     const int budget = kSmemLimit - 2048 - t.Cout * 8 - 512 - t.nchunks * (int)t.w_tile_bytes;
     int na = budget / (int)t.a_stage_bytes;
-    if (na > 4) na = 4;
+    if (na > 8) na = 8;
+    if (const char *e = getenv("WUNET_TN_NA")) na = std::min(na, std::max(2, atoi(e)));
     if (na < 2) return false;
     t.na = na;
     t.tmem_cols = 512;
@@ -1780,19 +1953,21 @@ static bool plan_block_tn(const TcLevel &lv, int i, int n, int B, int T, int num
     return true;
 }
 
-static int build_plan(TcState *st, const float *x, float *y, int B, int T, void *ws)
+static int build_plan(TcState *st, const float *x, float *y, int B, int T, void *ws, int mode)
 {
     const int n = st->n;
     TcPlan &pl = st->plan;
     size_t total;
-    tc_layout(n, st->ci, B, T, pl.off, total);
+    tc_layout(n, st->ci, B, T, pl.off, total, mode);
     pl.lv.assign(2 * n + 1, TcPlanLevel{});
+    const bool sp = mode != 0;
+    const uint64_t cm = sp ? 2 : 1;                      // stored channels per logical channel ([hi | lo] halves)
     char *base = static_cast<char *>(ws);
     auto lvl = [&](int i) { return reinterpret_cast<__nv_bfloat16 *>(base + pl.off[i]); };
     for (int i = 1; i < 2 * n + 1; ++i) {
         const TcLevel &lv = st->levels[i];
         TcPlanLevel &P = pl.lv[i];
-        if (parse_override(st->plan_ovr, i).any == false && plan_block_tn(lv, i, n, B, T, st->num_sms, P)) {
+        if (!sp && parse_override(st->plan_ovr, i).any == false && plan_block_tn(lv, i, n, B, T, st->num_sms, P)) {
             TnParams &t = P.tn;
             const bool dec = i > n;
             const bool last = (i == 2 * n);
@@ -1815,7 +1990,7 @@ static int build_plan(TcState *st, const float *x, float *y, int B, int T, void 
             P.tmO = P.tmA;
             continue;
         }
-        if (plan_block(lv, i, n, B, T, st->num_sms, st->plan_ovr, P)) return -1;
+        if (plan_block(lv, i, n, B, T, st->num_sms, st->plan_ovr, P, sp)) return -1;
         TcParams &p = P.p;
         const bool dec = i > n;
         const int L = p.L;
@@ -1830,19 +2005,20 @@ static int build_plan(TcState *st, const float *x, float *y, int B, int T, void 
             // decimated view of the previous encoder output: element (c, l, b) -> prev[b][2l][c]   (o[:, :, ::2])
             const int Cp = lv.cin0, Lp = 2 * L;
             const uint32_t b1 = p.packed ? (uint32_t)p.S : (uint32_t)p.R1, b2 = p.packed ? (uint32_t)p.FR : 1u;
-            if (make_map(st, &P.tmA, lvl(i - 1), Cp, L, B, (uint64_t)2 * Cp * 2, (uint64_t)Lp * Cp * 2, 64, b1, b2)) return -1;
+            if (make_map(st, &P.tmA, lvl(i - 1), cm * Cp, L, B, (uint64_t)2 * cm * Cp * 2, (uint64_t)Lp * cm * Cp * 2, 64, b1, b2)) return -1;
         } else {
             const int e = 2 * n - i;                        // skip = encoder e's full-resolution output
             const int Cs = lv.cin1;
             const uint32_t b1 = p.packed ? (uint32_t)p.S : (uint32_t)p.R1, b2 = p.packed ? (uint32_t)p.FR : 1u;
-            if (make_map(st, &P.tmA, lvl(e), Cs, L, B, (uint64_t)Cs * 2, (uint64_t)L * Cs * 2, 64, b1, b2)) return -1;
+            if (make_map(st, &P.tmA, lvl(e), cm * Cs, L, B, (uint64_t)cm * Cs * 2, (uint64_t)L * cm * Cs * 2, 64, b1, b2)) return -1;
             p.prev = lvl(i - 1);
             p.Lin = L / 2;
             p.up_scale = (L > 1) ? (float)(p.Lin - 1) / (float)(L - 1) : 0.f;
         }
-        if (p.out != nullptr) { if (make_map_out(st, &P.tmO, p.out, (uint64_t)lv.cout, (uint64_t)B * L)) return -1; }
+        if (p.out != nullptr && !sp) { if (make_map_out(st, &P.tmO, p.out, (uint64_t)lv.cout, (uint64_t)B * L)) return -1; }
         else P.tmO = P.tmA;
-        if (make_map(st, &P.tmW, lv.wp, lv.Ktot, lv.Npad, lv.k, (uint64_t)lv.Ktot * 2, (uint64_t)lv.Npad * lv.Ktot * 2, 64,
+        const uint64_t ktot = sp ? (uint64_t)lv.sp_chunks * 64 : (uint64_t)lv.Ktot;
+        if (make_map(st, &P.tmW, sp ? lv.wp_sp : lv.wp, ktot, lv.Npad, lv.k, ktot * 2, (uint64_t)lv.Npad * ktot * 2, 64,
                      (uint32_t)p.Nh, (uint32_t)p.tg))
             return -1;
     }
@@ -1860,7 +2036,7 @@ static int build_plan(TcState *st, const float *x, float *y, int B, int T, void 
                     p.m_tiles * p.nsplit, pl.lv[i].grid.x, (int)pl.lv[i].small, pl.lv[i].per_sm);
         }
     }
-    st->plan_ws = ws; st->plan_B = B; st->plan_T = T; st->plan_x = x; st->plan_y = y;
+    st->plan_ws = ws; st->plan_B = B; st->plan_T = T; st->plan_x = x; st->plan_y = y; st->plan_mode = mode;
     return 0;
 }
 
@@ -1872,7 +2048,7 @@ int tc_debug_plan(int n, int ci, const TcBlockSrc *blocks, int nblocks, int B, i
     std::vector<TcLevel> levels(nblocks);
     const char *mge = getenv("WUNET_TC_MERGE");
     const char *tne = getenv("WUNET_TC_TN");
-    derive_levels(levels, blocks, nblocks, n, !(mge && mge[0] == '0'), !(tne && tne[0] == '0'));
+    derive_levels(levels, blocks, nblocks, n, !(mge && mge[0] == '0'), tne && tne[0] == '1');
     const char *ovr = getenv("WUNET_TC_OVR");
     TcPlanLevel P{};
     const std::string ovr_s = ovr ? ovr : "";
@@ -1887,7 +2063,7 @@ int tc_debug_plan(int n, int ci, const TcBlockSrc *blocks, int nblocks, int B, i
     return 0;
 }
 
-static int tc_prepare(TcState *st, const float *x, float *y, int B, int T, void *ws)
+static int tc_prepare(TcState *st, const float *x, float *y, int B, int T, void *ws, int mode)
 {
     if (!st) return tc_fail("tensor-core state missing");
     const int ci = st->ci;
@@ -1899,9 +2075,15 @@ static int tc_prepare(TcState *st, const float *x, float *y, int B, int T, void 
         cudaFuncSetAttribute(conv_tc_kernel<5, true, kEpiWarpsSmall, kProducerWarpsSmall, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         cudaFuncSetAttribute(conv_tc_kernel<5, true, kEpiWarpsLarge, kProducerWarpsLarge, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         cudaFuncSetAttribute(conv_tc_kernel<5, true, kEpiWarpsSmall, kProducerWarpsSmall, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
-        cudaFuncSetAttribute(conv_tn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
-        cudaFuncSetAttribute(conv_tn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
-        cudaFuncSetAttribute(enc0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        cudaFuncSetAttribute(conv_tc_kernel<5, true, kEpiWarpsLarge, kProducerWarpsLarge, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+        cudaFuncSetAttribute(conv_tc_kernel<15, false, kEpiWarpsLarge, 0, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+        cudaFuncSetAttribute(conv_tn_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+        cudaFuncSetAttribute(conv_tn_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+#ifdef WUNET_TN_DEBUG
+#define TN_ATTR(D) cudaFuncSetAttribute(conv_tn_kernel<true, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit); cudaFuncSetAttribute(conv_tn_kernel<false, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+        TN_ATTR(1) TN_ATTR(2) TN_ATTR(4) TN_ATTR(8) TN_ATTR(16) TN_ATTR(32) TN_ATTR(3) TN_ATTR(7) TN_ATTR(24) TN_ATTR(56) TN_ATTR(63)
+#endif
+        cudaFuncSetAttribute(enc0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         int dev = 0, sms = 0;
         if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
             st->num_sms = sms;
@@ -1910,10 +2092,10 @@ static int tc_prepare(TcState *st, const float *x, float *y, int B, int T, void 
     (void)x; (void)y;
     const char *ovr = getenv("WUNET_TC_OVR");
     const std::string ovr_s = ovr ? ovr : "";
-    if (st->plan_ws != ws || st->plan_B != B || st->plan_T != T || st->plan_ovr != ovr_s) {
+    if (st->plan_ws != ws || st->plan_B != B || st->plan_T != T || st->plan_ovr != ovr_s || st->plan_mode != mode) {
         st->plan_ovr = ovr_s;
         st->plan_ws = nullptr;
-        if (build_plan(st, nullptr, nullptr, B, T, ws)) return -1;
+        if (build_plan(st, nullptr, nullptr, B, T, ws, mode)) return -1;
     }
     return 0;
 }
@@ -1923,7 +2105,9 @@ static int launch_enc0(TcState *st, const float *x, int f0, int nf, int T, void 
 {
     const TcLevel &lv = st->levels[0];
     const int C = lv.cout;
-    const size_t smem = (size_t)(15 * C + 2 * C + 4 + 1024 + 16) * sizeof(float) + (size_t)1024 * C * 2 + 16;
+    const int split = st->plan_mode != 0 ? 1 : 0;
+    const int RC = split ? 2 * C : C;
+    const size_t smem = (size_t)(15 * C + 2 * C + 4 + 1024 + 16) * sizeof(float) + (size_t)1024 * RC * 2 + 16;
     dim3 grid((unsigned)((T + 1023) / 1024), (unsigned)nf, 1);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid; cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
@@ -1932,7 +2116,7 @@ static int launch_enc0(TcState *st, const float *x, int f0, int nf, int T, void 
     attr[0].val.programmaticStreamSerializationAllowed = st->pdl ? 1 : 0;
     cfg.attrs = attr; cfg.numAttrs = 1;
     __nv_bfloat16 *out0 = reinterpret_cast<__nv_bfloat16 *>(static_cast<char *>(ws) + st->plan.off[0]);
-    cudaLaunchKernelEx(&cfg, enc0_kernel, x + (size_t)f0 * T, lv.w_src, lv.scale, lv.shift, out0 + (size_t)f0 * T * C, nf, T, C);
+    cudaLaunchKernelEx(&cfg, enc0_kernel, x + (size_t)f0 * T, lv.w_src, lv.scale, lv.shift, out0 + (size_t)f0 * T * RC, nf, T, C, split);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return tc_fail("enc0 launch failed: %s", cudaGetErrorString(e));
     return 0;
@@ -1954,8 +2138,17 @@ static int launch_block(TcState *st, int i, int t0, int t1, cudaStream_t stream,
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = st->pdl ? 1 : 0;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        if (P.upcat) cudaLaunchKernelEx(&cfg, conv_tn_kernel<true>, P.tmA, P.tmW, t);
-        else cudaLaunchKernelEx(&cfg, conv_tn_kernel<false>, P.tmA, P.tmW, t);
+#ifdef WUNET_TN_DEBUG
+#define TN_CASE(D) case D: if (P.upcat) cudaLaunchKernelEx(&cfg, conv_tn_kernel<true, D>, P.tmA, P.tmW, t); else cudaLaunchKernelEx(&cfg, conv_tn_kernel<false, D>, P.tmA, P.tmW, t); break;
+        if (const char *de = getenv("WUNET_TN_DBG")) t.dbg = atoi(de);
+        switch (t.dbg) { TN_CASE(1) TN_CASE(2) TN_CASE(4) TN_CASE(8) TN_CASE(16) TN_CASE(32) TN_CASE(3) TN_CASE(7) TN_CASE(24) TN_CASE(56) TN_CASE(63)
+        default:
+#endif
+        if (P.upcat) cudaLaunchKernelEx(&cfg, conv_tn_kernel<true, 0>, P.tmA, P.tmW, t);
+        else cudaLaunchKernelEx(&cfg, conv_tn_kernel<false, 0>, P.tmA, P.tmW, t);
+#ifdef WUNET_TN_DEBUG
+        }
+#endif
         const cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return tc_fail("conv_tn level %d launch failed: %s", i, cudaGetErrorString(e));
         return 0;
@@ -1971,7 +2164,10 @@ static int launch_block(TcState *st, int i, int t0, int t1, cudaStream_t stream,
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = st->pdl ? 1 : 0;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    if (P.upcat && p.mg) {
+    if (p.split) {
+        if (P.upcat) cudaLaunchKernelEx(&cfg, conv_tc_kernel<5, true, kEpiWarpsLarge, kProducerWarpsLarge, 0, 1>, P.tmA, P.tmW, P.tmO, p);
+        else cudaLaunchKernelEx(&cfg, conv_tc_kernel<15, false, kEpiWarpsLarge, 0, 0, 1>, P.tmA, P.tmW, P.tmO, p);
+    } else if (P.upcat && p.mg) {
         if (!P.small) cudaLaunchKernelEx(&cfg, conv_tc_kernel<5, true, kEpiWarpsLarge, kProducerWarpsLarge, 1>, P.tmA, P.tmW, P.tmO, p);
         else cudaLaunchKernelEx(&cfg, conv_tc_kernel<5, true, kEpiWarpsSmall, kProducerWarpsSmall, 1>, P.tmA, P.tmW, P.tmO, p);
     } else if (P.upcat && !P.small) cudaLaunchKernelEx(&cfg, conv_tc_kernel<5, true, kEpiWarpsLarge, kProducerWarpsLarge, 0>, P.tmA, P.tmW, P.tmO, p);
@@ -1984,9 +2180,9 @@ static int launch_block(TcState *st, int i, int t0, int t1, cudaStream_t stream,
 }
 
 int tc_forward(TcState *st, const float *x, float *y, int B, int T, void *ws, cudaStream_t stream, int *launches,
-               cudaEvent_t *ev)
+               cudaEvent_t *ev, int mode)
 {
-    if (tc_prepare(st, x, y, B, T, ws)) return -1;
+    if (tc_prepare(st, x, y, B, T, ws, mode)) return -1;
     const int n = st->n;
     int nl = 0;
     if (ev) cudaEventRecord(ev[0], stream);
@@ -2006,9 +2202,9 @@ int tc_forward(TcState *st, const float *x, float *y, int B, int T, void *ws, cu
 // Host-buffer pipeline (enhancement.py:64-66 form): the first kernel (enc0) and the last (decoder + fused head) run per
 // batch chunk, so the H2D copy of chunk c+1 overlaps enc0 of chunk c and the D2H copy of chunk c overlaps the head of c+1.
 int tc_forward_host(TcState *st, const float *x_host, float *y_host, float *x_dev, float *y_dev, int B, int T, void *ws,
-                    cudaStream_t stream, int *launches)
+                    cudaStream_t stream, int *launches, int mode)
 {
-    if (tc_prepare(st, x_dev, y_dev, B, T, ws)) return -1;
+    if (tc_prepare(st, x_dev, y_dev, B, T, ws, mode)) return -1;
     const int n = st->n;
     const TcParams &pl = st->plan.lv[2 * n].p;
     int nc = 1;
@@ -2053,7 +2249,7 @@ int tc_forward_host(TcState *st, const float *x_host, float *y_host, float *x_de
     return 0;
 }
 
-int tc_read_level(TcState *st, int block, const void *ws, int B, int T, float *out_ncl, cudaStream_t stream)
+int tc_read_level(TcState *st, int block, const void *ws, int B, int T, float *out_ncl, cudaStream_t stream, int mode)
 {
     if (!st) return tc_fail("tensor-core state missing");
     const int n = st->n;
@@ -2061,12 +2257,13 @@ int tc_read_level(TcState *st, int block, const void *ws, int B, int T, float *o
         return tc_fail("the last decoder block is fused with the head and not materialised (set WUNET_TC_STORE_LAST=1)");
     std::vector<size_t> off;
     size_t total;
-    tc_layout(n, st->ci, B, T, off, total);
+    tc_layout(n, st->ci, B, T, off, total, mode);
     const int L = (block <= n) ? (T >> block) : (T >> (2 * n - block));
     const int C = st->levels[block].cout;
     const long long nel = (long long)B * C * L;
-    nlc_bf16_to_ncl_f32_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, stream>>>(
-        reinterpret_cast<const __nv_bfloat16 *>(static_cast<const char *>(ws) + off[block]), out_ncl, B, L, C);
+    const __nv_bfloat16 *src = reinterpret_cast<const __nv_bfloat16 *>(static_cast<const char *>(ws) + off[block]);
+    if (mode) nlc_split_to_ncl_f32_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, stream>>>(src, out_ncl, B, L, C);
+    else nlc_bf16_to_ncl_f32_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, stream>>>(src, out_ncl, B, L, C);
     return cudaGetLastError() == cudaSuccess ? 0 : tc_fail("read_level launch failed");
 }
 
@@ -2089,7 +2286,7 @@ void tc_destroy(TcState *st)
         }
         cudaFree(st->trace);
     }
-    for (auto &lv : st->levels) { cudaFree(lv.wp); cudaFree(lv.ss); cudaFree(lv.w_own); cudaFree(lv.wp_tn); }
+    for (auto &lv : st->levels) { cudaFree(lv.wp); cudaFree(lv.ss); cudaFree(lv.w_own); cudaFree(lv.wp_tn); cudaFree(lv.wp_sp); }
     delete st;
 }
 

@@ -1,6 +1,12 @@
 // wunet_train.cu — training step of the Wave-U-Net: forward with BatchNorm1d in training mode and the
-// backward pass, fp32, NCL layout, straight CUDA-core kernels written for correctness first (one formula per kernel, in the
-// order autograd would replay them); validated on a B200 against float64 golden steps (tests/test_train_gpu.py).
+// backward pass, fp32, NCL layout, CUDA cores (one formula per kernel, in the order autograd would replay them); validated on a
+// B200 against float64 golden steps (tests/test_train_gpu.py). The three convolution-shaped passes carry ~99 % of the work:
+//   forward conv and input gradient  -> the tuned fp32 kernels of wunet_fp32.cu (sliding-window / implicit GEMM) with a linear
+//                                       epilogue; the input gradient is the same convolution with the weights transposed and
+//                                       flipped, read from dz (train_pack_kernel writes both packings every step);
+//   weight gradient                  -> train_wgrad_kernel below (register-tiled reduction over (batch, position) tiles staged in
+//                                       shared memory, split over the batch, combined with atomicAdd).
+// The naive one-thread-per-output kernels they replace are kept as WUNET_TRAIN_NAIVE=1 (cross-check, tests).
 //
 // Reference: trainer/trainer.py:34-38 (forward, loss.backward()), model/unet_basic.py:77-100 with the BatchNorm1d of
 // :12, :25, :55 in .train() mode (batch statistics; running statistics updated with momentum 0.1 and the unbiased variance).
@@ -12,6 +18,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 namespace wunet {
@@ -344,6 +351,95 @@ __global__ void train_upsample_adjoint_kernel(const float *__restrict__ din, flo
     g_prev[i] = acc;
 }
 
+// both packings of a block's weights, every step (the parameters change every step):
+//   wf[(ci*K + k)*Cout + co] = w[co][ci][k]            forward conv, operand layout of wunet_fp32.cu
+//   wb[(co*K + k)*Cin + ci]  = w[co][ci][K-1-k]        input gradient = conv of dz with the transposed, flipped weights
+__global__ void train_pack_kernel(const float *__restrict__ w, float *__restrict__ wf, float *__restrict__ wb, int Cout, int Cin, int K)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)Cout * Cin * K) return;
+    const int k = (int)(i % K);
+    const int ci = (int)((i / K) % Cin);
+    const int co = (int)(i / ((long long)K * Cin));
+    const float v = w[i];
+    wf[((size_t)ci * K + k) * Cout + co] = v;
+    wb[((size_t)co * K + (K - 1 - k)) * Cin + ci] = v;
+}
+
+__global__ void train_fill_kernel(float *__restrict__ p, float v, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// dW[co][ci][k] = sum_b sum_l dz[b][co][l] * in(b, ci, l + k - pad).
+// Block = 16 co x 64 ci; thread = 2 co x 2 ci x KS taps of accumulators (a warp shares its co pair: dz reads are broadcasts;
+// its lanes own ci = lane and lane + 32: conflict-free rows). The reduction runs over tiles of `lt` positions of one frame,
+// staged in shared memory (the block input is built on the fly by fetch_src: decimate / interpolate + cat), 4 positions per
+// inner step: 2 x (4 + KS - 1) + 8 shared loads for 16 KS FFMA. gridDim.z slices of the (frame, tile) list are combined
+// with atomicAdd (dW is zeroed first).
+template <int KS, int MODE>
+__global__ void __launch_bounds__(256) train_wgrad_kernel(const ConvArgs a, const float *__restrict__ dz, float *__restrict__ dw, int lt)
+{
+    constexpr int PAD = (KS - 1) / 2, CO_T = 16, CI_T = 64, LT_MAX = 128;
+    constexpr int XP = LT_MAX + KS - 1 + ((LT_MAX + KS - 1) % 2 == 0 ? 1 : 0);      // odd row pitch
+    __shared__ float xs[CI_T][XP];
+    __shared__ float ds[CO_T][LT_MAX];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int co0 = blockIdx.x * CO_T, ci0 = blockIdx.y * CI_T;
+    const int tiles_per_frame = (a.L + lt - 1) / lt;
+    const int ntiles = a.B * tiles_per_frame;
+    float acc[2][2][KS];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int k = 0; k < KS; ++k) acc[i][j][k] = 0.f;
+    const int xw = lt + KS - 1;
+    for (int t = blockIdx.z; t < ntiles; t += gridDim.z) {
+        const int b = t / tiles_per_frame;
+        const int l0 = (t - b * tiles_per_frame) * lt;
+        __syncthreads();
+        for (int i = tid; i < CI_T * xw; i += 256) {
+            const int ci = i / xw, j = i - ci * xw;
+            xs[ci][j] = (ci0 + ci < a.Cin) ? fetch_src<MODE>(a, b, ci0 + ci, l0 - PAD + j) : 0.f;
+        }
+        for (int i = tid; i < CO_T * lt; i += 256) {
+            const int co = i / lt, j = i - co * lt;
+            ds[co][j] = (co0 + co < a.Cout && l0 + j < a.L) ? __ldg(dz + ((size_t)b * a.Cout + co0 + co) * a.L + l0 + j) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int l = 0; l < lt; l += 4) {
+            float x0[4 + KS - 1], x1[4 + KS - 1], d0[4], d1[4];
+#pragma unroll
+            for (int j = 0; j < 4 + KS - 1; ++j) { x0[j] = xs[lane][l + j]; x1[j] = xs[lane + 32][l + j]; }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { d0[j] = ds[2 * warp][l + j]; d1[j] = ds[2 * warp + 1][l + j]; }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int k = 0; k < KS; ++k) {
+                    acc[0][0][k] = fmaf(d0[j], x0[j + k], acc[0][0][k]);
+                    acc[0][1][k] = fmaf(d0[j], x1[j + k], acc[0][1][k]);
+                    acc[1][0][k] = fmaf(d1[j], x0[j + k], acc[1][0][k]);
+                    acc[1][1][k] = fmaf(d1[j], x1[j + k], acc[1][1][k]);
+                }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int co = co0 + 2 * warp + i, ci = ci0 + lane + 32 * j;
+            if (co < a.Cout && ci < a.Cin) {
+#pragma unroll
+                for (int k = 0; k < KS; ++k) atomicAdd(dw + ((size_t)co * a.Cin + ci) * KS + k, acc[i][j][k]);
+            }
+        }
+}
+
 struct Shape { int cin, cout, k, L, mode, cin0, cin1; };
 
 void shapes_of(int n, int ci, int T, std::vector<Shape> &sh)
@@ -361,22 +457,26 @@ void shapes_of(int n, int ci, int T, std::vector<Shape> &sh)
 struct Layout {
     std::vector<size_t> z, act, ga;      // float offsets of the pre-BN outputs, activations, activation gradients
     std::vector<size_t> mean, invstd, s1, s2;
-    size_t din, total;
+    std::vector<size_t> wf, wb;          // the step's packed weights: forward / input-gradient operand layouts
+    size_t din, ones, zeros, total;      // ones / zeros: [kMaxC] identity scale and zero shift for the linear conv epilogue
 };
+constexpr int kMaxC = 2048;
 
 void layout_of(const std::vector<Shape> &sh, int B, Layout &lo)
 {
     const size_t nb = sh.size();
-    lo.z.resize(nb); lo.act.resize(nb); lo.ga.resize(nb); lo.mean.resize(nb); lo.invstd.resize(nb); lo.s1.resize(nb); lo.s2.resize(nb);
+    lo.z.resize(nb); lo.act.resize(nb); lo.ga.resize(nb); lo.mean.resize(nb); lo.invstd.resize(nb); lo.s1.resize(nb); lo.s2.resize(nb); lo.wf.resize(nb); lo.wb.resize(nb);
     size_t cur = 0, din_max = 0;
     auto take = [&](size_t n) { const size_t o = cur; cur += (n + 63) / 64 * 64; return o; };
     for (size_t i = 0; i < nb; ++i) {
         const size_t n = (size_t)B * sh[i].cout * sh[i].L;
         lo.z[i] = take(n); lo.act[i] = take(n); lo.ga[i] = take(n);
         lo.mean[i] = take(sh[i].cout); lo.invstd[i] = take(sh[i].cout); lo.s1[i] = take(sh[i].cout); lo.s2[i] = take(sh[i].cout);
+        lo.wf[i] = take((size_t)sh[i].cout * sh[i].cin * sh[i].k); lo.wb[i] = take((size_t)sh[i].cout * sh[i].cin * sh[i].k);
         din_max = std::max(din_max, (size_t)B * sh[i].cin * sh[i].L);
     }
     lo.din = take(din_max);
+    lo.ones = take(kMaxC); lo.zeros = take(kMaxC);
     lo.total = cur;
 }
 
@@ -397,6 +497,13 @@ ConvArgs conv_args(const std::vector<Shape> &sh, const Layout &lo, float *ws, co
 }
 
 unsigned blocks_for(long long n, int per) { return (unsigned)((n + per - 1) / per); }
+
+// WUNET_TRAIN_NAIVE=1: the one-thread-per-output reference kernels instead of the tuned ones (cross-check)
+bool train_naive()
+{
+    const char *e = getenv("WUNET_TRAIN_NAIVE");
+    return e && e[0] == '1';
+}
 
 }  // namespace
 
@@ -419,12 +526,24 @@ int train_forward(int n, int ci, const float *x, float *y, int B, int T, const T
     Layout lo;
     layout_of(sh, B, lo);
     float *ws = static_cast<float *>(workspace);
+    const bool naive = train_naive();
+    if (sh[0].cout * (2 * n) > kMaxC && !naive) return train_fail("channel plan too wide for the training kernels (%d channels)", sh[0].cout * 2 * n);
+    if (!naive) {
+        train_fill_kernel<<<(kMaxC + 255) / 256, 256, 0, st>>>(ws + lo.ones, 1.f, kMaxC);
+        train_fill_kernel<<<(kMaxC + 255) / 256, 256, 0, st>>>(ws + lo.zeros, 0.f, kMaxC);
+    }
     for (int i = 0; i < 2 * n + 1; ++i) {
         const Shape &s = sh[i];
-        const ConvArgs a = conv_args(sh, lo, ws, x, i, n, B);
+        ConvArgs a = conv_args(sh, lo, ws, x, i, n, B);
         float *z = ws + lo.z[i];
         const dim3 grid((unsigned)((s.L + 127) / 128), (unsigned)((s.cout + 7) / 8), (unsigned)B);
-        if (s.mode == SRC_DIRECT) train_conv_fwd_kernel<15, SRC_DIRECT><<<grid, 128, 0, st>>>(a, P.conv_w[i], P.conv_b[i], z);
+        if (!naive) {
+            // z = conv(in, w) + bias through the tuned fp32 conv kernels: identity scale, shift = conv bias, no activation
+            const long long nw = (long long)s.cout * s.cin * s.k;
+            train_pack_kernel<<<blocks_for(nw, 256), 256, 0, st>>>(P.conv_w[i], ws + lo.wf[i], ws + lo.wb[i], s.cout, s.cin, s.k);
+            a.wp = ws + lo.wf[i]; a.scale = ws + lo.ones; a.shift = P.conv_b[i]; a.out = z; a.linear = 1;
+            if (launch_conv_fp32(a, s.k, s.mode, st) < 0) return train_fail("training forward, block %d: conv launch failed", i);
+        } else if (s.mode == SRC_DIRECT) train_conv_fwd_kernel<15, SRC_DIRECT><<<grid, 128, 0, st>>>(a, P.conv_w[i], P.conv_b[i], z);
         else if (s.mode == SRC_DECIM) train_conv_fwd_kernel<15, SRC_DECIM><<<grid, 128, 0, st>>>(a, P.conv_w[i], P.conv_b[i], z);
         else train_conv_fwd_kernel<5, SRC_UPCAT><<<grid, 128, 0, st>>>(a, P.conv_w[i], P.conv_b[i], z);
         train_bn_stats_kernel<<<(unsigned)s.cout, 256, 0, st>>>(z, B, s.cout, s.L, momentum, ws + lo.mean[i], ws + lo.invstd[i],
@@ -449,6 +568,7 @@ int train_backward(int n, int ci, const float *x, const float *y, const float *d
     layout_of(sh, B, lo);
     float *ws = static_cast<float *>(workspace);
     const int last = 2 * n, C = sh[last].cout;
+    const bool naive = train_naive();
     if (part < -1 || part > 1) return train_fail("training backward: part must be -1, 0 or 1 (got %d)", part);
     if (part != 1) {
         cudaMemsetAsync(G.out_w, 0, (C + 1) * sizeof(float), st);
@@ -471,14 +591,29 @@ int train_backward(int n, int ci, const float *x, const float *y, const float *d
         const ConvArgs a = conv_args(sh, lo, ws, x, i, n, B);
         cudaMemsetAsync(G.conv_w[i], 0, (size_t)s.cout * s.cin * s.k * sizeof(float), st);
         const dim3 gw((unsigned)s.cout, (unsigned)((s.cin + 3) / 4), (unsigned)std::min(B, 8));
-        if (s.mode == SRC_DIRECT) train_conv_bwd_weight_kernel<15, SRC_DIRECT><<<gw, 128, 0, st>>>(a, ga, G.conv_w[i]);
+        if (!naive) {
+            const int lt = std::min(s.L, 128);
+            const int nco = (s.cout + 15) / 16, nci = (s.cin + 63) / 64;
+            const int ntiles = B * ((s.L + lt - 1) / lt);
+            const int slices = std::max(1, std::min(ntiles, 1184 / (nco * nci)));           // ~4 blocks per SM over the grid
+            const dim3 gt((unsigned)nco, (unsigned)nci, (unsigned)slices);
+            if (s.mode == SRC_DIRECT) train_wgrad_kernel<15, SRC_DIRECT><<<gt, 256, 0, st>>>(a, ga, G.conv_w[i], lt);
+            else if (s.mode == SRC_DECIM) train_wgrad_kernel<15, SRC_DECIM><<<gt, 256, 0, st>>>(a, ga, G.conv_w[i], lt);
+            else train_wgrad_kernel<5, SRC_UPCAT><<<gt, 256, 0, st>>>(a, ga, G.conv_w[i], lt);
+        } else if (s.mode == SRC_DIRECT) train_conv_bwd_weight_kernel<15, SRC_DIRECT><<<gw, 128, 0, st>>>(a, ga, G.conv_w[i]);
         else if (s.mode == SRC_DECIM) train_conv_bwd_weight_kernel<15, SRC_DECIM><<<gw, 128, 0, st>>>(a, ga, G.conv_w[i]);
         else train_conv_bwd_weight_kernel<5, SRC_UPCAT><<<gw, 128, 0, st>>>(a, ga, G.conv_w[i]);
         // input gradient and its routing to the producers of the block input
         if (s.mode != SRC_DIRECT) {
             float *din = ws + lo.din;
             const dim3 gd((unsigned)((s.L + 127) / 128), (unsigned)((s.cin + 7) / 8), (unsigned)B);
-            if (s.k == 15) train_conv_bwd_data_kernel<15><<<gd, 128, 0, st>>>(ga, P.conv_w[i], din, B, s.cin, s.cout, s.L);
+            if (!naive) {
+                // din = conv(dz, transposed + flipped weights): the forward conv kernels with dz as a plain [B][Cout][L] input
+                ConvArgs d{};
+                d.src0 = ga; d.wp = ws + lo.wb[i]; d.scale = ws + lo.ones; d.shift = ws + lo.zeros; d.out = din;
+                d.B = B; d.L = s.L; d.Cin = s.cout; d.Cin0 = s.cout; d.Cin1 = 0; d.Cout = s.cin; d.linear = 1;
+                if (launch_conv_fp32(d, s.k, SRC_DIRECT, st) < 0) return train_fail("training backward, block %d: input-gradient conv launch failed", i);
+            } else if (s.k == 15) train_conv_bwd_data_kernel<15><<<gd, 128, 0, st>>>(ga, P.conv_w[i], din, B, s.cin, s.cout, s.L);
             else train_conv_bwd_data_kernel<5><<<gd, 128, 0, st>>>(ga, P.conv_w[i], din, B, s.cin, s.cout, s.L);
             if (s.mode == SRC_DECIM) {
                 // encoder i >= 1 or the middle block: its input is act[i-1][:, :, ::2]; ga[i-1] already holds the skip gradient
