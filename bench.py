@@ -664,6 +664,18 @@ def main():
                                                "frac": round(flops64 / (ms32 * 1e-3) / ffma_peak, 4),
                                                "peak_source": "theoretical FFMA rate at sm_max_mhz (not driver-measured)"}}
         del m32
+        # the same <= 1e-4 contract on the tensor cores: split precision (bf16 hi + lo, three tcgen05 MMAs per product)
+        try:
+            mtc = make("fp32_tc")
+            with torch.no_grad():
+                ms_tc64 = time_steps(lambda: mtc(x64), 10)
+                ms_tc = time_steps(lambda: mtc(xs[0]), 10)
+            extras["fp32_tc"] = {"workload": "unet_basic forward, split-precision tcgen05 path (<= 1e-4 vs the reference)",
+                                 "batch64": {"value": round(64 / ms_tc64 * 1e3, 1), "unit": "frames/s", "ms_per_step": round(ms_tc64, 4)},
+                                 f"batch{B}": {"value": round(B / ms_tc * 1e3, 1), "unit": "frames/s", "ms_per_step": round(ms_tc, 4)}}
+            del mtc
+        except Exception as e:  # noqa: BLE001 - report, do not hide
+            extras["fp32_tc"] = {"error": str(e)[:200]}
         if not args.no_incumbent:
             extras["incumbent"] = incumbent_run(st, B, dev)
             extras["incumbent"]["speedup_vs_best_mode"] = round(value / max(extras["incumbent"][k]["frames_per_s"]

@@ -4,6 +4,10 @@
     ncu -i gpurun_out/prof.ncu-rep --page source --csv > src.csv   (optional, for the stall table)
     python tools/ncu_summarize.py raw.csv profiles/rNN_ncu_conv_tc_summary.csv [src.csv profiles/rNN_ncu_top_stalls.txt]
 
+The summary's header records the source hash of the library that is loaded when this script runs (wunet_version(): run it
+against the same build the capture was taken from); bench.py quotes `roofline.traffic` from the summary only when that hash
+equals the running library's.
+
 The level names follow the launch order of wunet_forward (enc0..enc11, middle, dec0..dec11); the per-launch times are
 cold-cache and serialised, so only the SHARES are comparable with the bench's event timings.
 """
@@ -36,7 +40,18 @@ def main():
     units = rows[1]
     idx = [(k, col(h, m)) for k, m in keys]
     total = 0.0
+    build = "unknown"
+    try:
+        import os
+        import re
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        from wave_u_net_for_speech_enhancement_b200 import _lib
+        m = re.search(r"src ([0-9a-f]+)", _lib.load().wunet_version().decode())
+        build = m.group(1) if m else "unknown"
+    except Exception:  # noqa: BLE001
+        pass
     with open(out, "w") as f:
+        f.write("# build %s\n" % build)
         f.write("# ncu --set full --clock-control none of the %d kernels of ONE bf16 forward (B=256, T=16384)\n" % len(data))
         f.write("# per-launch times are cold-cache and serialised: use SHARES. dram_* in MB; tensor_pct = "
                 "sm__pipe_tensor_subpipe_hmma_cycles_active % of peak\n")

@@ -730,39 +730,69 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         // frames shorter than a tile (packed), and every level in split-precision mode: generic per-(row, vector)
                         // path, ATen index math in fp32
                         const int items = p.rows_used * nvec;
+                        if (SP != 0) {
+                            // split precision: prev rows are [hi | lo] (2 Cin0 channels); interpolate hi + lo in fp32 with the fp32
+                            // path's formula (lam0 a + lam1 b), emit the high or the low bf16 part of the result. Two items per
+                            // thread are in flight: their 8 loads are issued before the first is used (the unit is latency-bound).
+                            constexpr int U = 2;
+#pragma unroll 1
+                            for (int itb = pt; itb < items; itb += U * NPROD) {
+                                uint4 h0[U], l0v[U], h1[U], l1v[U];
+                                float lam1[U];
+                                bool ok[U];
+#pragma unroll
+                                for (int u = 0; u < U; ++u) {
+                                    const int itx = itb + u * NPROD;
+                                    const int row = itx / nvec, vec = itx - row * nvec;
+                                    int bb = b0, l = l0 - PAD + row;
+                                    if (p.packed) { const int f = row / p.S; bb = b0 + f; l = row - f * p.S - PAD; }
+                                    const int ch = cu.idx * 64 + vec * 8;
+                                    ok[u] = itx < items && bb < p.B && l >= 0 && l < p.L && ch < p.Cin0;
+                                    h0[u] = l0v[u] = h1[u] = l1v[u] = make_uint4(0u, 0u, 0u, 0u);
+                                    lam1[u] = 0.f;
+                                    if (ok[u]) {
+                                        const float s = p.up_scale * (float)l;
+                                        const int i0 = (int)s;
+                                        const int i1 = i0 + (i0 < p.Lin - 1 ? 1 : 0);
+                                        lam1[u] = s - (float)i0;
+                                        const __nv_bfloat16 *r0 = p.prev + ((size_t)bb * p.Lin + i0) * (2 * p.Cin0) + ch;
+                                        const __nv_bfloat16 *r1 = p.prev + ((size_t)bb * p.Lin + i1) * (2 * p.Cin0) + ch;
+                                        h0[u] = __ldg(reinterpret_cast<const uint4 *>(r0)); l0v[u] = __ldg(reinterpret_cast<const uint4 *>(r0 + p.Cin0));
+                                        h1[u] = __ldg(reinterpret_cast<const uint4 *>(r1)); l1v[u] = __ldg(reinterpret_cast<const uint4 *>(r1 + p.Cin0));
+                                    }
+                                }
+#pragma unroll
+                                for (int u = 0; u < U; ++u) {
+                                    const int itx = itb + u * NPROD;
+                                    if (itx >= items) break;
+                                    const int row = itx / nvec, vec = itx - row * nvec;
+                                    const float lam0 = 1.f - lam1[u];
+                                    const uint32_t ah[4] = {h0[u].x, h0[u].y, h0[u].z, h0[u].w}, al[4] = {l0v[u].x, l0v[u].y, l0v[u].z, l0v[u].w};
+                                    const uint32_t bh[4] = {h1[u].x, h1[u].y, h1[u].z, h1[u].w}, bl[4] = {l1v[u].x, l1v[u].y, l1v[u].z, l1v[u].w};
+                                    uint32_t r[4];
+#pragma unroll
+                                    for (int q4 = 0; q4 < 4; ++q4) {
+                                        const float2 fah = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&ah[q4]));
+                                        const float2 fal = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&al[q4]));
+                                        const float2 fbh = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&bh[q4]));
+                                        const float2 fbl = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&bl[q4]));
+                                        const float vx = lam0 * (fah.x + fal.x) + lam1[u] * (fbh.x + fbl.x);
+                                        const float vy = lam0 * (fah.y + fal.y) + lam1[u] * (fbh.y + fbl.y);
+                                        const float hx = __bfloat162float(__float2bfloat16_rn(vx)), hy = __bfloat162float(__float2bfloat16_rn(vy));
+                                        r[q4] = cu.lo ? pack_bf16(vx - hx, vy - hy) : pack_bf16(vx, vy);
+                                    }
+                                    *reinterpret_cast<uint4 *>(dst + row * 128 + ((vec ^ (row & 7)) << 4)) =
+                                        ok[u] ? make_uint4(r[0], r[1], r[2], r[3]) : make_uint4(0u, 0u, 0u, 0u);
+                                }
+                            }
+                        } else
                         for (int itx = pt; itx < items; itx += NPROD) {
                             const int row = itx / nvec, vec = itx - row * nvec;
-                            int bb = b0, l = l0 - PAD + row;                       // full-length frames (split-precision mode only)
+                            int bb = b0, l = l0 - PAD + row;
                             if (p.packed) { const int f = row / p.S; bb = b0 + f; l = row - f * p.S - PAD; }
                             const int ch = cu.idx * 64 + vec * 8;
                             uint4 o = make_uint4(0u, 0u, 0u, 0u);
-                            if (SP != 0 && bb < p.B && l >= 0 && l < p.L && ch < p.Cin0) {
-                                // split precision: prev rows are [hi | lo] (2 Cin0 channels); interpolate hi + lo in fp32 with the
-                                // fp32 path's formula (lam0 a + lam1 b), emit the high or the low bf16 part of the result
-                                const float s = p.up_scale * (float)l;
-                                const int i0 = (int)s;
-                                const int i1 = i0 + (i0 < p.Lin - 1 ? 1 : 0);
-                                const float lam1 = s - (float)i0, lam0 = 1.f - lam1;
-                                const __nv_bfloat16 *r0 = p.prev + ((size_t)bb * p.Lin + i0) * (2 * p.Cin0) + ch;
-                                const __nv_bfloat16 *r1 = p.prev + ((size_t)bb * p.Lin + i1) * (2 * p.Cin0) + ch;
-                                const uint4 h0 = __ldg(reinterpret_cast<const uint4 *>(r0)), l0v = __ldg(reinterpret_cast<const uint4 *>(r0 + p.Cin0));
-                                const uint4 h1 = __ldg(reinterpret_cast<const uint4 *>(r1)), l1v = __ldg(reinterpret_cast<const uint4 *>(r1 + p.Cin0));
-                                const uint32_t ah[4] = {h0.x, h0.y, h0.z, h0.w}, al[4] = {l0v.x, l0v.y, l0v.z, l0v.w};
-                                const uint32_t bh[4] = {h1.x, h1.y, h1.z, h1.w}, bl[4] = {l1v.x, l1v.y, l1v.z, l1v.w};
-                                uint32_t r[4];
-#pragma unroll
-                                for (int q4 = 0; q4 < 4; ++q4) {
-                                    const float2 fah = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&ah[q4]));
-                                    const float2 fal = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&al[q4]));
-                                    const float2 fbh = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&bh[q4]));
-                                    const float2 fbl = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&bl[q4]));
-                                    const float vx = lam0 * (fah.x + fal.x) + lam1 * (fbh.x + fbl.x);
-                                    const float vy = lam0 * (fah.y + fal.y) + lam1 * (fbh.y + fbl.y);
-                                    const float hx = __bfloat162float(__float2bfloat16_rn(vx)), hy = __bfloat162float(__float2bfloat16_rn(vy));
-                                    r[q4] = cu.lo ? pack_bf16(vx - hx, vy - hy) : pack_bf16(vx, vy);
-                                }
-                                o = make_uint4(r[0], r[1], r[2], r[3]);
-                            } else if (SP == 0 && bb < p.B && l >= 0 && l < p.L && ch < p.Cin0) {
+                            if (bb < p.B && l >= 0 && l < p.L && ch < p.Cin0) {
                                 const float s = p.up_scale * (float)l;
                                 const int i0 = (int)s;
                                 const int i1 = i0 + (i0 < p.Lin - 1 ? 1 : 0);
@@ -838,8 +868,9 @@ struct TnParams {
     unsigned char c_up[8], c_ch[8], c_nk[8], c_slot[8], c_row[8];   // per chunk: producer-written?, 64-channel chunk index inside its
                                                // segment, K16 steps, weight slot, extra operand row offset (tap group * 5)
     int pad;                                   // (KS - 1) / 2
-    int wpg, npg;                              // producer warps per group, groups (each group owns every npg-th upsampled chunk)
-    uint32_t a_stage_bytes, w_tile_bytes, tmem_cols;
+    int wpg, npg;                              // producer warps per group, groups (each group owns every npg-th tile)
+    int ntma, nup_items;                       // TMA-loaded chunks per tile; producer items per tile (all upsampled chunks)
+    uint32_t a_stage_bytes, a_sub_bytes, w_tile_bytes, tmem_cols;   // stage = all chunks of a tile, one sub-buffer (MT x 16 KB) each
     const __nv_bfloat16 *prev;                 // decoder: previous block output [B][L/2][Cin0]
     int Lin;
     float up_scale;
@@ -862,7 +893,7 @@ __host__ __device__ inline TnSmem tn_smem_map(const TnParams &p)
     m.bars = (m.ss + (uint32_t)p.Cout * 8 + 64 * 4 + 15) & ~15u;
     return m;
 }
-inline size_t tn_smem_total(const TnParams &p) { return tn_smem_map(p).bars + 8 * (8 + 8 + 1 + 2 + 2) + 16 + 1024; }
+inline size_t tn_smem_total(const TnParams &p) { return tn_smem_map(p).bars + 8 * (8 + 8 + 1 + 2 + 2) + 16 + 1024; }   // barrier slots sized for 8 stages
 
 __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&v)[8])
 {
@@ -898,7 +929,7 @@ conv_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
         for (int s = 0; s < 8; ++s) {
-            mbar_init(a_full + 8 * s, UPCAT ? 1 + p.wpg : 1);
+            mbar_init(a_full + 8 * s, (UPCAT && p.nup_items > 0) ? 1 + p.wpg : 1);
             mbar_init(a_empty + 8 * s, 1);
         }
         mbar_init(w_full, 1);
@@ -937,26 +968,23 @@ conv_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int c = 0; c < p.nchunks; ++c)
                 tma_load_3d(base + sm.w + (uint32_t)c * p.w_tile_bytes, &tmW, w_full, p.c_slot[c] * 64, 0, 0);
             asm volatile("griddepcontrol.wait;" ::: "memory");
-            uint32_t cnt = 0;
-            for (int tile = first_tile; tile < total_tiles; tile += gridDim.x) {
+            // ONE operand stage per tile: all K chunks of a tile share a stage and a barrier pair. A chunk is only a few long MMAs
+            // here (N' up to 240), and every stage hand-off costs the tensor pipe a few hundred idle cycles: per-chunk
+            // stages left the pipe idle two thirds of the time (profiles/r02_tn_roles.txt).
+            uint32_t it = 0;
+            for (int tile = first_tile; tile < total_tiles; tile += gridDim.x, ++it) {
                 int b0, l0;
                 tile_coords(tile, b0, l0);
-                for (int c = 0; c < p.nchunks; ++c, ++cnt) {
-                    const uint32_t sa = cnt % (uint32_t)p.na, pa = (cnt / (uint32_t)p.na) & 1u;
-                    mbar_wait(a_empty + 8 * sa, pa ^ 1);
-                    if (!p.c_up[c]) {
-                        if (DBG & 16) mbar_arrive(a_full + 8 * sa);
-                        else {
-                        mbar_expect_tx(a_full + 8 * sa, (uint32_t)nblk * 4096u);
-                        const uint32_t dst = base + sm.a + sa * p.a_stage_bytes;
-                        const int lc = l0 - p.pad + p.c_row[c];
-                        for (int k = 0; k < nblk; ++k)
-                            tma_load_3d(dst + (uint32_t)k * 4096u, &tmA, a_full + 8 * sa, p.c_ch[c] * 64, lc + 28 * k, b0);
-                        }
-                        if (UPCAT) mbar_arrive_n(a_full + 8 * sa, (uint32_t)p.wpg);     // the producers do not touch this stage
-                    } else {
-                        mbar_arrive(a_full + 8 * sa);                                   // the owning producer group completes it
-                    }
+                const uint32_t sa = it % (uint32_t)p.na, pa = (it / (uint32_t)p.na) & 1u;
+                mbar_wait(a_empty + 8 * sa, pa ^ 1);
+                if (p.ntma == 0 || (DBG & 16)) { mbar_arrive(a_full + 8 * sa); continue; }
+                mbar_expect_tx(a_full + 8 * sa, (uint32_t)p.ntma * (uint32_t)nblk * 4096u);
+                for (int c = 0; c < p.nchunks; ++c) {
+                    if (p.c_up[c]) continue;
+                    const uint32_t dst = base + sm.a + sa * p.a_stage_bytes + (uint32_t)c * p.a_sub_bytes;
+                    const int lc = l0 - p.pad + p.c_row[c];
+                    for (int k = 0; k < nblk; ++k)
+                        tma_load_3d(dst + (uint32_t)k * 4096u, &tmA, a_full + 8 * sa, p.c_ch[c] * 64, lc + 28 * k, b0);
                 }
             }
         }
@@ -966,18 +994,18 @@ conv_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Npad >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             mbar_wait(w_full, 0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            uint32_t cnt = 0;
             int it = 0;
             for (int tile = first_tile; tile < total_tiles; tile += gridDim.x, ++it) {
                 const int buf = it & 1;
+                const uint32_t sa = (uint32_t)it % (uint32_t)p.na, pa = ((uint32_t)it / (uint32_t)p.na) & 1u;
                 mbar_wait(acc_empty + 8 * buf, (((uint32_t)it >> 1) & 1u) ^ 1u);
+                mbar_wait(a_full + 8 * sa, pa);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t acc_col = tmem_base + (uint32_t)(buf * p.MT * p.Nstride);
-                for (int c = 0; c < p.nchunks; ++c, ++cnt) {
-                    const uint32_t sa = cnt % (uint32_t)p.na, pa = (cnt / (uint32_t)p.na) & 1u;
-                    mbar_wait(a_full + 8 * sa, pa);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t a_lo = (((base + sm.a + sa * p.a_stage_bytes) >> 4) & 0x3FFFu) | (1u << 16);
+                const uint32_t a_stage = (((base + sm.a + sa * p.a_stage_bytes) >> 4) & 0x3FFFu) | (1u << 16);
+#pragma unroll 1
+                for (int c = 0; c < p.nchunks; ++c) {
+                    const uint32_t a_lo = a_stage + (uint32_t)c * (p.a_sub_bytes >> 4);
                     const uint32_t b_lo = (((base + sm.w + (uint32_t)c * p.w_tile_bytes) >> 4) & 0x3FFFu) | (1u << 16);
                     const int nk = p.c_nk[c];
 #pragma unroll 1
@@ -989,8 +1017,8 @@ conv_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (nk > 2) umma_bf16_lohi(d, am + 4, b_lo + 4, hi, idesc, 1u);
                         if (nk > 3) umma_bf16_lohi(d, am + 6, b_lo + 6, hi, idesc, 1u);
                     }
-                    umma_commit(a_empty + 8 * sa);
                 }
+                umma_commit(a_empty + 8 * sa);
                 umma_commit(acc_full + 8 * buf);
             }
         }
@@ -1077,83 +1105,89 @@ conv_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ======================= upsample producers =======================
         // As in conv_tc_kernel (16 output rows x one 16-byte channel vector per thread, packed-bf16 interpolation straight into
         // the swizzled operand), with the operand rows mapped to positions block by block (row 32 k + i <-> l0 - PAD + 28 k + i)
-        // and the producer warps split into groups that work on different upsampled chunks at the same time: one chunk has
-        // fewer items than there are producer threads, and its latency (~1.5 k cycles) is longer than a tile's MMAs.
+        // and the producer warps split into groups that work on different TILES at the same time: a tile has fewer items
+        // than there are producer threads, and an item's latency (~1.5 k cycles + its loads) is longer than a tile's MMAs.
         const int pw = warp - kFirstProducer;
         const int grp = pw / p.wpg;
-        if (grp < p.npg) {
+        if (grp < p.npg && p.nup_items > 0) {
             const int pt = (pw - grp * p.wpg) * 32 + lane;
             const int nthreads = p.wpg * 32;
-            const int nruns = 8 * p.MT;                            // 16-row runs per tile (two per 32-row block)
-            uint32_t cnt = 0, unit = 0;
-            for (int tile = first_tile; tile < total_tiles; tile += gridDim.x) {
+            // items of a tile: for every upsampled chunk (16-row run, 16-byte channel vector); a group owns every npg-th tile
+            uint32_t it = 0;
+            for (int tile = first_tile; tile < total_tiles; tile += gridDim.x, ++it) {
                 int b0, l0;
                 tile_coords(tile, b0, l0);
-                for (int c = 0; c < p.nchunks; ++c, ++cnt) {
-                    // Every group follows EVERY chunk's stage release in order, also those it does not write: an mbarrier wait
-                    // only tells the current phase from the previous one, so a waiter must never get two uses of a stage ahead
-                    // of (or behind) the barrier it polls. Skipping the chunks of other groups did exactly that.
-                    const uint32_t sa = cnt % (uint32_t)p.na, pa = (cnt / (uint32_t)p.na) & 1u;
-                    const bool mine = p.c_up[c] && (unit % (uint32_t)p.npg) == (uint32_t)grp;
-                    if (p.c_up[c]) ++unit;
-                    if (!mine) { mbar_wait(a_empty + 8 * sa, pa ^ 1); continue; }
-                    const int nvec = p.c_nk[c] * 2;
-                    const int nitems = nruns * nvec;
-                    uint4 xr[10];
-                    auto fetch = [&](int item) {
-                        const int run = item / nvec, vec = item - run * nvec;
-                        const int ch = p.c_ch[c] * 64 + vec * 8;
-                        const int lstart = l0 - p.pad + 28 * (run >> 1) + 16 * (run & 1);      // even
-                        const int ms = lstart >> 1;
-                        const bool chok = ch < p.Cin0;
-                        const __nv_bfloat16 *pb = p.prev + (size_t)b0 * p.Lin * p.Cin0 + ch;
-#pragma unroll
-                        for (int qq = 0; qq < 10; ++qq) {
-                            int m = ms - 1 + qq;
-                            m = m < 0 ? 0 : (m > p.Lin - 1 ? p.Lin - 1 : m);
-                            xr[qq] = chok ? __ldg(reinterpret_cast<const uint4 *>(pb + (size_t)m * p.Cin0)) : make_uint4(0u, 0u, 0u, 0u);
-                        }
-                    };
-                    if (DBG & 32) {
-                        mbar_wait(a_empty + 8 * sa, pa ^ 1);
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(a_full + 8 * sa);
-                        continue;
-                    }
-                    if (pt < nitems) fetch(pt);                    // issued before the wait: DRAM latency overlaps it
+                // Every group follows EVERY tile's stage release in order, also of the tiles it does not write: an mbarrier wait
+                // only tells the current phase from the previous one, so a waiter must never get two uses of a stage ahead of
+                // (or behind) the barrier it polls.
+                const uint32_t sa = it % (uint32_t)p.na, pa = (it / (uint32_t)p.na) & 1u;
+                const bool mine = (it % (uint32_t)p.npg) == (uint32_t)grp;
+                if (!mine) { mbar_wait(a_empty + 8 * sa, pa ^ 1); continue; }
+                if (DBG & 32) {
                     mbar_wait(a_empty + 8 * sa, pa ^ 1);
-                    const uint32_t stage = base + sm.a + sa * p.a_stage_bytes;
-#pragma unroll 1
-                    for (int item = pt; item < nitems; item += nthreads) {
-                        if (item != pt) fetch(item);
-                        const int run = item / nvec, vec = item - run * nvec;
-                        const int ch = p.c_ch[c] * 64 + vec * 8;
-                        const int lstart = l0 - p.pad + 28 * (run >> 1) + 16 * (run & 1);
-                        const int ms = lstart >> 1;
-                        const bool chok = ch < p.Cin0;
-                        const float lf0 = (float)lstart, mf0 = (float)(ms - 1);
-                        const uint32_t drow = stage + (uint32_t)(16 * run) * 128u;
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const int l = lstart + j;
-                            const int qa = (j >> 1) + (j & 1);
-                            const float lam1 = fmaf(p.up_scale, lf0 + (float)j, -(mf0 + (float)qa));
-                            const __nv_bfloat162 lam = __float2bfloat162_rn(lam1);
-                            const __nv_bfloat162 *a2 = reinterpret_cast<const __nv_bfloat162 *>(&xr[qa]);
-                            const __nv_bfloat162 *b2 = reinterpret_cast<const __nv_bfloat162 *>(&xr[qa + 1]);
-                            __nv_bfloat162 r2[4];
-#pragma unroll
-                            for (int q4 = 0; q4 < 4; ++q4) r2[q4] = __hfma2(lam, __hsub2(b2[q4], a2[q4]), a2[q4]);
-                            uint4 o = *reinterpret_cast<const uint4 *>(r2);
-                            const uint32_t keep = (chok && (unsigned)l < (unsigned)p.L) ? 0xffffffffu : 0u;
-                            o.x &= keep; o.y &= keep; o.z &= keep; o.w &= keep;
-                            st_shared_v4_if(drow + (uint32_t)(j * 128 + ((vec ^ (j & 7)) << 4)), o, true);
-                        }
-                    }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) mbar_arrive(a_full + 8 * sa);
+                    continue;
                 }
+                uint4 xr[10];
+                // item -> (chunk c, run, vec): the upsampled chunks are laid out one after the other in the item index
+                auto locate = [&](int item, int &c, int &run, int &vec) {
+                    c = 0;
+                    for (;; ++c) {
+                        if (!p.c_up[c]) continue;
+                        const int n = 8 * p.MT * 2 * (int)p.c_nk[c];
+                        if (item < n) break;
+                        item -= n;
+                    }
+                    const int nvec = 2 * (int)p.c_nk[c];
+                    run = item / nvec; vec = item - run * nvec;
+                };
+                auto fetch = [&](int c, int run, int vec) {
+                    const int ch = p.c_ch[c] * 64 + vec * 8;
+                    const int lstart = l0 - p.pad + 28 * (run >> 1) + 16 * (run & 1);      // even
+                    const int ms = lstart >> 1;
+                    const bool chok = ch < p.Cin0;
+                    const __nv_bfloat16 *pb = p.prev + (size_t)b0 * p.Lin * p.Cin0 + ch;
+#pragma unroll
+                    for (int qq = 0; qq < 10; ++qq) {
+                        int m = ms - 1 + qq;
+                        m = m < 0 ? 0 : (m > p.Lin - 1 ? p.Lin - 1 : m);
+                        xr[qq] = chok ? __ldg(reinterpret_cast<const uint4 *>(pb + (size_t)m * p.Cin0)) : make_uint4(0u, 0u, 0u, 0u);
+                    }
+                };
+                int c = 0, run = 0, vec = 0;
+                if (pt < p.nup_items) { locate(pt, c, run, vec); fetch(c, run, vec); }     // issued before the wait: DRAM latency overlaps it
+                mbar_wait(a_empty + 8 * sa, pa ^ 1);
+                const uint32_t stage = base + sm.a + sa * p.a_stage_bytes;
+#pragma unroll 1
+                for (int item = pt; item < p.nup_items; item += nthreads) {
+                    if (item != pt) { locate(item, c, run, vec); fetch(c, run, vec); }
+                    const int ch = p.c_ch[c] * 64 + vec * 8;
+                    const int lstart = l0 - p.pad + 28 * (run >> 1) + 16 * (run & 1);
+                    const int ms = lstart >> 1;
+                    const bool chok = ch < p.Cin0;
+                    const float lf0 = (float)lstart, mf0 = (float)(ms - 1);
+                    const uint32_t drow = stage + (uint32_t)c * p.a_sub_bytes + (uint32_t)(16 * run) * 128u;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int l = lstart + j;
+                        const int qa = (j >> 1) + (j & 1);
+                        const float lam1 = fmaf(p.up_scale, lf0 + (float)j, -(mf0 + (float)qa));
+                        const __nv_bfloat162 lam = __float2bfloat162_rn(lam1);
+                        const __nv_bfloat162 *a2 = reinterpret_cast<const __nv_bfloat162 *>(&xr[qa]);
+                        const __nv_bfloat162 *b2 = reinterpret_cast<const __nv_bfloat162 *>(&xr[qa + 1]);
+                        __nv_bfloat162 r2[4];
+#pragma unroll
+                        for (int q4 = 0; q4 < 4; ++q4) r2[q4] = __hfma2(lam, __hsub2(b2[q4], a2[q4]), a2[q4]);
+                        uint4 o = *reinterpret_cast<const uint4 *>(r2);
+                        const uint32_t keep = (chok && (unsigned)l < (unsigned)p.L) ? 0xffffffffu : 0u;
+                        o.x &= keep; o.y &= keep; o.z &= keep; o.w &= keep;
+                        st_shared_v4_if(drow + (uint32_t)(j * 128 + ((vec ^ (j & 7)) << 4)), o, true);
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(a_full + 8 * sa);
             }
         }
     }
@@ -1921,18 +1955,23 @@ static bool plan_block_tn(const TcLevel &lv, int i, int n, int B, int T, int num
         for (int g = 0; g < lv.tn_groups; ++g) add(0, 0, lv.cin0, g, 5 * g);
     }
     t.nchunks = k;
-    t.a_stage_bytes = (uint32_t)(MT * 4 * 4096);
+    t.a_sub_bytes = (uint32_t)(MT * 4 * 4096);
+    t.a_stage_bytes = (uint32_t)t.nchunks * t.a_sub_bytes;
     t.w_tile_bytes = (uint32_t)round_up(t.Npad * 128, 1024);
     const int budget = kSmemLimit - 2048 - t.Cout * 8 - 512 - t.nchunks * (int)t.w_tile_bytes;
     int na = budget / (int)t.a_stage_bytes;
-    if (na > 8) na = 8;
+    if (na > 4) na = 4;
     if (const char *e = getenv("WUNET_TN_NA")) na = std::min(na, std::max(2, atoi(e)));
     if (na < 2) return false;
     t.na = na;
     t.tmem_cols = 512;
     // producer groups: enough warps per group to give every thread at most one item of the widest upsampled chunk
     int items = 0;
-    for (int c = 0; c < t.nchunks; ++c) if (t.c_up[c]) items = std::max(items, 8 * MT * 2 * (int)t.c_nk[c]);
+    for (int c = 0; c < t.nchunks; ++c) {
+        if (t.c_up[c]) items += 8 * MT * 2 * (int)t.c_nk[c];
+        else ++t.ntma;
+    }
+    t.nup_items = items;
     t.wpg = std::max(1, std::min(kProducerWarpsLarge, (items + 31) / 32));
     t.npg = std::max(1, kProducerWarpsLarge / t.wpg);
     t.head = last ? 1 : 0;

@@ -396,7 +396,8 @@ __global__ void __launch_bounds__(256) train_wgrad_kernel(const ConvArgs a, cons
         for (int j = 0; j < 2; ++j)
 #pragma unroll
             for (int k = 0; k < KS; ++k) acc[i][j][k] = 0.f;
-    const int xw = lt + KS - 1;
+    const int lt4 = (lt + 3) & ~3;                    // the inner loop takes 4 positions at a time: frames of 1 or 2 samples are
+    const int xw = lt4 + KS - 1;                       // padded with zero gradients / out-of-frame (zero) inputs
     for (int t = blockIdx.z; t < ntiles; t += gridDim.z) {
         const int b = t / tiles_per_frame;
         const int l0 = (t - b * tiles_per_frame) * lt;
@@ -405,9 +406,9 @@ __global__ void __launch_bounds__(256) train_wgrad_kernel(const ConvArgs a, cons
             const int ci = i / xw, j = i - ci * xw;
             xs[ci][j] = (ci0 + ci < a.Cin) ? fetch_src<MODE>(a, b, ci0 + ci, l0 - PAD + j) : 0.f;
         }
-        for (int i = tid; i < CO_T * lt; i += 256) {
-            const int co = i / lt, j = i - co * lt;
-            ds[co][j] = (co0 + co < a.Cout && l0 + j < a.L) ? __ldg(dz + ((size_t)b * a.Cout + co0 + co) * a.L + l0 + j) : 0.f;
+        for (int i = tid; i < CO_T * lt4; i += 256) {
+            const int co = i / lt4, j = i - co * lt4;
+            ds[co][j] = (co0 + co < a.Cout && j < lt && l0 + j < a.L) ? __ldg(dz + ((size_t)b * a.Cout + co0 + co) * a.L + l0 + j) : 0.f;
         }
         __syncthreads();
 #pragma unroll 1
