@@ -10,6 +10,9 @@ The arithmetic of the bf16 tensor-core path (csrc/wunet_tc.cu) restated on the C
 * decoder inputs: the interpolated half in packed-bf16 arithmetic (lam = bf16(fma(up_scale, l, -m)), d = bf16(b - a),
   r = bf16(fma(lam, d, a))) for levels of at least 128 samples, in fp32 (lam0*f0 + lam1*f1, then bf16) for the packed
   short levels — exactly the two producer code paths;
+* decoder blocks of at most 16 samples run as one dense GEMM over frames (gemm_tc_kernel) whose weights for the upsampled input
+  have the interpolation folded in: W_eff = sum_t w[t] U[l+t-2, m] in fp32, rounded to bf16, applied to the previous block's
+  bf16 rows directly (no rounding of interpolated values);
 * head: the last block's fp32 (unrounded) activations, fp32 fma chain, tanh.
 
 A GPU result that differs from this model by more than a bf16 ulp at a handful of rounding flips is a kernel bug; the
@@ -66,6 +69,35 @@ def _upsample_hfma2(prev: torch.Tensor) -> torch.Tensor:
     return _bf16((lam[None, None, :].double() * d.double() + a.double()).float())
 
 
+def _block_folded(prev: torch.Tensor, skip: torch.Tensor, st, prefix: str) -> torch.Tensor:
+    """Decoder block of <= 16 samples as gemm_tc_kernel computes it: interpolation folded into the weights of the upsampled
+    input (expand_gemm_weights_kernel), skip half as a plain 5-tap convolution; fp32 result before the bf16 store."""
+    w = torch.from_numpy(np.asarray(st[f"{prefix}.0.weight"], np.float32))            # [Cout][Cprev + Cskip][5]
+    Cprev, Lin = prev.shape[1], prev.shape[2]
+    L = 2 * Lin
+    up_scale = np.float32(Lin - 1) / np.float32(L - 1) if L > 1 else np.float32(0)
+    sidx = (torch.arange(L, dtype=torch.float32) * up_scale)
+    i0 = sidx.to(torch.int64)
+    i1 = i0 + (i0 < Lin - 1).to(torch.int64)
+    lam1 = (sidx - i0.to(torch.float32)).double()
+    U = torch.zeros(L, Lin, dtype=torch.float64)
+    U[torch.arange(L), i0] += 1.0 - lam1
+    U[torch.arange(L), i1] += lam1
+    wp = w[:, :Cprev, :].double()
+    weff = torch.zeros(w.shape[0], Cprev, L, Lin, dtype=torch.float64)                 # [co][ci][l][m]
+    for t in range(5):
+        for l in range(L):
+            lp = l + t - 2
+            if 0 <= lp < L:
+                weff[:, :, l, :] += wp[:, :, t, None] * U[lp][None, None, :]
+    weff = _bf16(weff.float()).double()
+    acc = torch.einsum("bim,oilm->bol", prev.double(), weff)
+    acc = acc + F.conv1d(skip.double(), _bf16(w[:, Cprev:, :]).double(), None, padding=2)
+    s, shift = _fold(st, prefix)
+    v = acc.float() * s[None, :, None] + shift[None, :, None]
+    return torch.where(v >= 0, v, np.float32(LRELU_SLOPE) * v)
+
+
 def _upsample_fp32(prev: torch.Tensor) -> torch.Tensor:
     """Producer generic path (packed short levels): ATen index math and lam0*f0 + lam1*f1 in fp32, then bf16."""
     Lin = prev.shape[2]
@@ -105,8 +137,11 @@ def forward_bf16_model(state, x: np.ndarray, n_layers: int = 12, channels_interv
     o = keep(n, _bf16(_block(o, state, "middle", 15, True)))
     for j in range(n):
         L = 2 * o.shape[2]
-        up = _upsample_hfma2(o) if L >= 128 else _upsample_fp32(o)
-        v = _block(torch.cat([up, skips[n - 1 - j]], dim=1), state, plan[n + 1 + j][0], 5, True)
+        if L <= 16 and j != n - 1:
+            v = _block_folded(o, skips[n - 1 - j], state, plan[n + 1 + j][0])
+        else:
+            up = _upsample_hfma2(o) if L >= 128 else _upsample_fp32(o)
+            v = _block(torch.cat([up, skips[n - 1 - j]], dim=1), state, plan[n + 1 + j][0], 5, True)
         o = v if j == n - 1 else keep(n + 1 + j, _bf16(v))      # the last block feeds the fused head unrounded
         if j == n - 1:
             levels.append(o)

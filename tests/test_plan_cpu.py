@@ -42,6 +42,16 @@ def test_plan_invariants(n, ci, B):
             d = _lib.debug_plan(n, ci, B, T, i, SMS)
             ks = 15 if i <= n else 5
             ctx = (n, ci, B, T, i, d)
+            if d["small"] == 2:
+                # dense GEMM over frames (blocks of at most 16 samples): 256 frames x Nh columns per CTA, K = 64-channel chunks
+                assert d["L"] <= 16 and i != 2 * n, ctx
+                N = d["L"] * d["Cout"]
+                assert d["Nh"] % 16 == 0 and N % d["Nh"] == 0 and d["nsplit"] == N // d["Nh"], ctx
+                assert d["m_tiles"] * 128 >= B and d["tmem_cols"] >= d["Nh"] and d["tmem_cols"] in (32, 64, 128, 256, 512), ctx
+                assert 2 <= d["na"] <= 8 and d["na"] * (d["a_stage_bytes"] + d["b_stage_bytes"]) <= d["smem"] <= 227 * 1024, ctx
+                cin = d["Cin0"] + d["Cin1"]
+                assert d["nchunks"] >= -(-cin // 64), ctx
+                continue
             # column tiling
             assert d["Nh"] % 16 == 0 and 16 <= d["Nh"] <= 256, ctx
             assert (d["nsplit"] - 1) * d["Nh"] < d["Npad"] <= d["nsplit"] * d["Nh"], ctx

@@ -203,8 +203,9 @@ struct TcParams {
     int B, L, Cout, T;
     int Cin0, Cin1;            // K segments: ENC: Cin0 = Cin, Cin1 = 0; DEC: Cin0 = upsampled prev, Cin1 = skip
     int nchunks0, nchunks;     // 64-channel chunks in segment 0 / in total
-    unsigned char chunk_map[48]; // K-loop order: bit 7 = chunk of the upsampled segment, bits 0-5 = chunk index inside its segment;
-                                 // bit 6: merged tail chunk (MG kernels) / low-part data (split-precision kernels)
+    unsigned char chunk_map[48]; // K-loop order: bit 7 = chunk of the upsampled segment, bits 0-4 = chunk index inside its segment;
+                                 // bit 6: merged tail chunk (MG kernels) / low-part data (split-precision kernels); bit 5 (split
+                                 // precision): the position re-uses the operand stage of the position before it
     // N tiling
     int Npad, Nh, Nstride;     // padded Cout, columns per CTA, TMEM column stride between sub-tile accumulators
     // M tiling
@@ -262,18 +263,19 @@ __host__ __device__ inline SmemMap smem_map(const TcParams &p)
 inline size_t smem_total(const TcParams &p) { return smem_map(p).bars + 8 * (8 + 2 * kMaxBStages + 4) + 16 + (p.mg ? 32 : 0) + 1024; }
 
 // K-loop position c -> (segment, chunk index inside the segment, K16 steps, 64-wide slot in the packed weights)
-struct ChunkInfo { bool up; int idx, nk, kslot; bool merged; int vo, nvec; bool lo; };
+struct ChunkInfo { bool up; int idx, nk, kslot; bool merged; int vo, nvec; bool lo, reuse; };
 template <bool UPCAT, int MG, int SP = 0>
 __device__ __forceinline__ ChunkInfo chunk_info(const TcParams &p, int c)
 {
     ChunkInfo ci;
     const int m = p.chunk_map[c];
-    ci.lo = false;
+    ci.lo = false; ci.reuse = false;
     if (SP != 0) {                                // split precision: the weight slot is the K-loop position itself
         ci.merged = false;
         ci.up = UPCAT && (m & 0x80);
         ci.lo = (m & 0x40) != 0;
-        ci.idx = m & 0x3f;
+        ci.reuse = (m & 0x20) != 0;                // same operand stage as the position before (hi data x w_lo after hi data x w_hi)
+        ci.idx = m & 0x1f;
         const int seg = (ci.up || !UPCAT) ? p.Cin0 - 64 * ci.idx : p.Cin1 - 64 * ci.idx;
         ci.nk = ((seg < 64 ? seg : 64) + 15) >> 4;
         ci.kslot = c;
@@ -392,6 +394,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 int b0, l0, n0;
                 tile_coords(a_tile, b0, l0, n0);
                 const ChunkInfo aci = chunk_info<UPCAT, MG, SP>(p, a_c);
+                if (SP != 0 && aci.reuse) {                      // no new operand data: the stage of the previous position is used again
+                    if (++a_c == p.nchunks) { a_c = 0; a_tile += gridDim.x; }
+                    return true;
+                }
                 const bool from_tma = !aci.up;
                 TRACE(0, tr0);
                 mbar_wait(a_empty + 8 * sa, pa ^ 1);
@@ -479,10 +485,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t acc_col = tmem_base + buf * p.MT * p.Nstride;
                 for (int c = 0; c < p.nchunks; ++c) {
-                    const int nk = chunk_info<UPCAT, MG, SP>(p, c).nk;
-                    mbar_wait(a_full + 8 * sa, pa);
-                    TRACE(1, tr1);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const ChunkInfo mci = chunk_info<UPCAT, MG, SP>(p, c);
+                    const int nk = mci.nk;
+                    if (!(SP != 0 && mci.reuse)) {
+                        mbar_wait(a_full + 8 * sa, pa);
+                        TRACE(1, tr1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    }
                     const uint32_t a_base = base + sm.a + sa * p.a_stage_bytes;
                     uint32_t a_lo = ((a_base >> 4) & 0x3FFFu) | (1u << 16);
                     for (int g = 0; g < p.ngroups; ++g) {
@@ -507,8 +516,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (!p.resident) umma_commit(b_empty + 8 * sb);
                         if (++sb == p.nb) { sb = 0; pb ^= 1; }
                     }
-                    umma_commit(a_empty + 8 * sa);
-                    if (++sa == p.na) { sa = 0; pa ^= 1; }
+                    // split precision: the next position may multiply the same operand stage with the low weight part
+                    if (!(SP != 0 && c + 1 < p.nchunks && chunk_info<UPCAT, MG, SP>(p, c + 1).reuse)) {
+                        umma_commit(a_empty + 8 * sa);
+                        if (++sa == p.na) { sa = 0; pa ^= 1; }
+                    }
                 }
                 umma_commit(acc_full + 8 * buf);
             }
@@ -703,6 +715,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int b0, l0, n0;
             tile_coords(tile, b0, l0, n0);
             for (int c = 0; c < p.nchunks; ++c) {
+                if (SP != 0 && chunk_info<UPCAT, MG, SP>(p, c).reuse) continue;      // no new operand data for this position
                 const bool fast = unit_fast(c);
                 if (fast && !pref) fetch(b0, l0, c, pt);
                 if (pt == 0) TRACE(4, tr4);
@@ -1225,6 +1238,195 @@ __global__ void pack_tn_kernel(const float *__restrict__ w, __nv_bfloat16 *__res
 }
 
 // -------------------------------------------------------------------------------------------------
+// bottom of the U (frames of at most 16 samples): the block as ONE dense GEMM over frames
+// -------------------------------------------------------------------------------------------------
+// With L <= 16 the implicit GEMM over positions wastes 60-80 % of its MMA rows on per-frame halos and cannot fill the SMs.
+// Here the frames are the GEMM rows: the channels-last activations ARE the matrix [B][L*C],
+//     Y[b][(l, co)] = sum_(l', ci) X[b][(l', ci)] * W'[(l, co)][(l', ci)],
+// with Toeplitz-expanded weights W'[(l,co)][(l',ci)] = w[co][ci][l'-l+pad] (zero outside the taps; built once per weight
+// update by expand_*_kernel). An encoder's decimation is the tensor map's row stride; a decoder's linear interpolation is
+// folded into the expanded weights of its upsampled input (W * U, in fp32, then bf16), so both of its sources are plain TMA
+// operands and there are no producer warps. One CTA = 128 frames x Nh output columns; K runs over 64-channel chunks of the
+// input positions that reach the CTA's output positions (the band), several chunks per pipeline stage.
+struct GemmParams {
+    int B, N, Nh;                  // rows (frames), output columns (= L * Cout), columns per CTA
+    int cout;                      // channels per output position (the folded BatchNorm vector repeats with this period)
+    int L;                         // output positions
+    // two sources: chunk list = [source 0 positions x 64-channel chunks | source 1 positions x chunks]; weight K slot = global index
+    int npos[2], cpp[2];           // input positions, 64-channel chunks per position
+    int reach_lo[2], reach_hi[2];  // input positions [l_lo + reach_lo, l_hi + reach_hi] reach output positions [l_lo, l_hi]; for a
+    int halve[2];                  // half-resolution source (decoder: previous block) the output range is halved first
+    int nstages, cps;              // ring depth, K chunks per stage
+    uint32_t a_bytes, w_bytes, tmem_cols;
+    const float2 *ss;              // [cout] folded BatchNorm (scale, shift)
+    __nv_bfloat16 *out;            // [B][N]
+};
+
+__global__ void __launch_bounds__(192, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtensorMap tmW,
+               const GemmParams p)
+{
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t *base_ptr = smem_raw + (base - smem_u32(smem_raw));
+    // a stage holds `cps` consecutive K chunks: [A: cps x 16 KB (128 frames x 64 channels each) | W: cps x w_bytes]. Every stage
+    // hand-off idles the tensor pipe for a few hundred cycles and a chunk is only 4 short MMAs: fat stages amortise it.
+    const uint32_t stage_bytes = (uint32_t)p.cps * (16384u + p.w_bytes);
+    const uint32_t bars = base + (uint32_t)p.nstages * stage_bytes;                 // full[8] empty[8] acc | tmem slot
+    const uint32_t full = bars, empty = bars + 64, acc_full = bars + 128, tmem_slot = bars + 136;
+    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(base_ptr + (size_t)p.nstages * stage_bytes + 136);
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * p.Nh, b0 = blockIdx.y * 128;
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm0)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
+        for (int s = 0; s < 8; ++s) { mbar_init(full + 8 * s, 1); mbar_init(empty + 8 * s, 1); }
+        mbar_init(acc_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 5) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
+    // the band: input positions of each source that reach this CTA's output positions
+    const int l_lo = n0 / p.cout, l_hi = min(p.N - 1, n0 + p.Nh - 1) / p.cout;
+    int plo[2], cnt[2], nch = 0;
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const int a = p.halve[s] ? (l_lo >> 1) : l_lo, b = p.halve[s] ? (l_hi >> 1) : l_hi;
+        plo[s] = max(0, a + p.reach_lo[s]);
+        const int phi = min(p.npos[s] - 1, b + p.reach_hi[s]);
+        cnt[s] = p.npos[s] > 0 ? (phi - plo[s] + 1) * p.cpp[s] : 0;
+        nch += cnt[s];
+    }
+    const int nst = (nch + p.cps - 1) / p.cps;                   // stages of this CTA's K loop
+    const int n_this = min(p.Nh, p.N - n0);
+    if (warp == 4) {
+        if (lane == 0) {
+            for (int it = 0; it < nst; ++it) {
+                const uint32_t st = (uint32_t)it % (uint32_t)p.nstages, ph = ((uint32_t)it / (uint32_t)p.nstages) & 1u;
+                const int k0 = it * p.cps, kn = min(p.cps, nch - k0);
+                mbar_wait(empty + 8 * st, ph ^ 1);
+                mbar_expect_tx(full + 8 * st, (uint32_t)kn * (16384u + (uint32_t)p.Nh * 128u));
+                const uint32_t dst = base + st * stage_bytes;
+                for (int j = 0; j < kn; ++j) {
+                    int k = k0 + j, s = 0;
+                    if (k >= cnt[0]) { k -= cnt[0]; s = 1; }
+                    const int pos = plo[s] + k / p.cpp[s], cc = k % p.cpp[s];
+                    const int kslot = (s == 0 ? 0 : p.npos[0] * p.cpp[0]) + pos * p.cpp[s] + cc;
+                    tma_load_3d(dst + (uint32_t)j * 16384u, s == 0 ? &tm0 : &tm1, full + 8 * st, cc * 64, pos, b0);
+                    tma_load_3d(dst + (uint32_t)p.cps * 16384u + (uint32_t)j * p.w_bytes, &tmW, full + 8 * st, kslot * 64, n0, 0);
+                }
+            }
+        }
+    } else if (warp == 5) {
+        if (elect_one()) {
+            const uint32_t hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Nh >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            for (int it = 0; it < nst; ++it) {
+                const uint32_t st = (uint32_t)it % (uint32_t)p.nstages, ph = ((uint32_t)it / (uint32_t)p.nstages) & 1u;
+                const int kn = min(p.cps, nch - it * p.cps);
+                mbar_wait(full + 8 * st, ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a0 = (((base + st * stage_bytes) >> 4) & 0x3FFFu) | (1u << 16);
+                const uint32_t w0 = (((base + st * stage_bytes + (uint32_t)p.cps * 16384u) >> 4) & 0x3FFFu) | (1u << 16);
+#pragma unroll 1
+                for (int j = 0; j < kn; ++j) {
+                    const uint32_t a_lo = a0 + (uint32_t)j * 1024u, b_lo = w0 + (uint32_t)j * (p.w_bytes >> 4);
+                    umma_bf16_lohi(tmem_base, a_lo, b_lo, hi, idesc, (it | j) ? 1u : 0u);
+                    umma_bf16_lohi(tmem_base, a_lo + 2, b_lo + 2, hi, idesc, 1u);
+                    umma_bf16_lohi(tmem_base, a_lo + 4, b_lo + 4, hi, idesc, 1u);
+                    umma_bf16_lohi(tmem_base, a_lo + 6, b_lo + 6, hi, idesc, 1u);
+                }
+                umma_commit(empty + 8 * st);
+            }
+            umma_commit(acc_full);
+        }
+    } else {
+        // epilogue: warp q owns TMEM lanes (= frames) 32 q .. 32 q + 31
+        const int q = warp;
+        mbar_wait(acc_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int b = b0 + q * 32 + lane;
+#pragma unroll 1
+        for (int c16 = 0; c16 < n_this; c16 += 16) {
+            uint32_t v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c16, v);
+            uint32_t o[8];
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+                const int n = n0 + c16 + j;
+                const float2 s0 = __ldg(p.ss + n % p.cout), s1 = __ldg(p.ss + (n + 1) % p.cout);
+                o[j >> 1] = pack_bf16(lrelu(fmaf(__uint_as_float(v[j]), s0.x, s0.y)), lrelu(fmaf(__uint_as_float(v[j + 1]), s1.x, s1.y)));
+            }
+            if (b < p.B) {
+                uint4 *dst = reinterpret_cast<uint4 *>(p.out + (size_t)b * p.N + n0 + c16);
+                dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+                dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 5) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols));
+}
+
+// Toeplitz expansion of a block's weights for gemm_tc_kernel: wx[n = l * Cout + co][k], K slots of 64 channels:
+//   encoder / middle (dec = 0): slot (l' * cpp0 + cc) holds channels cc*64.. of input position l', value w[co][ci][l' - l + pad]
+//   decoder (dec = 1): source 0 = previous block at half resolution (position m), value sum_l' w[co][ci][l'-l+pad] U[l'][m] with
+//     U = F.interpolate(scale_factor=2, linear, align_corners=True) (fp32 index math as ATen: i0 = int(l' s), lam = l' s - i0);
+//     source 1 = skip at position l', channels offset by Cin0 in w.
+__global__ void expand_gemm_weights_kernel(const float *__restrict__ w, __nv_bfloat16 *__restrict__ wx, int Cout, int Cin0, int Cin1, int K,
+                                           int L, int dec, int npos0, int cpp0, int npos1, int cpp1, float up_scale)
+{
+    const int Ktot = (npos0 * cpp0 + npos1 * cpp1) * 64;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)L * Cout * Ktot) return;
+    const int k = (int)(i % Ktot);
+    const int n = (int)(i / Ktot);
+    const int l = n / Cout, co = n - l * Cout;
+    const int pad = (K - 1) / 2, Cin = Cin0 + Cin1;
+    int slot = k >> 6;
+    const int j = k & 63;
+    float v = 0.f;
+    if (slot < npos0 * cpp0) {
+        const int pos = slot / cpp0, ci = (slot - pos * cpp0) * 64 + j;
+        if (ci < Cin0) {
+            if (!dec) {
+                const int t = pos - l + pad;
+                if (t >= 0 && t < K) v = w[((size_t)co * Cin + ci) * K + t];
+            } else {
+                const int Lin = npos0;
+                for (int t = 0; t < K; ++t) {
+                    const int lp = l + t - pad;
+                    if (lp < 0 || lp >= L) continue;
+                    const float s = up_scale * (float)lp;
+                    const int i0 = (int)s;
+                    const int i1 = i0 + (i0 < Lin - 1 ? 1 : 0);
+                    const float lam1 = s - (float)i0, lam0 = 1.f - lam1;
+                    const float wv = w[((size_t)co * Cin + ci) * K + t];
+                    if (i0 == pos) v = fmaf(wv, lam0, v);
+                    if (i1 == pos) v = fmaf(wv, lam1, v);
+                }
+            }
+        }
+    } else {
+        slot -= npos0 * cpp0;
+        const int pos = slot / cpp1, ci = (slot - pos * cpp1) * 64 + j;
+        const int t = pos - l + pad;
+        if (ci < Cin1 && t >= 0 && t < K) v = w[((size_t)co * Cin + Cin0 + ci) * K + t];
+    }
+    wx[i] = __float2bfloat16_rn(v);
+}
+
+// -------------------------------------------------------------------------------------------------
 // enc0: Conv1d(1 -> C, k=15) + BN + LeakyReLU on CUDA cores (Cin = 1: K = 15, HBM-bound), fp32 in, bf16 NLC out
 // -------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256, 4) enc0_kernel(const float *__restrict__ x, const float *__restrict__ w /*[C][1][15]*/,
@@ -1407,6 +1609,10 @@ struct TcLevel {
                                        // one extra 64-wide K slot at the end of the packed weights (0 = not merged)
     __nv_bfloat16 *wp = nullptr;
     float2 *ss = nullptr;
+    float *w_f32 = nullptr;            // library-owned fp32 copy of the block's weights (source of the expansions made at plan time)
+    __nv_bfloat16 *wx = nullptr;       // Toeplitz-expanded weights of the dense bottom-of-U GEMM (gemm_tc_kernel), built for wx_L positions
+    int wx_L = 0;
+    size_t wx_elems = 0;
     __nv_bfloat16 *wp_sp = nullptr;    // split-precision packing [K][Npad][sp_chunks * 64] (sp_chunk_order lists the K-loop positions)
     int sp_chunks = 0;
     // taps-in-N variant (conv_tn_kernel): eligible blocks keep a second packed copy [tn_npad][tn_slots * 64]
@@ -1421,6 +1627,8 @@ static int sp_chunk_order(const TcLevel &lv, bool dec, unsigned char *map, Split
 
 struct TcPlanLevel {
     TcParams p;
+    GemmParams gp;                     // is_gemm: the block runs gemm_tc_kernel (tmA / tmO = its two sources, tmW = expanded weights)
+    bool is_gemm = false;
     TnParams tn;                       // is_tn: the block runs conv_tn_kernel (tmA / tmW are its maps, p is unused)
     bool is_tn = false;
     CUtensorMap tmA, tmW, tmO;
@@ -1430,6 +1638,7 @@ struct TcPlanLevel {
     size_t smem;
     bool upcat;
     bool small;                        // two-CTAs-per-SM kernel flavour
+    int kind = 0;                      // reported by wunet_debug_plan in the 'small' field: 2 = dense GEMM over frames (gemm_tc_kernel)
 };
 
 // Per-block tiling overrides for tuning sweeps: WUNET_TC_OVR="<block>:key=val,key=val;<block>:..." with keys
@@ -1497,6 +1706,7 @@ struct TcState {
     bool attr_set = false;
     bool pdl = false;                  // programmatic dependent launch between the blocks (WUNET_TC_PDL=1); measured slower, off
     bool merge = true;                 // merged tail chunks (WUNET_TC_MERGE=0 switches them off for A/B measurements)
+    bool gemm = true;                  // dense GEMM over frames for blocks of at most 16 samples (WUNET_TC_GEMM=0 switches it off)
     bool tn = false;                   // taps-in-N kernel for the shallow blocks: correct but not yet faster than conv_tc_kernel on a B200
                                        // (profiles/r02_tn_*.txt), so opt-in: WUNET_TC_TN=1
     int num_sms = 148;
@@ -1589,6 +1799,7 @@ int tc_set_weights(TcState **pst, int n, int ci, const TcBlockSrc *blocks, int n
         st->pdl = pe && pe[0] == '1';
         if (const char *xe = getenv("WUNET_TC_MERGE")) st->merge = xe[0] != '0';
         if (const char *xe = getenv("WUNET_TC_TN")) st->tn = xe[0] == '1';
+        if (const char *xe = getenv("WUNET_TC_GEMM")) st->gemm = xe[0] != '0';
 #ifdef WUNET_TC_TRACE
         if (const char *tl = getenv("WUNET_TC_TRACE_LEVEL")) {
             st->trace_level = atoi(tl);
@@ -1622,6 +1833,13 @@ int tc_set_weights(TcState **pst, int n, int ci, const TcBlockSrc *blocks, int n
         pack_tc_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, stream>>>(blocks[i].w, blocks[i].scale, blocks[i].shift, lv.wp,
                                                                           lv.ss, lv.cout, lv.cin0, lv.cin1, lv.k, lv.Npad, lv.Ktot);
         if (cudaGetLastError() != cudaSuccess) return tc_fail("pack_tc_kernel launch failed");
+        {
+            const size_t wn = (size_t)lv.cout * (lv.cin0 + lv.cin1) * lv.k;
+            if (!lv.w_f32 && cudaMalloc(&lv.w_f32, wn * sizeof(float)) != cudaSuccess) return tc_fail("cudaMalloc(w_f32) failed");
+            if (cudaMemcpyAsync(lv.w_f32, blocks[i].w, wn * sizeof(float), cudaMemcpyDeviceToDevice, stream) != cudaSuccess)
+                return tc_fail("weight copy failed");
+            lv.wx_L = 0;                                   // expansions are rebuilt with the next plan
+        }
         {
             // split-precision packing (fp32_tc): [K][Npad][positions * 64] in the split K-loop order
             SplitTable tab;
@@ -1679,9 +1897,9 @@ static int make_map(TcState *st, CUtensorMap *m, const void *base, uint64_t d0, 
     return 0;
 }
 
-// K-loop order of a block in split-precision mode: three passes over the single-precision order (encoders: natural; decoders:
-// full upsampled chunks, skip chunks, partial upsampled chunk - or the partial one first if it is the only one): hi data x
-// w_hi, lo data x w_hi, hi data x w_lo. Fills chunk_map bytes (bit 7 upsampled segment, bit 6 low data part, bits 0-5 chunk
+// K-loop order of a block in split-precision mode, built from the single-precision order (encoders: natural; decoders: full
+// upsampled chunks, skip chunks, partial upsampled chunk - or the partial one first if it is the only one): every chunk's hi
+// data x w_hi followed by the same operand stage x w_lo, then every chunk's lo data x w_hi. Fills chunk_map bytes (bit 7 upsampled segment, bit 6 low data part, bits 0-5 chunk
 // index) and the table the weight packing follows. Returns the number of positions.
 static int sp_chunk_order(const TcLevel &lv, bool dec, unsigned char *map, SplitTable *tab)
 {
@@ -1698,18 +1916,20 @@ static int sp_chunk_order(const TcLevel &lv, bool dec, unsigned char *map, Split
         if (nfull0 < n0) one[k++] = (unsigned char)(0x80 | nfull0);
     }
     int n = 0;
-    for (int pass = 0; pass < 3; ++pass)
-        for (int c = 0; c < k; ++c, ++n) {
-            const bool up = dec && (one[c] & 0x80);
-            const int idx = one[c] & 0x3f;
-            if (map) map[n] = (unsigned char)(one[c] | (pass == 1 ? 0x40 : 0));
-            if (tab) {
-                const int seg = (up || !dec) ? lv.cin0 : lv.cin1;
-                tab->base[n] = (short)(((up || !dec) ? 0 : lv.cin0) + 64 * idx);
-                tab->width[n] = (unsigned char)std::min(64, seg - 64 * idx);
-                tab->wlo[n] = (unsigned char)(pass == 2);
-            }
+    auto put = [&](int c, bool lo_data, bool w_lo, bool reuse) {
+        const bool up = dec && (one[c] & 0x80);
+        const int idx = one[c] & 0x1f;
+        if (map) map[n] = (unsigned char)(one[c] | (lo_data ? 0x40 : 0) | (reuse ? 0x20 : 0));
+        if (tab) {
+            const int seg = (up || !dec) ? lv.cin0 : lv.cin1;
+            tab->base[n] = (short)(((up || !dec) ? 0 : lv.cin0) + 64 * idx);
+            tab->width[n] = (unsigned char)std::min(64, seg - 64 * idx);
+            tab->wlo[n] = (unsigned char)w_lo;
         }
+        ++n;
+    };
+    for (int c = 0; c < k; ++c) { put(c, false, false, false); put(c, false, true, true); }     // hi data x w_hi, then x w_lo on the same stage
+    for (int c = 0; c < k; ++c) put(c, true, false, false);                                    // lo data x w_hi
     if (tab) tab->n = n;
     return n;
 }
@@ -1919,6 +2139,53 @@ static int plan_block(const TcLevel &lv, int i, int n, int B, int T, int num_sms
     return 0;
 }
 
+// Dense GEMM over frames for a block of at most 16 samples (gemm_tc_kernel). Host logic only: shapes and the launch grid.
+static bool plan_block_gemm(const TcLevel &lv, int i, int n, int B, int T, int num_sms, TcPlanLevel &P)
+{
+    const bool dec = i > n;
+    const int L = (i <= n) ? (T >> i) : (T >> (2 * n - i));
+    if (i < 1 || L > 16 || L < 1 || lv.cout % 8 != 0 || lv.cin0 % 8 != 0 || lv.cin1 % 8 != 0) return false;
+    if (i == 2 * n) return false;                               // the last block carries the fused head
+    GemmParams &g = P.gp;
+    memset(&g, 0, sizeof(g));
+    g.B = B; g.L = L; g.cout = lv.cout; g.N = L * lv.cout;
+    if (g.N % 16 != 0) return false;
+    // columns per CTA: a multiple of 16 that divides N, giving about one CTA per SM (times the 256-frame row tiles)
+    const int mtiles = (B + 127) / 128;
+    int best = 16;
+    for (int nh = 16; nh <= 256; nh += 16)
+        if (g.N % nh == 0 && (g.N / nh) * mtiles >= num_sms * 3 / 4) best = nh;
+    g.Nh = best;
+    const int pad = (lv.k - 1) / 2;
+    if (!dec) {
+        g.npos[0] = L; g.cpp[0] = (lv.cin0 + 63) / 64; g.reach_lo[0] = -pad; g.reach_hi[0] = pad; g.halve[0] = 0;
+        g.npos[1] = 0; g.cpp[1] = 0;
+    } else {
+        g.npos[0] = L / 2; g.cpp[0] = (lv.cin0 + 63) / 64; g.reach_lo[0] = -2; g.reach_hi[0] = 2; g.halve[0] = 1;
+        g.npos[1] = L; g.cpp[1] = (lv.cin1 + 63) / 64; g.reach_lo[1] = -pad; g.reach_hi[1] = pad; g.halve[1] = 0;
+        if (g.npos[0] < 1) return false;
+    }
+    g.a_bytes = 16384; g.w_bytes = (uint32_t)round_up(g.Nh * 128, 1024);
+    g.cps = 4;
+    int ns = (kSmemLimit - 2048) / (int)(g.cps * (g.a_bytes + g.w_bytes));
+    while (ns < 2 && g.cps > 1) { --g.cps; ns = (kSmemLimit - 2048) / (int)(g.cps * (g.a_bytes + g.w_bytes)); }
+    g.nstages = std::min(4, std::max(2, ns));
+    uint32_t cols = 32;
+    while ((int)cols < g.Nh) cols <<= 1;
+    g.tmem_cols = cols;
+    P.is_gemm = true; P.upcat = dec; P.small = false; P.per_sm = 1; P.threads = 192;
+    P.kind = 2;
+    P.smem = (size_t)g.nstages * g.cps * (g.a_bytes + g.w_bytes) + 8 * 20 + 1024;
+    P.grid = dim3((unsigned)(g.N / g.Nh), (unsigned)mtiles, 1);
+    TcParams &p = P.p;                                          // mirror what tests / tools read
+    memset(&p, 0, sizeof(p));
+    p.B = B; p.L = L; p.T = T; p.Cout = lv.cout; p.Cin0 = lv.cin0; p.Cin1 = lv.cin1; p.Npad = lv.Npad; p.Nh = g.Nh; p.nsplit = g.N / g.Nh;
+    p.Nstride = g.Nh; p.MT = 1; p.nacc = 1; p.FR = 128; p.packed = 1; p.S = L; p.m_tiles = mtiles; p.nchunks = g.npos[0] * g.cpp[0] + g.npos[1] * g.cpp[1];
+    p.na = g.nstages; p.nb = g.nstages; p.tg = 1; p.ngroups = 1; p.a_stage_bytes = g.cps * g.a_bytes; p.b_stage_bytes = g.cps * g.w_bytes;
+    p.a_tx_bytes = (int)(g.cps * g.a_bytes); p.rows_used = 128; p.tmem_cols = cols; p.tile_begin = 0; p.tile_end = p.m_tiles * p.nsplit; p.n_epi = 4;
+    return true;
+}
+
 // Tiling of a taps-in-N block (conv_tn_kernel): pure host logic like plan_block. Returns false if the block does not take
 // this path at this shape (frames shorter than a tile, channel plan not eligible).
 static bool plan_block_tn(const TcLevel &lv, int i, int n, int B, int T, int num_sms, TcPlanLevel &P)
@@ -1992,7 +2259,7 @@ static bool plan_block_tn(const TcLevel &lv, int i, int n, int B, int T, int num
     return true;
 }
 
-static int build_plan(TcState *st, const float *x, float *y, int B, int T, void *ws, int mode)
+static int build_plan(TcState *st, const float *x, float *y, int B, int T, void *ws, int mode, cudaStream_t stream)
 {
     const int n = st->n;
     TcPlan &pl = st->plan;
@@ -2006,6 +2273,38 @@ static int build_plan(TcState *st, const float *x, float *y, int B, int T, void 
     for (int i = 1; i < 2 * n + 1; ++i) {
         const TcLevel &lv = st->levels[i];
         TcPlanLevel &P = pl.lv[i];
+        if (!sp && st->gemm && parse_override(st->plan_ovr, i).any == false && plan_block_gemm(lv, i, n, B, T, st->num_sms, P)) {
+            GemmParams &g = P.gp;
+            TcLevel &lw = st->levels[i];
+            const bool dec = i > n;
+            const int ktot = (g.npos[0] * g.cpp[0] + g.npos[1] * g.cpp[1]) * 64;
+            const size_t need = (size_t)g.N * ktot;
+            if (lw.wx_L != g.L) {                              // (re)build the Toeplitz expansion for this frame length
+                if (lw.wx_elems < need) {
+                    cudaFree(lw.wx); lw.wx = nullptr; lw.wx_elems = 0;
+                    if (cudaMalloc(&lw.wx, need * sizeof(__nv_bfloat16)) != cudaSuccess) return tc_fail("cudaMalloc(expanded weights) failed");
+                    lw.wx_elems = need;
+                }
+                const float up = (dec && g.L > 1) ? (float)(g.L / 2 - 1) / (float)(g.L - 1) : 0.f;
+                expand_gemm_weights_kernel<<<(unsigned)((need + 255) / 256), 256, 0, stream>>>(lw.w_f32, lw.wx, lv.cout, lv.cin0, lv.cin1, lv.k, g.L,
+                                                                                               dec ? 1 : 0, g.npos[0], g.cpp[0], g.npos[1], g.cpp[1], up);
+                if (cudaGetLastError() != cudaSuccess) return tc_fail("expand_gemm_weights_kernel launch failed");
+                lw.wx_L = g.L;
+            }
+            g.ss = lv.ss; g.out = lvl(i);
+            if (!dec) {
+                const int Cp = lv.cin0, Lp = 2 * g.L;           // decimated view of the previous block's output
+                if (make_map(st, &P.tmA, lvl(i - 1), Cp, g.L, B, (uint64_t)2 * Cp * 2, (uint64_t)Lp * Cp * 2, 64, 1, 128)) return -1;
+                P.tmO = P.tmA;
+            } else {
+                const int e = 2 * n - i, Cs = lv.cin1, Cq = lv.cin0;
+                if (make_map(st, &P.tmA, lvl(i - 1), Cq, g.L / 2, B, (uint64_t)Cq * 2, (uint64_t)(g.L / 2) * Cq * 2, 64, 1, 128)) return -1;
+                if (make_map(st, &P.tmO, lvl(e), Cs, g.L, B, (uint64_t)Cs * 2, (uint64_t)g.L * Cs * 2, 64, 1, 128)) return -1;
+            }
+            if (make_map(st, &P.tmW, lw.wx, (uint64_t)ktot, (uint64_t)g.N, 1, (uint64_t)ktot * 2, (uint64_t)g.N * ktot * 2, 64, (uint32_t)g.Nh, 1))
+                return -1;
+            continue;
+        }
         if (!sp && parse_override(st->plan_ovr, i).any == false && plan_block_tn(lv, i, n, B, T, st->num_sms, P)) {
             TnParams &t = P.tn;
             const bool dec = i > n;
@@ -2064,6 +2363,12 @@ static int build_plan(TcState *st, const float *x, float *y, int B, int T, void 
     if (getenv("WUNET_TC_DEBUG")) {
         for (int i = 1; i < 2 * n + 1; ++i) {
             const TcParams &p = pl.lv[i].p;
+            if (pl.lv[i].is_gemm) {
+                const GemmParams &g = pl.lv[i].gp;
+                fprintf(stderr, "[wunet gemm] blk %2d L=%2d N=%5d Nh=%3d K chunks=%d+%d stages=%d x %d chunks grid=%ux%u smem=%zu\n", i, g.L, g.N, g.Nh,
+                        g.npos[0] * g.cpp[0], g.npos[1] * g.cpp[1], g.nstages, g.cps, pl.lv[i].grid.x, pl.lv[i].grid.y, pl.lv[i].smem);
+                continue;
+            }
             if (pl.lv[i].is_tn) {
                 const TnParams &t = pl.lv[i].tn;
                 fprintf(stderr, "[wunet tn] blk %2d L=%5d Cin=%3d+%3d Cout=%3d N'=%3d MT=%d chunks=%d na=%d wpg=%d npg=%d smem=%zu tiles=%d grid=%u\n", i, t.L,
@@ -2091,18 +2396,21 @@ int tc_debug_plan(int n, int ci, const TcBlockSrc *blocks, int nblocks, int B, i
     const char *ovr = getenv("WUNET_TC_OVR");
     TcPlanLevel P{};
     const std::string ovr_s = ovr ? ovr : "";
+    const char *ge = getenv("WUNET_TC_GEMM");
+    if (!(ge && ge[0] == '0') && parse_override(ovr_s, block).any == false && plan_block_gemm(levels[block], block, n, B, T, num_sms, P)) {
+    } else
     if (!(parse_override(ovr_s, block).any == false && plan_block_tn(levels[block], block, n, B, T, num_sms, P)))
         if (plan_block(levels[block], block, n, B, T, num_sms, ovr_s, P)) return -1;
     const TcParams &p = P.p;
     const int v[32] = {p.L, p.Cin0, p.Cin1, p.Cout, p.Npad, p.Nh, p.nsplit, p.Nstride, p.MT, p.nacc, p.packed, p.FR, p.S, p.m_tiles,
                        p.nchunks, p.resident, p.bulk_store, p.na, p.nb, p.tg, p.ngroups, (int)p.a_stage_bytes, (int)p.b_stage_bytes,
-                       p.a_tx_bytes, p.rows_used, (int)p.tmem_cols, (int)P.smem, P.threads, P.per_sm, (int)P.grid.x, (int)P.small,
+                       p.a_tx_bytes, p.rows_used, (int)p.tmem_cols, (int)P.smem, P.threads, P.per_sm, (int)P.grid.x, P.kind == 2 ? 2 : (int)P.small,
                        p.tiles_per_frame};
     for (int k = 0; k < 32; ++k) f[k] = v[k];
     return 0;
 }
 
-static int tc_prepare(TcState *st, const float *x, float *y, int B, int T, void *ws, int mode)
+static int tc_prepare(TcState *st, const float *x, float *y, int B, int T, void *ws, int mode, cudaStream_t stream)
 {
     if (!st) return tc_fail("tensor-core state missing");
     const int ci = st->ci;
@@ -2116,6 +2424,7 @@ static int tc_prepare(TcState *st, const float *x, float *y, int B, int T, void 
         cudaFuncSetAttribute(conv_tc_kernel<5, true, kEpiWarpsSmall, kProducerWarpsSmall, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         cudaFuncSetAttribute(conv_tc_kernel<5, true, kEpiWarpsLarge, kProducerWarpsLarge, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         cudaFuncSetAttribute(conv_tc_kernel<15, false, kEpiWarpsLarge, 0, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+        cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         cudaFuncSetAttribute(conv_tn_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         cudaFuncSetAttribute(conv_tn_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
 #ifdef WUNET_TN_DEBUG
@@ -2134,7 +2443,7 @@ static int tc_prepare(TcState *st, const float *x, float *y, int B, int T, void 
     if (st->plan_ws != ws || st->plan_B != B || st->plan_T != T || st->plan_ovr != ovr_s || st->plan_mode != mode) {
         st->plan_ovr = ovr_s;
         st->plan_ws = nullptr;
-        if (build_plan(st, nullptr, nullptr, B, T, ws, mode)) return -1;
+        if (build_plan(st, nullptr, nullptr, B, T, ws, mode, stream)) return -1;
     }
     return 0;
 }
@@ -2165,6 +2474,18 @@ static int launch_enc0(TcState *st, const float *x, int f0, int nf, int T, void 
 static int launch_block(TcState *st, int i, int t0, int t1, cudaStream_t stream, const float *x = nullptr, float *y = nullptr)
 {
     TcPlanLevel &P = st->plan.lv[i];
+    if (P.is_gemm) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = P.grid; cfg.blockDim = dim3(P.threads); cfg.dynamicSmemBytes = P.smem; cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = st->pdl ? 1 : 0;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, gemm_tc_kernel, P.tmA, P.tmO, P.tmW, P.gp);
+        const cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return tc_fail("gemm_tc level %d launch failed: %s", i, cudaGetErrorString(e));
+        return 0;
+    }
     if (P.is_tn) {
         TnParams t = P.tn;
         t.x = x; t.y = y;
@@ -2221,7 +2542,7 @@ static int launch_block(TcState *st, int i, int t0, int t1, cudaStream_t stream,
 int tc_forward(TcState *st, const float *x, float *y, int B, int T, void *ws, cudaStream_t stream, int *launches,
                cudaEvent_t *ev, int mode)
 {
-    if (tc_prepare(st, x, y, B, T, ws, mode)) return -1;
+    if (tc_prepare(st, x, y, B, T, ws, mode, stream)) return -1;
     const int n = st->n;
     int nl = 0;
     if (ev) cudaEventRecord(ev[0], stream);
@@ -2243,7 +2564,7 @@ int tc_forward(TcState *st, const float *x, float *y, int B, int T, void *ws, cu
 int tc_forward_host(TcState *st, const float *x_host, float *y_host, float *x_dev, float *y_dev, int B, int T, void *ws,
                     cudaStream_t stream, int *launches, int mode)
 {
-    if (tc_prepare(st, x_dev, y_dev, B, T, ws, mode)) return -1;
+    if (tc_prepare(st, x_dev, y_dev, B, T, ws, mode, stream)) return -1;
     const int n = st->n;
     const TcParams &pl = st->plan.lv[2 * n].p;
     int nc = 1;
@@ -2325,7 +2646,7 @@ void tc_destroy(TcState *st)
         }
         cudaFree(st->trace);
     }
-    for (auto &lv : st->levels) { cudaFree(lv.wp); cudaFree(lv.ss); cudaFree(lv.w_own); cudaFree(lv.wp_tn); cudaFree(lv.wp_sp); }
+    for (auto &lv : st->levels) { cudaFree(lv.wp); cudaFree(lv.ss); cudaFree(lv.w_own); cudaFree(lv.wp_tn); cudaFree(lv.wp_sp); cudaFree(lv.w_f32); cudaFree(lv.wx); }
     delete st;
 }
 
