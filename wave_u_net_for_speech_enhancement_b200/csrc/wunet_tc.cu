@@ -2146,6 +2146,8 @@ static bool plan_block_gemm(const TcLevel &lv, int i, int n, int B, int T, int n
     const int L = (i <= n) ? (T >> i) : (T >> (2 * n - i));
     if (i < 1 || L > 16 || L < 1 || lv.cout % 8 != 0 || lv.cin0 % 8 != 0 || lv.cin1 % 8 != 0) return false;
     if (i == 2 * n) return false;                               // the last block carries the fused head
+    if (B < 64) return false;                                   // small batches: the expanded weights (up to 65 MB per block) would be
+                                                                // streamed for a mostly empty 128-frame row tile (B=3: 0.52 vs 0.46 ms)
     GemmParams &g = P.gp;
     memset(&g, 0, sizeof(g));
     g.B = B; g.L = L; g.cout = lv.cout; g.N = L * lv.cout;
