@@ -103,6 +103,10 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_n(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2)
 {
     asm volatile(
@@ -237,6 +241,8 @@ struct TcParams {
     long long *trace;          // WUNET_TC_TRACE builds: per-role clock64 stamps of CTA 0 (development)
     // merged tail chunk (MG = 1 instantiations): the last K chunk of a decoder block is [skip tail (TMA) | upsampled tail
     // (producers)] in ONE stage - one K chunk fewer for dec6 / dec9 / dec10 of the reference architecture
+    int pf_late;               // 1: the producers' register prefetch of their next unit is issued when the K loop reaches that unit (after the
+                               // TMA chunks in between have been handed on) instead of right after the previous unit's hand-off
     int split;                 // split-precision mode (SP kernels): activations are stored as [hi | lo] bf16 channel halves (2 C channels per
                                // row), the K loop runs [hi data x w_hi | lo data x w_hi | hi data x w_lo] and the epilogue stores hi and lo
     int mg;                    // 1: chunk_map's last entry (0x40) is such a merged chunk
@@ -410,6 +416,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         tma_load_3d(base + sm.a + sa * p.a_stage_bytes + op * p.R1 * 128, &tmA, a_full + 8 * sa,
                                     cc * 64 + ((SP != 0 && aci.lo) ? (UPCAT ? p.Cin1 : p.Cin0) : 0),      // low part: second channel half
                                     lcoord + op * p.R1, b0);
+
                 } else if (MG != 0 && aci.merged) {
                     // skip tail by TMA into the leading vectors of the stage (zero fill behind it), completion on a_tma: the
                     // producers add the upsampled tail once it has landed and complete a_full
@@ -714,8 +721,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int tile = first_tile; tile < total_tiles; tile += gridDim.x) {
             int b0, l0, n0;
             tile_coords(tile, b0, l0, n0);
-            for (int c = 0; c < p.nchunks; ++c) {
+            bool lo_done = false;                                                    // split precision: the lo stage of this chunk was
+            for (int c = 0; c < p.nchunks; ++c) {                                    // written together with its hi stage
                 if (SP != 0 && chunk_info<UPCAT, MG, SP>(p, c).reuse) continue;      // no new operand data for this position
+                if (SP != 0 && lo_done) {                                            // (already arrived on its barrier)
+                    lo_done = false;
+                    if (++sa == p.na) { sa = 0; pa ^= 1; }
+                    continue;
+                }
                 const bool fast = unit_fast(c);
                 if (fast && !pref) fetch(b0, l0, c, pt);
                 if (pt == 0) TRACE(4, tr4);
@@ -744,6 +757,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         // path, ATen index math in fp32
                         const int items = p.rows_used * nvec;
                         if (SP != 0) {
+                            // the chunk's lo-data position follows two positions later ([hi x w_hi, re-use x w_lo, lo x w_hi]): fill its
+                            // stage (the next one of the ring) from the same interpolation instead of computing everything twice
+                            const bool pair = !cu.lo && c + 2 < p.nchunks && p.chunk_map[c + 2] == (p.chunk_map[c] | 0x40) &&
+                                              (p.chunk_map[c + 1] & 0x20);
+                            int sa2 = sa + 1, pa2 = pa;
+                            if (sa2 == p.na) { sa2 = 0; pa2 ^= 1; }
+                            if (pair) mbar_wait(a_empty + 8 * sa2, pa2 ^ 1);
+                            uint8_t *dst2 = base_ptr + sm.a + sa2 * p.a_stage_bytes;
                             // split precision: prev rows are [hi | lo] (2 Cin0 channels); interpolate hi + lo in fp32 with the fp32
                             // path's formula (lam0 a + lam1 b), emit the high or the low bf16 part of the result. Two items per
                             // thread are in flight: their 8 loads are issued before the first is used (the unit is latency-bound).
@@ -782,7 +803,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                     const float lam0 = 1.f - lam1[u];
                                     const uint32_t ah[4] = {h0[u].x, h0[u].y, h0[u].z, h0[u].w}, al[4] = {l0v[u].x, l0v[u].y, l0v[u].z, l0v[u].w};
                                     const uint32_t bh[4] = {h1[u].x, h1[u].y, h1[u].z, h1[u].w}, bl[4] = {l1v[u].x, l1v[u].y, l1v[u].z, l1v[u].w};
-                                    uint32_t r[4];
+                                    uint32_t r[4], r2[4];
 #pragma unroll
                                     for (int q4 = 0; q4 < 4; ++q4) {
                                         const float2 fah = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&ah[q4]));
@@ -793,10 +814,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                         const float vy = lam0 * (fah.y + fal.y) + lam1[u] * (fbh.y + fbl.y);
                                         const float hx = __bfloat162float(__float2bfloat16_rn(vx)), hy = __bfloat162float(__float2bfloat16_rn(vy));
                                         r[q4] = cu.lo ? pack_bf16(vx - hx, vy - hy) : pack_bf16(vx, vy);
+                                        r2[q4] = pack_bf16(vx - hx, vy - hy);
                                     }
                                     *reinterpret_cast<uint4 *>(dst + row * 128 + ((vec ^ (row & 7)) << 4)) =
                                         ok[u] ? make_uint4(r[0], r[1], r[2], r[3]) : make_uint4(0u, 0u, 0u, 0u);
+                                    if (pair)
+                                        *reinterpret_cast<uint4 *>(dst2 + row * 128 + ((vec ^ (row & 7)) << 4)) =
+                                            ok[u] ? make_uint4(r2[0], r2[1], r2[2], r2[3]) : make_uint4(0u, 0u, 0u, 0u);
                                 }
+                            }
+                            if (pair) {
+                                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive(a_full + 8 * sa2);
+                                lo_done = true;
                             }
                         } else
                         for (int itx = pt; itx < items; itx += NPROD) {
@@ -831,7 +862,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (pt == 0) TRACE(4, tr4);
                 if (lane == 0) mbar_arrive(a_full + 8 * sa);
                 if (++sa == p.na) { sa = 0; pa ^= 1; }
-                if (emitted_fast) {
+                // (The producers arrive on EVERY chunk's barrier, also on TMA chunks they do not write: an mbarrier wait only tells the
+                // current phase from the previous one, and a role that skipped the barriers of several consecutive TMA chunks would
+                // lose track of the ring's phases - tried in round 2: dead-lock on the blocks with more skip chunks than stages.)
+                if (emitted_fast && !p.pf_late) {
                     // next upsampled unit of this CTA (K-loop order): prefetch its first-round item. Issued AFTER the hand-off:
                     // fence.proxy.async compiles to MEMBAR.ALL.CTA, which would otherwise hold the arrive back until these
                     // loads have returned (trace: ~1900 cycles per unit).
@@ -913,10 +947,6 @@ __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&v)[8]
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                  : "r"(taddr));
-}
-__device__ __forceinline__ void mbar_arrive_n(uint32_t bar, uint32_t count)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
 
 template <bool UPCAT, int DBG>
@@ -1706,6 +1736,7 @@ struct TcState {
     bool attr_set = false;
     bool pdl = false;                  // programmatic dependent launch between the blocks (WUNET_TC_PDL=1); measured slower, off
     bool merge = true;                 // merged tail chunks (WUNET_TC_MERGE=0 switches them off for A/B measurements)
+    bool pf_late = false;              // WUNET_TC_PFLATE=1: see TcParams::pf_late
     bool gemm = true;                  // dense GEMM over frames for blocks of at most 16 samples (WUNET_TC_GEMM=0 switches it off)
     bool tn = false;                   // taps-in-N kernel for the shallow blocks: correct but not yet faster than conv_tc_kernel on a B200
                                        // (profiles/r02_tn_*.txt), so opt-in: WUNET_TC_TN=1
@@ -1800,6 +1831,7 @@ int tc_set_weights(TcState **pst, int n, int ci, const TcBlockSrc *blocks, int n
         if (const char *xe = getenv("WUNET_TC_MERGE")) st->merge = xe[0] != '0';
         if (const char *xe = getenv("WUNET_TC_TN")) st->tn = xe[0] == '1';
         if (const char *xe = getenv("WUNET_TC_GEMM")) st->gemm = xe[0] != '0';
+        if (const char *xe = getenv("WUNET_TC_PFLATE")) st->pf_late = xe[0] == '1';
 #ifdef WUNET_TC_TRACE
         if (const char *tl = getenv("WUNET_TC_TRACE_LEVEL")) {
             st->trace_level = atoi(tl);
@@ -1898,8 +1930,8 @@ static int make_map(TcState *st, CUtensorMap *m, const void *base, uint64_t d0, 
 }
 
 // K-loop order of a block in split-precision mode, built from the single-precision order (encoders: natural; decoders: full
-// upsampled chunks, skip chunks, partial upsampled chunk - or the partial one first if it is the only one): every chunk's hi
-// data x w_hi followed by the same operand stage x w_lo, then every chunk's lo data x w_hi. Fills chunk_map bytes (bit 7 upsampled segment, bit 6 low data part, bits 0-5 chunk
+// upsampled chunks, skip chunks, partial upsampled chunk - or the partial one first if it is the only one): per chunk, hi
+// data x w_hi, the same operand stage x w_lo, lo data x w_hi. Fills chunk_map bytes (bit 7 upsampled segment, bit 6 low data part, bits 0-5 chunk
 // index) and the table the weight packing follows. Returns the number of positions.
 static int sp_chunk_order(const TcLevel &lv, bool dec, unsigned char *map, SplitTable *tab)
 {
@@ -1928,8 +1960,11 @@ static int sp_chunk_order(const TcLevel &lv, bool dec, unsigned char *map, Split
         }
         ++n;
     };
-    for (int c = 0; c < k; ++c) { put(c, false, false, false); put(c, false, true, true); }     // hi data x w_hi, then x w_lo on the same stage
-    for (int c = 0; c < k; ++c) put(c, true, false, false);                                    // lo data x w_hi
+    for (int c = 0; c < k; ++c) {
+        put(c, false, false, false);      // hi data x w_hi
+        put(c, false, true, true);        // the same operand stage x w_lo
+        put(c, true, false, false);       // lo data x w_hi (the next stage: the producers fill it together with the hi stage)
+    }
     if (tab) tab->n = n;
     return n;
 }
@@ -2517,6 +2552,7 @@ static int launch_block(TcState *st, int i, int t0, int t1, cudaStream_t stream,
     }
     TcParams p = P.p;
     p.x = x; p.y = y;                                    // only the fused head (last block) reads x / writes y
+    p.pf_late = st->pf_late ? 1 : 0;
     if (t1 >= 0) { p.tile_begin = t0; p.tile_end = t1; }
     const int ntiles = p.tile_end - p.tile_begin;
     cudaLaunchConfig_t cfg{};
