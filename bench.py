@@ -347,6 +347,29 @@ def run_train(ctx):
         comm = {"allreduce_ms_alone": round(time_steps(ar, 10), 4), "bucket_bytes": bucket.flat.numel() * 4,
                 "backend": dist.get_backend(), "nranks": dist.get_world_size(),
                 "overlap": "part 0 (head + decoder gradients) is reduced while part 1 (middle + encoders) is computed"}
+    # incumbent on the same GPU (rank 0, single-GPU runs): the same step with PyTorch eager (cuDNN) kernels and autograd
+    incumbent = None
+    if world == 1 and not args.no_incumbent:
+        del model, opt
+        torch.cuda.empty_cache()
+        mt = Model(N_LAYERS, CH_INT, train_backend="torch")
+        mt.load_state_dict(st, strict=True)
+        mt = mt.to(dev).train()
+        ot = torch.optim.Adam(mt.parameters(), lr=1e-3, betas=(0.9, 0.999))
+        torch.backends.cudnn.benchmark = True
+
+        def tstep(i):
+            ot.zero_grad()
+            lt = loss_fn(clean[i % NBUF], mt(noisy[i % NBUF]))
+            lt.backward()
+            ot.step()
+        incumbent = {"what": "the same step with PyTorch eager: cuDNN convolutions (TF32 allowed, torch default), ATen BatchNorm / "
+                             "interpolate / cat, autograd, torch.optim.Adam", "batch": B}
+        for tf32 in (True, False):
+            torch.backends.cudnn.allow_tf32 = tf32
+            ms_inc = time_steps(lambda: tstep(0), 5, warm=2)
+            incumbent["tf32" if tf32 else "fp32"] = {"ms_per_step": round(ms_inc, 3), "frames_per_s": round(B / ms_inc * 1e3, 1)}
+        torch.backends.cudnn.allow_tf32 = True
     t = torch.tensor([ms_total, dt_e2e], device=dev, dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -363,7 +386,7 @@ def run_train(ctx):
                        "global_batch": B * world, "parallelism": f"dp{world}: one process per GPU, gradients averaged by one flat-bucket "
                                                                    f"all-reduce inside backward()" if world > 1 else "dp1",
                        "l2": "activations + gradients of a step: > 5 GB >> 126 MB L2"},
-            "clocks": clocks, "phases": phases, "comm": comm, "final_loss": float(loss.detach()),
+            "clocks": clocks, "phases": phases, "comm": comm, "incumbent": incumbent, "final_loss": float(loss.detach()),
             "e2e": {"value": B * world * steps / float(t[1]), "unit": "frames/s", "h2d_bytes_per_step": 2 * B * T * 4,
                     "d2h_bytes_per_step": 4, "api": "the unchanged trainer loop's calls: .to(device) of pinned (mixture, clean), "
                                                     "model(mixture), loss(clean, enhanced), backward(), optimizer.step(), loss.item()"},

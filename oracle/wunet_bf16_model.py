@@ -112,8 +112,11 @@ def _upsample_fp32(prev: torch.Tensor) -> torch.Tensor:
 
 
 def forward_bf16_model(state, x: np.ndarray, n_layers: int = 12, channels_interval: int = 24, return_levels: bool = False,
-                       forced=None):
+                       forced=None, dense_bottom=None):
     """-> y [B,1,T] fp32 (and the bf16-valued outputs of the 2n+1 blocks as fp32 arrays; the last one unrounded).
+
+    ``dense_bottom``: whether decoder blocks of at most 16 samples use the folded-interpolation weights of gemm_tc_kernel (the
+    library takes that kernel for batches of at least 64 frames; default: decided from the batch size like the library).
 
     ``forced``: optional list of the 2n block outputs measured on the GPU (fp32 arrays holding bf16 values). Block i is then
     evaluated on the GPU's outputs of the blocks before it ("teacher forcing"): rounding flips do not propagate, so every
@@ -121,6 +124,8 @@ def forward_bf16_model(state, x: np.ndarray, n_layers: int = 12, channels_interv
     plan = channel_plan(n_layers, channels_interval)
     n = n_layers
     xt = torch.from_numpy(np.asarray(x, np.float32))
+    if dense_bottom is None:
+        dense_bottom = xt.shape[0] >= 64
     levels, skips = [], []
 
     def keep(i, t):
@@ -137,7 +142,7 @@ def forward_bf16_model(state, x: np.ndarray, n_layers: int = 12, channels_interv
     o = keep(n, _bf16(_block(o, state, "middle", 15, True)))
     for j in range(n):
         L = 2 * o.shape[2]
-        if L <= 16 and j != n - 1:
+        if dense_bottom and L <= 16 and j != n - 1:
             v = _block_folded(o, skips[n - 1 - j], state, plan[n + 1 + j][0])
         else:
             up = _upsample_hfma2(o) if L >= 128 else _upsample_fp32(o)

@@ -25,7 +25,9 @@ def ulp_bf16(v):
     return np.exp2(np.floor(np.log2(np.maximum(np.abs(v), 1e-30))) - 7)
 
 
-@pytest.mark.parametrize("n,ci,B,T,seed", [(4, 8, 3, 256, 11), (12, 24, 2, 16384, 0)])
+# the third case has batch >= 64: blocks of at most 16 samples (enc5, middle, dec0 there) run the dense GEMM over frames, the
+# decoder among them with the interpolation folded into its weights
+@pytest.mark.parametrize("n,ci,B,T,seed", [(4, 8, 3, 256, 11), (12, 24, 2, 16384, 0), (6, 8, 64, 512, 5)])
 def test_levels_match_the_arithmetic_model(n, ci, B, T, seed, monkeypatch):
     monkeypatch.setenv("WUNET_TC_STORE_LAST", "1")               # materialise the last decoder block too
     st = wo.make_state(n, ci, seed=seed)

@@ -215,9 +215,12 @@ def test_bf16_config3_batch256_properties(state_full):
     assert err <= BF16_OUT_TOL
     perm = np.random.default_rng(1).permutation(B)
     assert np.array_equal(run(m, x[perm]), y[perm])
-    # batches >= 128 take the tuned tilings of wunet_tc.cu (kTuned), small batches the generic rules: the K-loop order,
-    # hence every output bit, must not depend on the tiling
-    assert np.array_equal(run(m, x[pick[:3]]), y[pick[:3]])
+    # batches >= 128 take the tuned tilings of wunet_tc.cu (kTuned), smaller ones the generic rules: the K-loop order, hence
+    # every output bit, must not depend on the tiling. (Batches below 64 frames take the packed-frame kernels instead of the
+    # dense GEMM for the blocks of at most 16 samples - different arithmetic for the folded interpolation, so they are compared
+    # among themselves.)
+    assert np.array_equal(run(m, x[:64]), y[:64])
+    assert np.array_equal(run(m, x[:3]), run(m, x[:5])[:3])
     assert np.isfinite(y).all() and np.abs(y).max() < 1.0
 
 

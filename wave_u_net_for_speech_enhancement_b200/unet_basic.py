@@ -206,7 +206,10 @@ class Model(nn.Module):
 
     Extra keyword arguments (not in the reference; configs pass ``"args": {}`` so defaults apply):
 
-    precision      "fp32" (default; FFMA path, <=1e-4 vs the reference) or "bf16" (tcgen05 path).
+    precision      "fp32_tc" (default): fp32-grade results on the tensor cores (bf16 hi + lo split, three tcgen05 MMAs per
+                   product; <=1e-4 vs the reference, measured 1e-6; needs channels_interval % 8 == 0 and <= 32);
+                   "fp32": the same contract on CUDA-core FFMA for any channel plan (12x slower);
+                   "bf16": bf16 activations / operands on tcgen05 (the fastest path; ~6e-4 on the output).
     train_backend  "native" (default): a forward in training mode runs ``wunet_train_forward`` (BatchNorm with batch
                    statistics, running buffers updated) behind a ``torch.autograd.Function`` whose backward is
                    ``wunet_train_backward_part``; the reference's loss, ``loss.backward()`` and optimizer run unchanged
@@ -219,7 +222,7 @@ class Model(nn.Module):
                    all-reduced in two parts so that the first overlaps the rest of the backward. "off": never.
     """
 
-    def __init__(self, n_layers: int = 12, channels_interval: int = 24, precision: str = "fp32",
+    def __init__(self, n_layers: int = 12, channels_interval: int = 24, precision: str = "fp32_tc",
                  train_backend: str = "native", data_parallel: str = "auto"):
         super().__init__()
         if precision not in _lib.PRECISIONS:
