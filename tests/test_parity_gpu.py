@@ -224,6 +224,23 @@ def test_bf16_config3_batch256_properties(state_full):
     assert np.isfinite(y).all() and np.abs(y).max() < 1.0
 
 
+def test_bf16_head_only_kernel_is_bit_identical(state_full):
+    """WUNET_TC_HEADK=1 (opt-in): the last decoder block runs the head-only instantiation - both operand chunks
+    written by the producer warps from a TMA-fed shared-memory ring, straight-line head epilogue. Same arithmetic in the same
+    order as the default kernel: every output bit equal, at a batch that takes the tuned (two CTAs per SM) tiling."""
+    B = 128
+    x = wo.make_input(B, 16384, seed=1357)
+    y0 = run(bf16_model(12, 24, state_full), x)
+    os.environ["WUNET_TC_HEADK"] = "1"
+    try:
+        y1 = run(bf16_model(12, 24, state_full), x)
+    finally:
+        os.environ.pop("WUNET_TC_HEADK", None)
+    assert np.array_equal(y0, y1)
+    want = wo.COracle(12, 24).forward(state_full, x[[0, 63, 127]])
+    assert np.abs(y1[[0, 63, 127]] - want).max() <= BF16_OUT_TOL
+
+
 def test_bf16_edge_vectors(golden_dir, state_full):
     g = np.load(os.path.join(golden_dir, "edges_n12_c24.npz"))
     m = bf16_model(12, 24, state_full)

@@ -38,7 +38,8 @@ def source_hash() -> str:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not is_stale():
+    out_so = os.environ.get("WUNET_SO_OUT") or SO            # development: variant builds next to the product library
+    if out_so == SO and not force and not is_stale():
         return SO
     objs = []
     common = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -47,12 +48,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
         common += ["-Xptxas", "-v"]
     if os.environ.get("WUNET_TC_TRACE"):
         common += ["-DWUNET_TC_TRACE"]
+    for macro in ("WUNET_WAIT_NS", "WUNET_WAIT_NS_MMA", "WUNET_OPERAND_FENCE"):    # development: mbarrier suspend-time hints (A/B builds, tools/lib_ab.sh)
+        if os.environ.get(macro):
+            common += [f"-D{macro}={int(os.environ[macro])}"]
     if os.environ.get("WUNET_TN_DEBUG"):
         common += ["-DWUNET_TN_DEBUG"]                  # development: conv_tn_kernel instantiations with one role switched off
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     procs = []
     for s in SOURCES:
-        o = os.path.join(HERE, "build", s.replace(".cu", ".o"))
+        o = os.path.join(HERE, "build", s.replace(".cu", ".o") if out_so == SO else os.path.basename(out_so) + "." + s.replace(".cu", ".o"))
         objs.append(o)
         cmd = common + ["-c", os.path.join(CSRC, s), "-o", o]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -62,9 +66,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out)
         if p.returncode != 0:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
-    link = [nvcc_path(), "-shared", "-o", SO] + objs + ["-cudart", "static"]
+    link = [nvcc_path(), "-shared", "-o", out_so] + objs + ["-cudart", "static"]
     subprocess.check_call(link)
-    return SO
+    return out_so
 
 
 if __name__ == "__main__":

@@ -78,15 +78,46 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, int count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+// Waiting on an mbarrier phase. try_wait suspends the thread in hardware only for a short, system-defined time (~80 cycles
+// measured on B200), so a plain retry loop is a hot spin: in the round-2 ncu capture of the decoder blocks a quarter of all
+// issued instructions were YIELD / TRYWAIT / BRA of waiting roles, competing with the epilogue and producer warps for the
+// issue slots. With a suspend-time hint ptxas emits NANOSLEEP.SYNCS (sleep until the barrier's phase flips or the time is
+// up) instead. WUNET_WAIT_NS: hint for the producer / epilogue / TMA roles, WUNET_WAIT_NS_MMA: for the MMA issuer; 0 = no hint.
+#ifndef WUNET_WAIT_NS
+#define WUNET_WAIT_NS 0
+#endif
+#ifndef WUNET_WAIT_NS_MMA
+#define WUNET_WAIT_NS_MMA 0
+#endif
+template <int NS>
+__device__ __forceinline__ void mbar_wait_ns(uint32_t bar, uint32_t parity)
 {
     uint32_t ok;
     do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (NS > 0)
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                : "=r"(ok) : "r"(bar), "r"(parity), "r"((uint32_t)NS) : "memory");
+        else
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     } while (!ok);
 }
+// tcgen05.fence::after_thread_sync after the MMA issuer's waits for operand stages (a_full / b_full). Strictly the mbarrier wait
+// is the acquire the MMA needs there (the operands arrive through the async proxy or st.shared + fence.proxy.async; the tcgen05
+// fence is about tcgen05 operations of different threads and stays after acc_empty in any case). Measured in round 2: a build
+// without these fences (-DWUNET_OPERAND_FENCE=0) is bit-identical and not faster (profiles/r02_ab_operand_fence.txt), so they stay.
+#ifndef WUNET_OPERAND_FENCE
+#define WUNET_OPERAND_FENCE 1
+#endif
+#if WUNET_OPERAND_FENCE
+#define OPERAND_FENCE() asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory")
+#else
+#define OPERAND_FENCE() do { } while (0)
+#endif
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) { mbar_wait_ns<WUNET_WAIT_NS>(bar, parity); }
+__device__ __forceinline__ void mbar_wait_mma(uint32_t bar, uint32_t parity) { mbar_wait_ns<WUNET_WAIT_NS_MMA>(bar, parity); }
 __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity)
 {
     uint32_t ok;
@@ -180,6 +211,12 @@ __device__ __forceinline__ void st_shared_v4_if(uint32_t addr, const uint4 &v, b
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t@p st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n\t}"
                  ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"((uint32_t)pred) : "memory");
 }
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b)
 {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -193,7 +230,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b)
 #else
 #define TRACE(role, idx) do { } while (0)
 #endif
-__device__ __forceinline__ float lrelu(float v) { return v >= 0.f ? v : kLreluSlope * v; }
+__device__ __forceinline__ float lrelu(float v) { return fmaxf(v, kLreluSlope * v); }   // == v >= 0 ? v : slope * v (0 < slope < 1)
 // tanh(x) = 1 - 2 / (exp(2x) + 1); saturates correctly at +-inf, abs error ~1e-6 (bf16 path only)
 __device__ __forceinline__ float tanh_fast(float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); }
 
@@ -249,11 +286,18 @@ struct TcParams {
     int mg_vo, mg_nvec;        // first 16-byte vector / number of vectors the producers write in it
     int mg_nk, mg_kslot;       // its K16 steps, its 64-wide slot in the packed weights
     int mg_skip_idx, mg_up_idx;// 64-channel chunk index of the tails inside their segments
+    // head-only instantiation (HD = 1): the previous-level rows a tile interpolates between are staged in a shared-memory ring
+    // by TMA (tmO = plain [B][Lin][Cin0] view of prev), several tiles ahead of the producers
+    int hd;                    // 1: launch the HD instantiation
+    int ps_n;                  // ring slots (0 = no ring); entries alternate [previous-level window | skip rows] of a tile
+    int ps_rows, ps_rows2;     // box rows of the two entry kinds (previous-level rows / skip rows)
+    uint32_t ps_bytes;         // slot pitch (128-byte multiple)
+    uint32_t ps_tx, ps_tx2;    // bytes one TMA box of either kind delivers
 };
 
 // smem carve-up (offsets from the 1024-aligned base): A stages | B stages | ss | barriers
 struct SmemMap {
-    uint32_t a, b, ss, stg, bars;
+    uint32_t a, b, ss, stg, ps, bars;
 };
 __host__ __device__ inline SmemMap smem_map(const TcParams &p)
 {
@@ -262,11 +306,16 @@ __host__ __device__ inline SmemMap smem_map(const TcParams &p)
     m.b = p.na * p.a_stage_bytes;
     m.ss = m.b + p.nb * p.b_stage_bytes;
     m.stg = (m.ss + (uint32_t)p.Npad * 8 + 64 * 4 + 1023) & ~1023u;   // after scale/shift + head weights
-    m.bars = m.stg + (p.bulk_store ? (uint32_t)(p.n_epi * 2048) : 0u);   // one [32 rows x 32 ch] bf16 slab per epilogue warp
+    m.ps = m.stg + (p.bulk_store ? (uint32_t)(p.n_epi * 2048) : 0u);     // one [32 rows x 32 ch] bf16 slab per epilogue warp
+    m.ps = (m.ps + 127) & ~127u;
+    m.bars = m.ps + (uint32_t)p.ps_n * p.ps_bytes;                       // HD: ring of previous-level row windows
     m.bars = (m.bars + 15) & ~15u;
     return m;
 }
-inline size_t smem_total(const TcParams &p) { return smem_map(p).bars + 8 * (8 + 2 * kMaxBStages + 4) + 16 + (p.mg ? 32 : 0) + 1024; }
+inline size_t smem_total(const TcParams &p)
+{
+    return smem_map(p).bars + 8 * (8 + 2 * kMaxBStages + 4) + 16 + ((p.mg || p.ps_n) ? 32 : 0) + (p.ps_n ? 128 : 0) + 1024;
+}
 
 // K-loop position c -> (segment, chunk index inside the segment, K16 steps, 64-wide slot in the packed weights)
 struct ChunkInfo { bool up; int idx, nk, kslot; bool merged; int vo, nvec; bool lo, reuse; };
@@ -308,7 +357,10 @@ __device__ __forceinline__ ChunkInfo chunk_info(const TcParams &p, int c)
 // -------------------------------------------------------------------------------------------------
 // MG = 1: decoder instantiations whose K loop ends in a merged tail chunk (p.mg); MG = 0 everything else (kept in separate
 // instantiations so that the code of the validated ones does not change while they are being developed).
-template <int KS, bool UPCAT, int EW, int PW, int MG, int SP = 0>
+// HD = 1: the last decoder block when only the network output is wanted (fused head, the block's own activations are not
+// stored; Cout <= 32, one N tile): a straight-line head-only epilogue and 8-row producer items (see the roles below). The
+// arithmetic and its order are those of the generic instantiation: bit-identical results.
+template <int KS, bool UPCAT, int EW, int PW, int MG, int SP = 0, int HD = 0>
 __global__ void __launch_bounds__(64 + 32 * (EW + PW), EW == kEpiWarpsSmall ? 2 : 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmO, const TcParams p)
@@ -327,6 +379,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t acc_full = bars + 64 + 16 * kMaxBStages, acc_empty = acc_full + 16;
     const uint32_t tmem_slot = acc_empty + 16;
     const uint32_t a_tma = tmem_slot + 16;            // [4], MG = 1 kernels (merged tail chunk) only (smem_total reserves them)
+    const uint32_t p_full = a_tma + 32, p_empty = a_tma + 96;   // [8] each, HD = 1 kernels only: ring of row windows (see the TMA role)
     volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(base_ptr + sm.bars + 64 + 16 * kMaxBStages + 32);
 
     // Programmatic dependent launch: let the next block's kernel be scheduled as our CTAs retire, so its prologue (barrier
@@ -346,7 +399,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
         if (p.bulk_store) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmO)) : "memory");
         for (int s = 0; s < 4; ++s) {
-            mbar_init(a_full + 8 * s, UPCAT ? 1 + kProducerWarps : 1);
+            mbar_init(a_full + 8 * s, HD != 0 ? kProducerWarps : (UPCAT ? 1 + kProducerWarps : 1));
             mbar_init(a_empty + 8 * s, 1);
         }
         for (int s = 0; s < 2; ++s) {
@@ -356,6 +409,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int s = 0; s < min(p.nb, kMaxBStages); ++s) { mbar_init(b_full + 8 * s, 1); mbar_init(b_empty + 8 * s, 1); }
         if (MG != 0 && p.mg)
             for (int s = 0; s < 4; ++s) mbar_init(a_tma + 8 * s, 1);
+        if (HD != 0)
+            for (int s = 0; s < 8; ++s) { mbar_init(p_full + 8 * s, 1); mbar_init(p_empty + 8 * s, kProducerWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kMmaWarp) {
@@ -363,12 +418,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     {   // folded BatchNorm scale/shift of all output columns
+        if (HD != 0) {
+            // head-only kernel: one float4 per output column {scale, shift, head weight, extra}; extra of column 0 = head bias,
+            // of column 1 = head weight of the raw-input channel. Columns past Cout are zero.
+            float4 *hp = reinterpret_cast<float4 *>(base_ptr + sm.ss);
+            if (threadIdx.x < 32) {
+                const int c = threadIdx.x;
+                const float2 st = c < p.Npad ? p.ss[c] : make_float2(0.f, 0.f);
+                hp[c] = make_float4(st.x, st.y, c < p.Cout ? p.head_w[c] : 0.f, c == 0 ? p.head_b[0] : (c == 1 ? p.head_w[p.Cout] : 0.f));
+            }
+        } else {
         float2 *ss = reinterpret_cast<float2 *>(base_ptr + sm.ss);
         for (int i = threadIdx.x; i < p.Npad; i += blockDim.x) ss[i] = p.ss[i];
         if (p.head) {
             float *hw = reinterpret_cast<float *>(base_ptr + sm.ss) + 2 * p.Npad;
             if ((int)threadIdx.x <= p.Cout) hw[threadIdx.x] = p.head_w[threadIdx.x];
             if ((int)threadIdx.x == p.Cout + 1) hw[threadIdx.x] = p.head_b[0];
+        }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -443,6 +509,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 asm volatile("griddepcontrol.wait;" ::: "memory");        // activations of the previous block from here on
             }
+            if (HD != 0) {
+                // head-only instantiation: BOTH operand chunks are written by the producer warps; this lane only feeds them. Per
+                // tile two ring entries, in K-loop order: the window of previous-level rows the upsampled chunk interpolates
+                // between (rows (l0 - PAD)/2 - 1 ..., tmO = plain [B][Lin][Cin0] view) and the tile's skip rows (l0 - PAD ...,
+                // tmA = plain [B][L][Cin1] view; rows outside the frame are zero-filled = Conv1d padding). The lane runs as far
+                // ahead as the ring has free slots (ps_n entries), so the DRAM latency of neither stream reaches the producers.
+                int ps_i = 0, ps_par = 0;
+                for (int tile = first_tile; tile < total_tiles; tile += gridDim.x) {
+                    int b0, l0, n0;
+                    tile_coords(tile, b0, l0, n0);
+                    for (int half = 0; half < 2; ++half) {
+                        TRACE(0, tr0);
+                        mbar_wait(p_empty + 8 * ps_i, ps_par ^ 1);
+                        TRACE(0, tr0);
+                        const uint32_t dsts = base + sm.ps + (uint32_t)ps_i * p.ps_bytes;
+                        if (half == 0) {
+                            mbar_expect_tx(p_full + 8 * ps_i, p.ps_tx);
+                            tma_load_3d(dsts, &tmO, p_full + 8 * ps_i, 0, ((l0 - PAD) >> 1) - 1, b0);
+                        } else {
+                            mbar_expect_tx(p_full + 8 * ps_i, p.ps_tx2);
+                            tma_load_3d(dsts, &tmA, p_full + 8 * ps_i, 0, l0 - PAD, b0);
+                        }
+                        if (++ps_i == p.ps_n) { ps_i = 0; ps_par ^= 1; }
+                    }
+                }
+            } else {
             for (int pre = 0; pre < p.na - 1; ++pre) issue_a(true);          // A tiles run na-1 chunks ahead of the weights
             if (p.na == 1) issue_a(true);
             for (int tile = first_tile; tile < total_tiles; tile += gridDim.x) {
@@ -464,6 +556,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (!a_done) issue_a(true);
                 }
             }
+            }
         }
     } else if (warp == kMmaWarp) {
         // ======================= MMA issuer =======================
@@ -477,7 +570,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t b_step = tile_bytes >> 4;
             // descriptor words: hi = SBO(1024 B) | version 1 | SWIZZLE_128B, lo = (addr >> 4) | LBO(1)
             const uint32_t hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
-            if (p.resident) { mbar_wait(b_full, 0); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+            if (p.resident) { mbar_wait_mma(b_full, 0); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
             for (int tile = first_tile; tile < total_tiles; tile += gridDim.x, ++it) {
                 int b0, l0, n0;
                 tile_coords(tile, b0, l0, n0);
@@ -487,7 +580,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int buf = (p.nacc == 2) ? (it & 1) : 0;
                 const uint32_t use = (p.nacc == 2) ? (uint32_t)(it >> 1) : (uint32_t)it;
                 TRACE(1, tr1);
-                mbar_wait(acc_empty + 8 * buf, (use & 1) ^ 1);
+                mbar_wait_mma(acc_empty + 8 * buf, (use & 1) ^ 1);
                 TRACE(1, tr1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t acc_col = tmem_base + buf * p.MT * p.Nstride;
@@ -495,9 +588,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const ChunkInfo mci = chunk_info<UPCAT, MG, SP>(p, c);
                     const int nk = mci.nk;
                     if (!(SP != 0 && mci.reuse)) {
-                        mbar_wait(a_full + 8 * sa, pa);
+                        mbar_wait_mma(a_full + 8 * sa, pa);
                         TRACE(1, tr1);
-                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        OPERAND_FENCE();
                     }
                     const uint32_t a_base = base + sm.a + sa * p.a_stage_bytes;
                     uint32_t a_lo = ((a_base >> 4) & 0x3FFFu) | (1u << 16);
@@ -506,9 +599,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (p.resident) {
                             b_base = base + sm.b + (uint32_t)(c * p.ngroups + g) * p.b_stage_bytes;
                         } else {
-                            mbar_wait(b_full + 8 * sb, pb);
+                            mbar_wait_mma(b_full + 8 * sb, pb);
                             TRACE(1, tr1);
-                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                            OPERAND_FENCE();
                             b_base = base + sm.b + sb * p.b_stage_bytes;
                         }
                         uint32_t b_lo = ((b_base >> 4) & 0x3FFFu) | (1u << 16);
@@ -562,6 +655,40 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (warp == 0 && lane == 0) TRACE(2, tr2);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t acc_col = buf * p.MT * p.Nstride;
+            if (HD != 0) {
+                // head-only epilogue: BatchNorm + LeakyReLU of the (<= 32) columns of this thread's row, then
+                // cat([o, input], 1) -> Conv1d(C+1 -> 1, k=1) -> Tanh (model/unet_basic.py:98-99), accumulated in column order like
+                // the generic path. No bf16 conversion, no store of the block's activations, parameters as one LDS.128 per column.
+                const float4 *hp = reinterpret_cast<const float4 *>(base_ptr + sm.ss);
+                const float hbias = hp[0].w, hwin = hp[1].w;
+#pragma unroll 1
+                for (int mt = 0; mt < p.MT; ++mt) {
+                    const int l = l0 + mt * 128 + q * 32 + lane;
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc_col + (uint32_t)(mt * p.Nstride);
+                    float hacc = hbias;
+#pragma unroll
+                    for (int h16 = 0; h16 < 2; ++h16) {
+                        if (16 * h16 < p.Cout) {                                   // warp-uniform
+                            uint32_t v[16];
+                            tmem_ld16(taddr + 16 * h16, v);
+#pragma unroll
+                            for (int g8 = 0; g8 < 2; ++g8) {
+                                if (16 * h16 + 8 * g8 < p.Cout) {                  // warp-uniform; columns past Cout carry zero weights
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) {
+                                        const float4 c4 = hp[16 * h16 + 8 * g8 + j];
+                                        hacc = fmaf(c4.z, lrelu(fmaf(__uint_as_float(v[8 * g8 + j]), c4.x, c4.y)), hacc);
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    if (b0 < p.B && l < p.L) {
+                        hacc = fmaf(hwin, mt == 0 ? xin0 : (mt == 1 ? xin1 : (mt == 2 ? xin2 : xin3)), hacc);
+                        p.y[(size_t)b0 * p.T + l] = tanh_fast(hacc);
+                    }
+                }
+            } else {
             // Work items (mt, 32-column chunk) are dealt round-robin to the warps sharing a quadrant. One rolled code path
             // serves the three store flavours (TMA-store slab, direct row stores, fused head): 16 accumulator columns are
             // read per tcgen05.ld, converted 8 at a time.
@@ -646,6 +773,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     p.y[(size_t)bb * p.T + l] = tanh_fast(hacc);
                 }
             }
+            }
             // accumulator buffer drained: hand it back to the MMA warp
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
@@ -655,17 +783,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else if (UPCAT) {
         // ======================= upsample producers (decoder) =======================
         // F.interpolate(scale_factor=2, mode="linear", align_corners=True) of the previous block's output, written straight
-        // into the swizzled operand tile. A thread owns (16 consecutive output rows) x (one 16-byte channel vector): the 10
-        // previous-level rows they interpolate between (row l lies between prev rows (l-1)>>1 and that + 1, since
-        // src = l*(Lin-1)/(2Lin-1)) are fetched into registers one work unit AHEAD, so their DRAM latency overlaps the wait
-        // for the shared-memory stage.
+        // into the swizzled operand tile. A thread owns (RPI = 16 consecutive output rows) x (one 16-byte channel vector): the
+        // RPI/2 + 2 = 10 previous-level rows they interpolate between (row l lies between prev rows (l-1)>>1 and that + 1,
+        // since src = l*(Lin-1)/(2Lin-1)) are fetched into registers one work unit AHEAD, so their DRAM latency overlaps the
+        // wait for the shared-memory stage. The head-only instantiation (HD: 24 upsampled channels = 3 vectors per row) uses
+        // 8-row items: with 16-row items only 48 of its 128 producer threads had work (ncu, round 2).
+        constexpr int RPI = HD != 0 ? 8 : 16;             // rows per item
+        constexpr int WR = RPI / 2 + 2;                   // previous-level rows per item
         const int pt = (warp - kFirstProducer) * 32 + lane;
         int sa = 0, pa = 0;
         int tr4 = 0; (void)tr4;
         uint32_t tma_par = 0;                              // merged chunks: phase parity of a_tma[stage], one bit per stage
-        uint4 xr[10];
+        uint4 xr[WR];
         bool pref = false;
-        const int nruns = (p.rows_used + 15) >> 4;
+        const int nruns = (p.rows_used + RPI - 1) / RPI;
         // a chunk whose first-round items can be prefetched into the register window one work unit ahead
         auto unit_fast = [&](int c) { return SP == 0 && !p.packed && chunk_info<UPCAT, MG, SP>(p, c).up; };
         // loads of item `item` of unit (frame ub0, first row ul0, K-loop position c) into the window
@@ -675,11 +806,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (item >= nruns * nvec) return;
             const int run = item / nvec, vec = item - run * nvec;
             const int ch = u.idx * 64 + vec * 8;
-            const int ms = (ul0 - PAD + 16 * run) >> 1;
+            const int ms = (ul0 - PAD + RPI * run) >> 1;
             const bool chok = ch < p.Cin0 && ub0 < p.B;
             const __nv_bfloat16 *pb = p.prev + (size_t)ub0 * p.Lin * p.Cin0 + ch;
 #pragma unroll
-            for (int qq = 0; qq < 10; ++qq) {
+            for (int qq = 0; qq < WR; ++qq) {
                 int m = ms - 1 + qq;
                 m = m < 0 ? 0 : (m > p.Lin - 1 ? p.Lin - 1 : m);
                 xr[qq] = chok ? __ldg(reinterpret_cast<const uint4 *>(pb + (size_t)m * p.Cin0)) : make_uint4(0u, 0u, 0u, 0u);
@@ -688,19 +819,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // interpolate + store the 16 rows of one item from the register window. Straight-line code (masks and a predicated
         // store instead of branches): the 16 rows are independent, and a branch per row serialises their dependent chains
         // (trace: ~3600 cycles per item with branches, the stage hand-off was waiting on it).
-        auto emit = [&](uint8_t *dst, int l0, int c, int item, const uint4 (&w)[10]) {
+        auto emit = [&](uint8_t *dst, int l0, int c, int item, const uint4 (&w)[WR]) {
             const ChunkInfo u = chunk_info<UPCAT, MG, SP>(p, c);
             const int nvec = u.nvec;
             const int run = item / nvec, vec = item - run * nvec;
             const int ch = u.idx * 64 + vec * 8;
             const int dvec = u.vo + vec;                                       // 16-byte vector inside the stage row
-            const int lstart = l0 - PAD + 16 * run;                            // even
+            const int lstart = l0 - PAD + RPI * run;                           // even
             const int ms = lstart >> 1;
             const bool chok = ch < p.Cin0;
             const float lf0 = (float)lstart, mf0 = (float)(ms - 1);            // small integers: exact in fp32
-            const uint32_t drow = smem_u32(dst) + (uint32_t)(16 * run) * 128u;
+            const uint32_t drow = smem_u32(dst) + (uint32_t)(RPI * run) * 128u;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
+            for (int j = 0; j < RPI; ++j) {
                 const int l = lstart + j;
                 const int qa = (j >> 1) + (j & 1);
                 // out = a + lam1 * (b - a) in packed bf16 (HFMA2); lam1 = up_scale * l - (ms - 1 + qa), one fused rounding
@@ -714,10 +845,70 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 uint4 o = *reinterpret_cast<const uint4 *>(r2);
                 const uint32_t keep = (chok && (unsigned)l < (unsigned)p.L) ? 0xffffffffu : 0u;   // zero rows = Conv1d padding
                 o.x &= keep; o.y &= keep; o.z &= keep; o.w &= keep;
-                // predicated (not branched) 16-byte store; (16 * run + j) & 7 == j & 7
-                st_shared_v4_if(drow + (uint32_t)(j * 128 + ((dvec ^ (j & 7)) << 4)), o, 16 * run + j < p.rows_used);
+                // predicated (not branched) 16-byte store; (RPI * run + j) & 7 == j & 7
+                st_shared_v4_if(drow + (uint32_t)(j * 128 + ((dvec ^ (j & 7)) << 4)), o, RPI * run + j < p.rows_used);
             }
         };
+        if (HD != 0) {
+            // head-only instantiation: both operand chunks come out of the ring the TMA lane fills several entries ahead - the
+            // upsampled chunk is interpolated from its window of previous-level rows, the skip chunk is copied into the swizzled
+            // stage layout - so no global-load latency sits between two hand-offs (the generic path's register prefetch leaves
+            // ~3000 cycles of it exposed per unit). One ring entry per chunk, in K-loop order.
+            int ps_i = 0, ps_par = 0;
+            for (int tile = first_tile; tile < total_tiles; tile += gridDim.x) {
+                int b0, l0, n0;
+                tile_coords(tile, b0, l0, n0);
+                const int base_m = ((l0 - PAD) >> 1) - 1;                           // previous-level row held by scratch row 0
+                const int rlo = max(0, -base_m), rhi = min(p.ps_rows - 1, p.Lin - 1 - base_m);
+                for (int c = 0; c < p.nchunks; ++c) {
+                    const ChunkInfo cu = chunk_info<UPCAT, MG, SP>(p, c);
+                    const uint32_t scr = base + sm.ps + (uint32_t)ps_i * p.ps_bytes;
+                    if (pt == 0) TRACE(4, tr4);
+                    mbar_wait(p_full + 8 * ps_i, ps_par);
+                    if (pt == 0) TRACE(4, tr4);
+                    mbar_wait(a_empty + 8 * sa, pa ^ 1);
+                    if (pt == 0) TRACE(4, tr4);
+                    uint8_t *dst = base_ptr + sm.a + sa * p.a_stage_bytes;
+                    if (cu.up) {
+                        const uint32_t rowb = (uint32_t)p.Cin0 * 2u;                // dense box rows
+                        const int nvec = cu.nvec, nitems = nruns * nvec;
+#pragma unroll 1
+                        for (int itx = pt; itx < nitems; itx += NPROD) {
+                            const int run = itx / nvec, vec = itx - run * nvec;
+                            const bool chok = cu.idx * 64 + vec * 8 < p.Cin0;
+#pragma unroll
+                            for (int qq = 0; qq < WR; ++qq) {
+                                int r = (RPI / 2) * run + qq;
+                                r = r < rlo ? rlo : (r > rhi ? rhi : r);
+                                xr[qq] = chok ? ld_shared_v4(scr + (uint32_t)r * rowb + (uint32_t)(cu.idx * 128 + vec * 16)) : make_uint4(0u, 0u, 0u, 0u);
+                            }
+                            emit(dst, l0, c, itx, xr);
+                        }
+                    } else {
+                        // skip rows l0 - PAD ... (zero rows outside the frame) -> vectors 0 .. 2 nk - 1 of the stage rows, zeros
+                        // past the last channel
+                        const uint32_t rowb = (uint32_t)p.Cin1 * 2u;
+                        const int nv = cu.nk * 2, nitems = p.rows_used * nv;
+                        const uint32_t dsts = smem_u32(dst);
+#pragma unroll 2
+                        for (int itx = pt; itx < nitems; itx += NPROD) {
+                            const int row = itx / nv, vec = itx - row * nv;
+                            const uint4 v = (cu.idx * 64 + vec * 8 < p.Cin1)
+                                                ? ld_shared_v4(scr + (uint32_t)row * rowb + (uint32_t)(cu.idx * 128 + vec * 16))
+                                                : make_uint4(0u, 0u, 0u, 0u);
+                            st_shared_v4_if(dsts + (uint32_t)(row * 128 + ((vec ^ (row & 7)) << 4)), v, true);
+                        }
+                    }
+                    if (pt == 0) TRACE(4, tr4);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy writes -> tensor core reads
+                    __syncwarp();
+                    if (pt == 0) TRACE(4, tr4);
+                    if (lane == 0) { mbar_arrive(a_full + 8 * sa); mbar_arrive(p_empty + 8 * ps_i); }
+                    if (++sa == p.na) { sa = 0; pa ^= 1; }
+                    if (++ps_i == p.ps_n) { ps_i = 0; ps_par ^= 1; }
+                }
+            }
+        } else
         for (int tile = first_tile; tile < total_tiles; tile += gridDim.x) {
             int b0, l0, n0;
             tile_coords(tile, b0, l0, n0);
@@ -1734,7 +1925,7 @@ struct TcPlanLevel {
 // Per-block tiling overrides for tuning sweeps: WUNET_TC_OVR="<block>:key=val,key=val;<block>:..." with keys
 // mt, ns (column splits), na, nacc, tg, res (0/1), small (0/1), bulk (0/1), packed (1: pack L=128 frames). Unset keys keep
 // the heuristic's choice.
-struct TcOverride { int mt = 0, ns = 0, na = 0, nacc = 0, tg = 0, res = -1, small = -1, bulk = -1, packed = -1; bool any = false; };
+struct TcOverride { int mt = 0, ns = 0, na = 0, nacc = 0, tg = 0, nb = 0, res = -1, small = -1, bulk = -1, packed = -1; bool any = false; };
 static void parse_kv(const std::string &seg, TcOverride &ov)
 {
     size_t q = 0;
@@ -1750,6 +1941,7 @@ static void parse_kv(const std::string &seg, TcOverride &ov)
         if (k == "mt") ov.mt = v; else if (k == "ns") ov.ns = v; else if (k == "na") ov.na = v;
         else if (k == "nacc") ov.nacc = v; else if (k == "tg") ov.tg = v; else if (k == "res") ov.res = v;
         else if (k == "small") ov.small = v; else if (k == "bulk") ov.bulk = v; else if (k == "packed") ov.packed = v;
+        else if (k == "nb") ov.nb = v;
         ov.any = true;
     }
 }
@@ -1793,6 +1985,9 @@ struct TcState {
     const float *out_w = nullptr, *out_b = nullptr;
     EncodeTiledFn encode = nullptr;
     bool store_last = false;           // WUNET_TC_STORE_LAST=1: also materialise the last decoder block (tests)
+    bool headk = false;                // WUNET_TC_HEADK=1: head-only instantiation for the last block (bit-identical; slower at the
+                                       // tiling its shared-memory ring allows)
+    int head_mt = 1;                   // its M sub-tiles per CTA (WUNET_TC_HEADMT)
     bool attr_set = false;
     bool pdl = false;                  // programmatic dependent launch between the blocks (WUNET_TC_PDL=1); measured slower, off
     bool merge = true;                 // merged tail chunks (WUNET_TC_MERGE=0 switches them off for A/B measurements)
@@ -1892,6 +2087,8 @@ int tc_set_weights(TcState **pst, int n, int ci, const TcBlockSrc *blocks, int n
         if (const char *xe = getenv("WUNET_TC_TN")) st->tn = xe[0] == '1';
         if (const char *xe = getenv("WUNET_TC_GEMM")) st->gemm = xe[0] != '0';
         if (const char *xe = getenv("WUNET_TC_PFLATE")) st->pf_late = xe[0] == '1';
+        if (const char *xe = getenv("WUNET_TC_HEADK")) st->headk = xe[0] == '1';
+        if (const char *xe = getenv("WUNET_TC_HEADMT")) st->head_mt = std::max(1, std::min(4, atoi(xe)));
 #ifdef WUNET_TC_TRACE
         if (const char *tl = getenv("WUNET_TC_TRACE_LEVEL")) {
             st->trace_level = atoi(tl);
@@ -1972,6 +2169,21 @@ static int make_map_out(TcState *st, CUtensorMap *m, const void *base, uint64_t 
     return 0;
 }
 
+// un-swizzled [d2][d1][d0] bf16 view with dense box rows (the head-only kernel's ring of previous-level rows)
+static int make_map_plain(TcState *st, CUtensorMap *m, const void *base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b1)
+{
+    cuuint64_t gdim[3] = {d0, d1, d2};
+    cuuint64_t gstr[2] = {d0 * 2, d1 * d0 * 2};
+    cuuint32_t box[3] = {(cuuint32_t)d0, b1, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = st->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(base), gdim, gstr, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return tc_fail("cuTensorMapEncodeTiled(plain) failed (%d): dims %llu,%llu,%llu box rows %u", (int)r,
+                                          (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2, b1);
+    return 0;
+}
+
 static int make_map(TcState *st, CUtensorMap *m, const void *base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1_bytes,
                     uint64_t s2_bytes, uint32_t b0, uint32_t b1, uint32_t b2)
 {
@@ -2031,7 +2243,10 @@ static int sp_chunk_order(const TcLevel &lv, bool dec, unsigned char *map, Split
 
 // Tiling decision for conv block i: pure host logic (no CUDA calls), so that tests can exercise it without a GPU
 // (wunet_debug_plan). Fills every tiling field of P.p and the launch shape; pointers and tensor maps are added by build_plan.
-static int plan_block(const TcLevel &lv, int i, int n, int B, int T, int num_sms, const std::string &ovr, TcPlanLevel &P, bool sp = false)
+// hd_mt > 0: the block is the last one and only the network output is wanted (head-only instantiation, see build_plan): M
+// sub-tiles per CTA for it, so that the ring of previous-level rows fits next to the input ring (small flavour only).
+static int plan_block(const TcLevel &lv, int i, int n, int B, int T, int num_sms, const std::string &ovr, TcPlanLevel &P, bool sp = false,
+                      int hd_mt = 0)
 {
     TcParams &p = P.p;
     memset(&p, 0, sizeof(p));
@@ -2137,6 +2352,7 @@ static int plan_block(const TcLevel &lv, int i, int n, int B, int T, int num_sms
         else if (ns32 <= 128) MT = 2;      // 2 x 2 x 128 columns: double-buffered accumulators beat the bigger MT=4 tile (73 vs 105 us on enc4)
         else MT = dec ? 2 : 1;             // N > 128: encoders gain from double buffering at MT=1 (enc5: 60 vs 74 us); decoders do not
         if (ov.mt > 0) MT = ov.mt;
+        if (hd_mt > 0 && small && i == 2 * n) MT = hd_mt;
         while (MT > 1 && 128 * MT > L) --MT;
         geometry(MT, ns_sel);
     } else if (ov.mt > 0 || ov.ns > 0) {
@@ -2199,6 +2415,7 @@ static int plan_block(const TcLevel &lv, int i, int n, int B, int T, int num_sms
                 p.b_stage_bytes = (uint32_t)stage;
                 int nb = (ring_budget - na * (int)p.a_stage_bytes) / stage;
                 if (nb > kMaxBStages) nb = kMaxBStages;
+                if (ov.nb >= min_stages && nb > ov.nb) nb = ov.nb;
                 p.nb = nb;
                 ok = true;
                 break;
@@ -2425,7 +2642,8 @@ static int build_plan(TcState *st, const float *x, float *y, int B, int T, void 
             P.tmO = P.tmA;
             continue;
         }
-        if (plan_block(lv, i, n, B, T, st->num_sms, st->plan_ovr, P, sp)) return -1;
+        const bool hd_want = (i == 2 * n) && !st->store_last && !sp && st->headk;
+        if (plan_block(lv, i, n, B, T, st->num_sms, st->plan_ovr, P, sp, hd_want ? st->head_mt : 0)) return -1;
         TcParams &p = P.p;
         const bool dec = i > n;
         const int L = p.L;
@@ -2452,6 +2670,29 @@ static int build_plan(TcState *st, const float *x, float *y, int B, int T, void 
         }
         if (p.out != nullptr && !sp) { if (make_map_out(st, &P.tmO, p.out, (uint64_t)lv.cout, (uint64_t)B * L)) return -1; }
         else P.tmO = P.tmA;
+        p.hd = 0; p.ps_n = 0; p.ps_rows = p.ps_rows2 = 0; p.ps_bytes = 0; p.ps_tx = p.ps_tx2 = 0;
+        if (last && dec && p.out == nullptr && !sp && P.small && !p.mg && !p.packed && !p.bulk_store && p.resident && p.Npad <= 32 &&
+            p.Nh == p.Npad && p.MT <= 4 && lv.cin0 % 8 == 0 && lv.cin1 % 8 == 0 && p.nchunks == 2 && (p.chunk_map[0] & 0x80) &&
+            !(p.chunk_map[1] & 0x80) && st->headk) {
+            // head-only instantiation (conv_tc_kernel<..., HD = 1>): both operand chunks are producer-written from a ring of
+            // [previous-level window | skip rows] entries; as many slots (3..8) as still leave two CTAs per SM
+            // output row j of the tile interpolates between window rows (j >> 1) + (j & 1) and that + 1 (the producers clamp the
+            // index for the masked rows past rows_used of their last item)
+            const int rows = ((p.rows_used + 1) >> 1) + 2, rows2 = p.rows_used;
+            if (rows <= 256 && rows2 <= 256 && p.Lin >= rows && L >= rows2) {
+                p.ps_rows = rows; p.ps_rows2 = rows2;
+                p.ps_tx = (uint32_t)rows * (uint32_t)lv.cin0 * 2u;
+                p.ps_tx2 = (uint32_t)rows2 * (uint32_t)lv.cin1 * 2u;
+                p.ps_bytes = (uint32_t)round_up((int)std::max(p.ps_tx, p.ps_tx2), 128);
+                for (p.ps_n = 8; p.ps_n >= 3 && (int)smem_total(p) > kSmemLimitSmall; --p.ps_n) { }
+                if (p.ps_n >= 3) {
+                    p.hd = 1;
+                    P.smem = smem_total(p);
+                    if (make_map_plain(st, &P.tmO, lvl(i - 1), (uint64_t)lv.cin0, (uint64_t)p.Lin, (uint64_t)B, (uint32_t)rows)) return -1;
+                    if (make_map_plain(st, &P.tmA, lvl(2 * n - i), (uint64_t)lv.cin1, (uint64_t)L, (uint64_t)B, (uint32_t)rows2)) return -1;
+                } else p.ps_n = 0;
+            }
+        }
         const uint64_t ktot = sp ? (uint64_t)lv.sp_chunks * 64 : (uint64_t)lv.Ktot;
         if (make_map(st, &P.tmW, sp ? lv.wp_sp : lv.wp, ktot, lv.Npad, lv.k, ktot * 2, (uint64_t)lv.Npad * ktot * 2, 64,
                      (uint32_t)p.Nh, (uint32_t)p.tg))
@@ -2472,9 +2713,9 @@ static int build_plan(TcState *st, const float *x, float *y, int B, int T, void 
                         t.Cin0, t.Cin1, t.Cout, t.Npad, t.MT, t.nchunks, t.na, t.wpg, t.npg, pl.lv[i].smem, t.tile_end, pl.lv[i].grid.x);
                 continue;
             }
-            fprintf(stderr, "[wunet tc] blk %2d L=%5d Cin=%3d+%3d Cout=%3d Nh=%3d x%d MT=%d nacc=%d packed=%d FR=%d res=%d bulk=%d na=%d nb=%d tg=%d smem=%zu tmem=%u tiles=%d grid=%u small=%d per_sm=%d\n",
+            fprintf(stderr, "[wunet tc] blk %2d L=%5d Cin=%3d+%3d Cout=%3d Nh=%3d x%d MT=%d nacc=%d packed=%d FR=%d res=%d bulk=%d na=%d nb=%d tg=%d smem=%zu tmem=%u tiles=%d grid=%u small=%d per_sm=%d hd=%d ring=%d\n",
                     i, p.L, p.Cin0, p.Cin1, p.Cout, p.Nh, p.nsplit, p.MT, p.nacc, p.packed, p.FR, p.resident, p.bulk_store, p.na, p.nb, p.tg, pl.lv[i].smem, p.tmem_cols,
-                    p.m_tiles * p.nsplit, pl.lv[i].grid.x, (int)pl.lv[i].small, pl.lv[i].per_sm);
+                    p.m_tiles * p.nsplit, pl.lv[i].grid.x, (int)pl.lv[i].small, pl.lv[i].per_sm, p.hd, p.ps_n);
         }
     }
     st->plan_ws = ws; st->plan_B = B; st->plan_T = T; st->plan_x = x; st->plan_y = y; st->plan_mode = mode;
@@ -2497,7 +2738,13 @@ int tc_debug_plan(int n, int ci, const TcBlockSrc *blocks, int nblocks, int B, i
     if (!(ge && ge[0] == '0') && parse_override(ovr_s, block).any == false && plan_block_gemm(levels[block], block, n, B, T, num_sms, P)) {
     } else
     if (!(parse_override(ovr_s, block).any == false && plan_block_tn(levels[block], block, n, B, T, num_sms, P)))
-        if (plan_block(levels[block], block, n, B, T, num_sms, ovr_s, P)) return -1;
+    {
+        // the last block as the forward plans it by default (head-only instantiation unless WUNET_TC_STORE_LAST=1 / WUNET_TC_HEADK=0)
+        const char *sl = getenv("WUNET_TC_STORE_LAST"), *hk = getenv("WUNET_TC_HEADK"), *hm = getenv("WUNET_TC_HEADMT");
+        const bool hd_want = block == 2 * n && !(sl && sl[0] == '1') && (hk && hk[0] == '1');
+        const int head_mt = hm ? std::max(1, std::min(4, atoi(hm))) : 1;
+        if (plan_block(levels[block], block, n, B, T, num_sms, ovr_s, P, false, hd_want ? head_mt : 0)) return -1;
+    }
     const TcParams &p = P.p;
     const int v[32] = {p.L, p.Cin0, p.Cin1, p.Cout, p.Npad, p.Nh, p.nsplit, p.Nstride, p.MT, p.nacc, p.packed, p.FR, p.S, p.m_tiles,
                        p.nchunks, p.resident, p.bulk_store, p.na, p.nb, p.tg, p.ngroups, (int)p.a_stage_bytes, (int)p.b_stage_bytes,
@@ -2519,6 +2766,7 @@ static int tc_prepare(TcState *st, const float *x, float *y, int B, int T, void 
         cudaFuncSetAttribute(conv_tc_kernel<5, true, kEpiWarpsSmall, kProducerWarpsSmall, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         cudaFuncSetAttribute(conv_tc_kernel<5, true, kEpiWarpsLarge, kProducerWarpsLarge, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         cudaFuncSetAttribute(conv_tc_kernel<5, true, kEpiWarpsSmall, kProducerWarpsSmall, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+        cudaFuncSetAttribute(conv_tc_kernel<5, true, kEpiWarpsSmall, kProducerWarpsSmall, 0, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         cudaFuncSetAttribute(conv_tc_kernel<5, true, kEpiWarpsLarge, kProducerWarpsLarge, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         cudaFuncSetAttribute(conv_tc_kernel<15, false, kEpiWarpsLarge, 0, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
@@ -2625,6 +2873,9 @@ static int launch_block(TcState *st, int i, int t0, int t1, cudaStream_t stream,
     if (p.split) {
         if (P.upcat) cudaLaunchKernelEx(&cfg, conv_tc_kernel<5, true, kEpiWarpsLarge, kProducerWarpsLarge, 0, 1>, P.tmA, P.tmW, P.tmO, p);
         else cudaLaunchKernelEx(&cfg, conv_tc_kernel<15, false, kEpiWarpsLarge, 0, 0, 1>, P.tmA, P.tmW, P.tmO, p);
+    } else if (p.hd) {
+        // last decoder block, only the network output wanted: head-only instantiation
+        cudaLaunchKernelEx(&cfg, conv_tc_kernel<5, true, kEpiWarpsSmall, kProducerWarpsSmall, 0, 0, 1>, P.tmA, P.tmW, P.tmO, p);
     } else if (P.upcat && p.mg) {
         if (!P.small) cudaLaunchKernelEx(&cfg, conv_tc_kernel<5, true, kEpiWarpsLarge, kProducerWarpsLarge, 1>, P.tmA, P.tmW, P.tmO, p);
         else cudaLaunchKernelEx(&cfg, conv_tc_kernel<5, true, kEpiWarpsSmall, kProducerWarpsSmall, 1>, P.tmA, P.tmW, P.tmO, p);
