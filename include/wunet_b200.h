@@ -109,6 +109,24 @@ int wunet_stream_submit(wunet_ctx *ctx, const float *x_host, float *y_host, int 
 int wunet_stream_wait(wunet_ctx *ctx, int ticket);
 
 /*
+ * Host-side data path around the streaming operator - pure host code, no CUDA call:
+ * wunet_frame_clips_*() does for MANY clips what enhancement.py:57-62 does for one (zero-pad the 1-D clip to a multiple of
+ * sample_length, split it into chunks): clip i occupies max(1, ceil(lengths[i] / sample_length)) consecutive rows of
+ * frames[total_frames][sample_length], clips follow each other in order, the remaining rows are zero-filled (silent frames
+ * that keep the batch size constant). The _i16 form takes 16-bit PCM as stored in a wav file and converts it like the
+ * reference's loader does (librosa.load / soundfile: sample / 32768), fused into the same pass.
+ * wunet_unframe_clips_f32() is the inverse for the model output: concatenate each clip's chunks and drop the padding
+ * (enhancement.py:68-71) into caller-allocated clips_out[i][lengths[i]]. `nthreads` host threads share the rows.
+ * frames should be the pinned staging buffer handed to wunet_stream_submit().
+ */
+int wunet_frame_clips_f32(const float *const *clips, const long long *lengths, int nclips, int sample_length, float *frames,
+                          long long total_frames, int nthreads);
+int wunet_frame_clips_i16(const int16_t *const *clips, const long long *lengths, int nclips, int sample_length, float *frames,
+                          long long total_frames, int nthreads);
+int wunet_unframe_clips_f32(const float *frames, float *const *clips_out, const long long *lengths, int nclips, int sample_length,
+                            long long total_frames, int nthreads);
+
+/*
  * Test/diagnostic hook: copy the full-resolution output of block `block` from the workspace of the
  * LAST wunet_forward() call (same ctx, same workspace, B, T, precision) to out_dev as fp32
  * [B,Cout,L] (the reference's NCL layout) — what a forward hook on encoder[i] / middle /

@@ -120,7 +120,7 @@ def test_library_builds_and_exports_header_symbols():
     so = wbuild.build()
     lib = ctypes.CDLL(so)
     header = open(os.path.join(ROOT, "include", "wunet_b200.h")).read()
-    declared = sorted(set(re.findall(r"\b(wunet_[a-z_]+)\s*\(", header)))
+    declared = sorted(set(re.findall(r"\b(wunet_[a-z0-9_]+)\s*\(", header)))
     assert declared, "no declarations parsed"
     for sym in declared:
         assert hasattr(lib, sym), f"{sym} declared in include/wunet_b200.h but not exported"

@@ -45,6 +45,10 @@ def load() -> ctypes.CDLL:
     lib.wunet_stream_submit.argtypes = [vp, vp, vp, ci, ci, ci, ctypes.POINTER(ci)]
     lib.wunet_stream_wait.argtypes = [vp, ci]
     lib.wunet_read_level.argtypes = [vp, ci, vp, ci, ci, ci, vp, vp]
+    ll = ctypes.c_longlong
+    lib.wunet_frame_clips_f32.argtypes = [vp, vp, ci, ci, vp, ll, ci]
+    lib.wunet_frame_clips_i16.argtypes = [vp, vp, ci, ci, vp, ll, ci]
+    lib.wunet_unframe_clips_f32.argtypes = [vp, vp, vp, ci, ci, ll, ci]
     lib.wunet_last_launch_count.argtypes = [vp]
     lib.wunet_profile_enable.argtypes = [vp, ci]
     lib.wunet_profile_read.argtypes = [vp, vp, ci, ctypes.POINTER(ci)]
@@ -68,6 +72,7 @@ EXPORTED_SYMBOLS = [
     "wunet_set_weights", "wunet_workspace_bytes", "wunet_forward", "wunet_forward_host", "wunet_stream_submit", "wunet_stream_wait", "wunet_read_level",
     "wunet_last_launch_count", "wunet_profile_enable", "wunet_profile_read", "wunet_debug_plan",
     "wunet_train_workspace_bytes", "wunet_train_forward", "wunet_train_backward", "wunet_train_backward_part",
+    "wunet_frame_clips_f32", "wunet_frame_clips_i16", "wunet_unframe_clips_f32",
 ]
 
 PLAN_FIELDS = ["L", "Cin0", "Cin1", "Cout", "Npad", "Nh", "nsplit", "Nstride", "MT", "nacc", "packed", "FR", "S", "m_tiles",

@@ -1,5 +1,9 @@
 // wunet_api.cu — the C ABI declared in include/wunet_b200.h: context, weight packing, workspace
 // carving and the kernel sequence of Model.forward (reference model/unet_basic.py:77-100).
+#include <algorithm>
+#include <cstring>
+#include <thread>
+#include <vector>
 #include "../../include/wunet_b200.h"
 #include "wunet_common.cuh"
 #include "wunet_tc.cuh"
@@ -537,6 +541,110 @@ int wunet_profile_read(wunet_ctx *c, float *ms, int capacity, int *count)
     CUDA_TRY(cudaEventSynchronize(c->ev[c->ev_recorded - 1]));
     for (int i = 0; i < nseg; ++i) CUDA_TRY(cudaEventElapsedTime(&ms[i], c->ev[i], c->ev[i + 1]));
     *count = nseg;
+    return WUNET_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// host-side data path: clips <-> zero-padded 16384-sample frames, the loop bodies of
+// enhancement.py:57-62 / :68-71 for many clips at once, on several host threads (the single-threaded numpy copies of the
+// Python shim were what bounded enhance_waveforms at ~26 k frames/s per process, a fifth of the device rate)
+// ---------------------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct FrameJob {
+    const void *const *clips; const long long *len; int nclips; int SL; long long total; float scale;
+    std::vector<long long> first;        // first frame of clip i; first[nclips] = frames used
+};
+
+inline int build_job(FrameJob &j)
+{
+    j.first.resize((size_t)j.nclips + 1);
+    long long f = 0;
+    for (int i = 0; i < j.nclips; ++i) {
+        if (j.len[i] < 0 || (j.len[i] > 0 && !j.clips[i])) return -1;
+        j.first[i] = f;
+        f += std::max<long long>(1, (j.len[i] + j.SL - 1) / j.SL);     // an empty clip still takes one (silent) frame
+    }
+    j.first[j.nclips] = f;
+    return f <= j.total ? 0 : -2;
+}
+
+template <class Fn> void run_threads(long long nitems, int nthreads, Fn fn)
+{
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 64) nthreads = 64;
+    if ((long long)nthreads > nitems) nthreads = (int)std::max<long long>(1, nitems);
+    if (nthreads == 1) { fn(0, nitems); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; ++t)
+        th.emplace_back([=]() { fn(nitems * t / nthreads, nitems * (t + 1) / nthreads); });
+    for (auto &x : th) x.join();
+}
+
+template <class T> int frame_clips(FrameJob &j, float *frames, int nthreads)
+{
+    if (!frames || j.SL <= 0 || j.nclips < 0 || j.total < 0 || (j.nclips > 0 && (!j.clips || !j.len))) return fail(WUNET_EINVAL, "frame_clips: bad argument");
+    const int rc = build_job(j);
+    if (rc == -1) return fail(WUNET_EINVAL, "frame_clips: negative length or null clip");
+    if (rc == -2) return fail(WUNET_EINVAL, "frame_clips: %lld frames needed, room for %lld", j.first[j.nclips], j.total);
+    const FrameJob *jp = &j;
+    run_threads(j.total, nthreads, [jp, frames](long long f0, long long f1) {
+        const FrameJob &q = *jp;
+        int ci = (int)(std::upper_bound(q.first.begin(), q.first.end(), f0) - q.first.begin()) - 1;   // clip holding frame f0
+        for (long long f = f0; f < f1; ++f) {
+            float *dst = frames + f * q.SL;
+            if (f >= q.first[q.nclips]) { std::memset(dst, 0, sizeof(float) * q.SL); continue; }     // silent frames behind the clips
+            while (f >= q.first[ci + 1]) ++ci;
+            const long long off = (f - q.first[ci]) * q.SL;
+            const long long n = std::max<long long>(0, std::min<long long>(q.SL, q.len[ci] - off));
+            const T *src = static_cast<const T *>(q.clips[ci]) + off;
+            if (sizeof(T) == sizeof(float)) std::memcpy(dst, src, sizeof(float) * n);
+            else for (long long k = 0; k < n; ++k) dst[k] = (float)src[k] * q.scale;
+            if (n < q.SL) std::memset(dst + n, 0, sizeof(float) * (q.SL - n));                        // enhancement.py:58 padding
+        }
+    });
+    return WUNET_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int wunet_frame_clips_f32(const float *const *clips, const long long *lengths, int nclips, int sample_length, float *frames,
+                          long long total_frames, int nthreads)
+{
+    FrameJob j{reinterpret_cast<const void *const *>(clips), lengths, nclips, sample_length, total_frames, 1.f, {}};
+    return frame_clips<float>(j, frames, nthreads);
+}
+
+int wunet_frame_clips_i16(const int16_t *const *clips, const long long *lengths, int nclips, int sample_length, float *frames,
+                          long long total_frames, int nthreads)
+{
+    FrameJob j{reinterpret_cast<const void *const *>(clips), lengths, nclips, sample_length, total_frames, 1.f / 32768.f, {}};
+    return frame_clips<int16_t>(j, frames, nthreads);
+}
+
+int wunet_unframe_clips_f32(const float *frames, float *const *clips_out, const long long *lengths, int nclips, int sample_length,
+                            long long total_frames, int nthreads)
+{
+    if (!frames || sample_length <= 0 || nclips < 0 || (nclips > 0 && (!clips_out || !lengths))) return fail(WUNET_EINVAL, "unframe_clips: bad argument");
+    FrameJob j{reinterpret_cast<const void *const *>(clips_out), lengths, nclips, sample_length, total_frames, 1.f, {}};
+    const int rc = build_job(j);
+    if (rc == -1) return fail(WUNET_EINVAL, "unframe_clips: negative length or null clip");
+    if (rc == -2) return fail(WUNET_EINVAL, "unframe_clips: %lld frames needed, %lld given", j.first[j.nclips], j.total);
+    const FrameJob *jp = &j;
+    run_threads(j.first[nclips], nthreads, [jp, frames, clips_out](long long f0, long long f1) {
+        const FrameJob &q = *jp;
+        int ci = (int)(std::upper_bound(q.first.begin(), q.first.end(), f0) - q.first.begin()) - 1;
+        for (long long f = f0; f < f1; ++f) {
+            while (f >= q.first[ci + 1]) ++ci;
+            const long long off = (f - q.first[ci]) * q.SL;
+            const long long n = std::max<long long>(0, std::min<long long>(q.SL, q.len[ci] - off));   // the trim of enhancement.py:69
+            if (n > 0) std::memcpy(clips_out[ci] + off, frames + f * q.SL, sizeof(float) * n);
+        }
+    });
     return WUNET_OK;
 }
 
