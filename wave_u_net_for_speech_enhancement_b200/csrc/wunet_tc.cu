@@ -1988,6 +1988,7 @@ struct TcState {
     bool headk = false;                // WUNET_TC_HEADK=1: head-only instantiation for the last block (bit-identical; slower at the
                                        // tiling its shared-memory ring allows)
     int head_mt = 1;                   // its M sub-tiles per CTA (WUNET_TC_HEADMT)
+    int enc_l2promo = 256;             // L2 promotion of the encoders' decimated input views (WUNET_TC_L2PROMO = 0 / 64 / 128 / 256)
     bool attr_set = false;
     bool pdl = false;                  // programmatic dependent launch between the blocks (WUNET_TC_PDL=1); measured slower, off
     bool merge = true;                 // merged tail chunks (WUNET_TC_MERGE=0 switches them off for A/B measurements)
@@ -2089,6 +2090,7 @@ int tc_set_weights(TcState **pst, int n, int ci, const TcBlockSrc *blocks, int n
         if (const char *xe = getenv("WUNET_TC_PFLATE")) st->pf_late = xe[0] == '1';
         if (const char *xe = getenv("WUNET_TC_HEADK")) st->headk = xe[0] == '1';
         if (const char *xe = getenv("WUNET_TC_HEADMT")) st->head_mt = std::max(1, std::min(4, atoi(xe)));
+        if (const char *xe = getenv("WUNET_TC_L2PROMO")) st->enc_l2promo = atoi(xe);
 #ifdef WUNET_TC_TRACE
         if (const char *tl = getenv("WUNET_TC_TRACE_LEVEL")) {
             st->trace_level = atoi(tl);
@@ -2184,15 +2186,20 @@ static int make_map_plain(TcState *st, CUtensorMap *m, const void *base, uint64_
     return 0;
 }
 
+// l2promo: L2 fetch granularity of the map's loads in bytes (0 = none). The decimated views of the encoders (every second row)
+// take a smaller one than the dense views: with 256-byte promotion the skipped rows are fetched from DRAM as well.
 static int make_map(TcState *st, CUtensorMap *m, const void *base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1_bytes,
-                    uint64_t s2_bytes, uint32_t b0, uint32_t b1, uint32_t b2)
+                    uint64_t s2_bytes, uint32_t b0, uint32_t b1, uint32_t b2, int l2promo = 256)
 {
     cuuint64_t gdim[3] = {d0, d1, d2};
     cuuint64_t gstr[2] = {s1_bytes, s2_bytes};
     cuuint32_t box[3] = {b0, b1, b2};
     cuuint32_t estr[3] = {1, 1, 1};
+    const CUtensorMapL2promotion promo = l2promo >= 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                                         : l2promo >= 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                         : l2promo >= 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_NONE;
     const CUresult r = st->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(base), gdim, gstr, box, estr,
-                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo,
                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
         return tc_fail("cuTensorMapEncodeTiled failed (%d): dims %llu,%llu,%llu strides %llu,%llu box %u,%u,%u", (int)r,
@@ -2658,7 +2665,7 @@ static int build_plan(TcState *st, const float *x, float *y, int B, int T, void 
             // decimated view of the previous encoder output: element (c, l, b) -> prev[b][2l][c]   (o[:, :, ::2])
             const int Cp = lv.cin0, Lp = 2 * L;
             const uint32_t b1 = p.packed ? (uint32_t)p.S : (uint32_t)p.R1, b2 = p.packed ? (uint32_t)p.FR : 1u;
-            if (make_map(st, &P.tmA, lvl(i - 1), cm * Cp, L, B, (uint64_t)2 * cm * Cp * 2, (uint64_t)Lp * cm * Cp * 2, 64, b1, b2)) return -1;
+            if (make_map(st, &P.tmA, lvl(i - 1), cm * Cp, L, B, (uint64_t)2 * cm * Cp * 2, (uint64_t)Lp * cm * Cp * 2, 64, b1, b2, st->enc_l2promo)) return -1;
         } else {
             const int e = 2 * n - i;                        // skip = encoder e's full-resolution output
             const int Cs = lv.cin1;
