@@ -370,8 +370,22 @@ class Model(nn.Module):
         x = x.contiguous()
         return x if x.data_ptr() % 16 == 0 else x.clone(memory_format=torch.contiguous_format)
 
+    def _empty_batch(self, x: torch.Tensor) -> Optional[torch.Tensor]:
+        """A batch of zero frames: the reference's eval forward returns an empty [0, 1, T] tensor (every layer accepts an empty
+        batch) and still raises from torch.cat for a bad length; nothing to launch here."""
+        if x.shape[0] != 0:
+            return None
+        T = int(x.shape[-1])
+        if T < 1 or T % (1 << self.n_layers) != 0:
+            raise _lib.WunetError(f"input length T={T} is not a multiple of 2^n_layers={1 << self.n_layers} (the reference raises "
+                             "from torch.cat, model/unet_basic.py:95)")
+        return torch.empty_like(x)
+
     def _forward_native(self, x: torch.Tensor) -> torch.Tensor:
         self._check_input(x)
+        empty = self._empty_batch(x)
+        if empty is not None:
+            return empty
         if not x.is_cuda:
             raise RuntimeError("wave_u_net_for_speech_enhancement_b200 has no CPU fallback: move the model and the "
                                "input to a CUDA (sm_100a) device")
@@ -398,6 +412,9 @@ class Model(nn.Module):
             raise RuntimeError("forward_host takes a host tensor")
         if self.training:
             raise NotImplementedError("forward_host is eval-only")
+        empty = self._empty_batch(x_host)
+        if empty is not None:
+            return empty if out is None else out
         x_host = x_host.contiguous()
         device = self.out[0].weight.device
         if device.type != "cuda":
