@@ -1,3 +1,4 @@
+# gpurun --gpus 8 -- 'bash tools/gpu_8gpu_benches.sh': train / enhance / forward benches on 8 GPUs and the 2-rank NCCL test.
 mkdir -p gpurun_out/r2m
 cd /root/repo
 export NCCL_DEBUG=WARN

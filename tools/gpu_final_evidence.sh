@@ -1,3 +1,4 @@
+# The round's final evidence pass on one GPU: ncu launch list, ncu --set full capture, bench.py, GPU tests.
 mkdir -p gpurun_out/r2y
 cd /root/repo
 O=gpurun_out/r2y

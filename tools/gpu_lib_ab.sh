@@ -1,3 +1,5 @@
+# A/B of variant builds of the library (WUNET_SO_OUT=... WUNET_WAIT_NS=... python -m wave_u_net_for_speech_enhancement_b200.build --force)
+# on a GPU box: per-block times of each build through tools/lib_times.py. Run with gpurun -- 'bash tools/gpu_lib_ab.sh'.
 mkdir -p gpurun_out/r2s
 cd /root/repo
 L=/root/repo/wave_u_net_for_speech_enhancement_b200/build

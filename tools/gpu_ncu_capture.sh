@@ -1,3 +1,4 @@
+# ncu launch list + --set full capture of one bf16 forward (B=256); summarise with tools/ncu_summarize.py.
 mkdir -p gpurun_out/r2k
 cd /root/repo
 K='regex:conv_tc_kernel|enc0_kernel|gemm_tc_kernel'

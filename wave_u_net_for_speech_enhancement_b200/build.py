@@ -48,7 +48,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         common += ["-Xptxas", "-v"]
     if os.environ.get("WUNET_TC_TRACE"):
         common += ["-DWUNET_TC_TRACE"]
-    for macro in ("WUNET_WAIT_NS", "WUNET_WAIT_NS_MMA", "WUNET_OPERAND_FENCE"):    # development: mbarrier suspend-time hints (A/B builds, tools/lib_ab.sh)
+    for macro in ("WUNET_WAIT_NS", "WUNET_WAIT_NS_MMA", "WUNET_OPERAND_FENCE"):    # development: mbarrier suspend-time hints (A/B builds, tools/gpu_lib_ab.sh, tools/lib_times.py)
         if os.environ.get(macro):
             common += [f"-D{macro}={int(os.environ[macro])}"]
     if os.environ.get("WUNET_TN_DEBUG"):
