@@ -241,6 +241,27 @@ def test_bf16_head_only_kernel_is_bit_identical(state_full):
     assert np.abs(y1[[0, 63, 127]] - want).max() <= BF16_OUT_TOL
 
 
+def test_bf16_large_ragged_batch_and_long_frames(state_full):
+    """Sizes past the benchmark's: a batch of 1000 frames (no multiple of any tile / packing factor; 12 GB workspace) and
+    frames of 65536 samples (4x the reference's sample_length: 4x the tiles per frame on every level). Oracle-checked frames
+    + agreement with the same frames run in a batch of 256 (bit exact: batches >= 64 share their K-loop order)."""
+    B = 1000
+    x = wo.make_input(B, 16384, seed=4321)
+    m = bf16_model(12, 24, state_full)
+    y = run(m, x)
+    assert y.shape == (B, 1, 16384) and np.isfinite(y).all()
+    pick = [0, 255, 256, 511, 777, 998, 999]
+    want = wo.COracle(12, 24).forward(state_full, x[pick])
+    assert np.abs(y[pick] - want).max() <= BF16_OUT_TOL
+    assert np.array_equal(run(m, x[744:1000]), y[744:1000])
+    T = 65536
+    xl = wo.make_input(3, T, seed=97)
+    yl = run(m, xl)
+    wantl = wo.COracle(12, 24).forward(state_full, xl[1:2])
+    assert np.abs(yl[1:2] - wantl).max() <= BF16_OUT_TOL
+    assert np.array_equal(run(m, xl[[2, 0, 1]]), yl[[2, 0, 1]])
+
+
 def test_bf16_edge_vectors(golden_dir, state_full):
     g = np.load(os.path.join(golden_dir, "edges_n12_c24.npz"))
     m = bf16_model(12, 24, state_full)
