@@ -79,6 +79,36 @@ def test_native_framing_ragged_empty_and_reused_buffer():
         assert b.dtype == np.float32 and np.array_equal(b, c)
 
 
+def test_native_framing_round_trip_property():
+    """Random clip lists (hypothesis): frame -> unframe is the identity, every pad sample is zero, the index matches the
+    per-clip chunk counts of enhancement.py:57-62, for any thread count."""
+    from hypothesis import given, settings, strategies as hst
+
+    @settings(max_examples=40, deadline=None)
+    @given(hst.lists(hst.integers(min_value=0, max_value=5 * S + 3), min_size=1, max_size=9), hst.integers(1, 8), hst.integers(1, 7))
+    def check(lengths, threads, round_to):
+        rng = np.random.default_rng(sum(lengths) + threads)
+        clips = [rng.standard_normal(n).astype(np.float32) for n in lengths]
+        old = enhance.HOST_THREADS
+        enhance.HOST_THREADS = threads
+        try:
+            frames, index = enhance.frame_clips(clips, S, pin=False, round_to=round_to)
+            flat = frames.numpy().reshape(-1).copy()
+            back = enhance.unframe_clips(frames, index)
+        finally:
+            enhance.HOST_THREADS = old
+        assert frames.shape[0] % round_to == 0
+        f = 0
+        for (f0, nf, n), c, b in zip(index, clips, back):
+            assert f0 == f and nf == max(1, -(-n // S)) and n == len(c)
+            assert np.array_equal(flat[f0 * S:f0 * S + n], c) and not flat[f0 * S + n:(f0 + nf) * S].any()
+            assert np.array_equal(b, c)
+            f += nf
+        assert not flat[f * S:].any()
+
+    check()
+
+
 def test_native_framing_int16_pcm_matches_loader_scaling():
     """16-bit PCM clips are converted like librosa.load / soundfile do (sample / 32768), in the framing pass."""
     rng = np.random.default_rng(4)
