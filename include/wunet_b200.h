@@ -185,6 +185,13 @@ int wunet_train_backward_part(wunet_ctx *ctx, const float *x, const float *y, co
  *  [27] threads per CTA  [28] CTAs per SM  [29] grid  [30] small (two-CTAs-per-SM) flavour  [31] tiles per frame */
 int wunet_debug_plan(int n_layers, int channels_interval, int B, int T, int block, int num_sms, int *fields, int capacity);
 
+/* Introspection for tests, host-only: the "row-pair" form of one conv block's weights (WUNET_TC_PAIR). A block
+ * with `ksize` taps over positions (w = [cout][cin0 + cin1][ksize] fp32, reference layout; model/unet_basic.py:10,23) is the same
+ * operator as a block with 2*((ksize-1)/2+1)/2+1 taps over PAIRS of positions: row m = positions 2m and 2m+1, 2*cout output
+ * columns, 2*(cin0 + cin1) virtual input channels (decoder != 0: the first segment in the producers' [q0 range | q1 range] order).
+ * Writes out[2*cout][2*(cin0+cin1)][taps'] fp32 - what the library packs for the tensor cores. No reference counterpart. */
+int wunet_debug_pair_weights(const float *w, int cout, int cin0, int cin1, int ksize, int decoder, float *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -53,6 +53,7 @@ def load() -> ctypes.CDLL:
     lib.wunet_profile_enable.argtypes = [vp, ci]
     lib.wunet_profile_read.argtypes = [vp, vp, ci, ctypes.POINTER(ci)]
     lib.wunet_debug_plan.argtypes = [ci, ci, ci, ci, ci, ci, ctypes.POINTER(ci), ci]
+    lib.wunet_debug_pair_weights.argtypes = [vp, ci, ci, ci, ci, ci, vp]
     lib.wunet_train_workspace_bytes.argtypes = [vp, ci, ci]
     lib.wunet_train_workspace_bytes.restype = cs
     lib.wunet_train_forward.argtypes = [vp, vp, vp, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_float, vp, cs, vp]
@@ -70,7 +71,7 @@ def check(rc: int) -> None:
 EXPORTED_SYMBOLS = [
     "wunet_version", "wunet_last_error", "wunet_create", "wunet_destroy", "wunet_num_blocks", "wunet_block_shape",
     "wunet_set_weights", "wunet_workspace_bytes", "wunet_forward", "wunet_forward_host", "wunet_stream_submit", "wunet_stream_wait", "wunet_read_level",
-    "wunet_last_launch_count", "wunet_profile_enable", "wunet_profile_read", "wunet_debug_plan",
+    "wunet_last_launch_count", "wunet_profile_enable", "wunet_profile_read", "wunet_debug_plan", "wunet_debug_pair_weights",
     "wunet_train_workspace_bytes", "wunet_train_forward", "wunet_train_backward", "wunet_train_backward_part",
     "wunet_frame_clips_f32", "wunet_frame_clips_i16", "wunet_unframe_clips_f32",
 ]

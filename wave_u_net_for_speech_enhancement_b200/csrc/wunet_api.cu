@@ -523,6 +523,12 @@ int wunet_debug_plan(int n_layers, int channels_interval, int B, int T, int bloc
     return WUNET_OK;
 }
 
+int wunet_debug_pair_weights(const float *w, int cout, int cin0, int cin1, int ksize, int decoder, float *out)
+{
+    if (tc_debug_pair_weights(w, cout, cin0, cin1, ksize, decoder, out)) return fail(WUNET_EINVAL, "%s", tc_error());
+    return WUNET_OK;
+}
+
 int wunet_profile_enable(wunet_ctx *c, int enable)
 {
     if (!c) return fail(WUNET_EINVAL, "null context");

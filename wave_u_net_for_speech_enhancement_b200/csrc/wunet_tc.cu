@@ -360,7 +360,12 @@ __device__ __forceinline__ ChunkInfo chunk_info(const TcParams &p, int c)
 // HD = 1: the last decoder block when only the network output is wanted (fused head, the block's own activations are not
 // stored; Cout <= 32, one N tile): a straight-line head-only epilogue and 8-row producer items (see the roles below). The
 // arithmetic and its order are those of the generic instantiation: bit-identical results.
-template <int KS, bool UPCAT, int EW, int PW, int MG, int SP = 0, int HD = 0>
+// PR = 1 ("row-pair" instantiation, round 2 second half): the block is run on PAIRS of positions - operand row m holds positions
+// 2m and 2m+1 side by side ([L/2][2 C] is the same memory as [L][C]), the output row their 2 Cout results, and the K = 5 taps
+// become 3 taps over row pairs with Toeplitz-expanded weights (pair_weight() below). N doubles (the M=128 MMA of a narrow block
+// is bound by its operand reads, 32 + N/4 cycles) and the K loop shrinks; for the decoder the producers write the upsampled
+// half as [q0: 32 channels | q1: the same 32 channels] per 64-wide chunk and the fused head produces two samples per row.
+template <int KS, bool UPCAT, int EW, int PW, int MG, int SP = 0, int HD = 0, int PR = 0>
 __global__ void __launch_bounds__(64 + 32 * (EW + PW), EW == kEpiWarpsSmall ? 2 : 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmO, const TcParams p)
@@ -432,8 +437,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int i = threadIdx.x; i < p.Npad; i += blockDim.x) ss[i] = p.ss[i];
         if (p.head) {
             float *hw = reinterpret_cast<float *>(base_ptr + sm.ss) + 2 * p.Npad;
-            if ((int)threadIdx.x <= p.Cout) hw[threadIdx.x] = p.head_w[threadIdx.x];
-            if ((int)threadIdx.x == p.Cout + 1) hw[threadIdx.x] = p.head_b[0];
+            const int hc = PR != 0 ? p.Cout >> 1 : p.Cout;            // channels the 1x1 head sums over (row-pair mode: Cout = 2 hc)
+            if ((int)threadIdx.x <= hc) hw[threadIdx.x] = p.head_w[threadIdx.x];
+            if ((int)threadIdx.x == hc + 1) hw[threadIdx.x] = p.head_b[0];
         }
         }
     }
@@ -643,6 +649,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (warp == 0 && lane == 0) TRACE(2, tr2);
             // fused head: fetch the raw-input samples of this thread's rows before waiting for the accumulators
             float xin0 = 0.f, xin1 = 0.f, xin2 = 0.f, xin3 = 0.f;     // scalars (not an array): they must stay in registers
+            if (PR != 0 && p.head && b0 < p.B) {
+                // row-pair mode: row l holds samples 2l and 2l+1 (MT <= 2: xin0/xin1 = the pair of sub-tile 0, xin2/xin3 of sub-tile 1)
+                const int lb = l0 + q * 32 + lane;
+                const float2 *xp2 = reinterpret_cast<const float2 *>(p.x + (size_t)b0 * p.T) + lb;
+                if (lb < p.L) { const float2 v2 = __ldg(xp2); xin0 = v2.x; xin1 = v2.y; }
+                if (p.MT > 1 && lb + 128 < p.L) { const float2 v2 = __ldg(xp2 + 128); xin2 = v2.x; xin3 = v2.y; }
+            } else
             if (p.head && b0 < p.B) {
                 const float *xp = p.x + (size_t)b0 * p.T + l0 + q * 32 + lane;
                 const int lb = l0 + q * 32 + lane;
@@ -705,7 +718,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (p.packed) { const int f = row / p.S; bb = b0 + f; l = row - f * p.S; if (f >= p.FR) l = p.L; }
                 else { bb = b0; l = l0 + row; }
                 const bool valid = (bb < p.B) && (l < p.L);
-                float hacc = p.head ? hw[p.Cout + 1] : 0.f;
+                const int hc = PR != 0 ? p.Cout >> 1 : p.Cout;
+                float hacc = p.head ? hw[hc + 1] : 0.f;
+                float haccb = hacc;                               // row-pair mode: the second sample of the row (columns hc .. 2 hc - 1)
                 bool did = false;                                 // this warp converted the row's (single) chunk
 #pragma unroll 1
                 for (int cc = 0; cc < ncc; ++cc) {
@@ -749,6 +764,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             } else if (SP == 0 && p.out != nullptr && valid && col_ok) {
                                 *reinterpret_cast<uint4 *>(p.out + ((size_t)bb * p.L + l) * p.Cout + n0 + col) = o;
                             }
+                            if (PR != 0 && p.head) {
+                                // hc % 8 == 0: a group of 8 columns belongs to one of the two samples
+                                if (col < hc) {
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) hacc = fmaf(hw[col + j], f[j], hacc);
+                                } else if (col < p.Cout) {
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) haccb = fmaf(hw[col - hc + j], f[j], haccb);
+                                }
+                            } else
                             if (p.head) {
 #pragma unroll
                                 for (int j = 0; j < 8; ++j)
@@ -767,6 +792,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                 }
+                if (PR != 0 && p.head && valid) {
+                    // row-pair mode (one epilogue warp per quadrant: this warp converted every column of the row): two samples
+                    hacc = fmaf(hw[hc], mt == 0 ? xin0 : xin2, hacc);
+                    haccb = fmaf(hw[hc], mt == 0 ? xin1 : xin3, haccb);
+                    *reinterpret_cast<float2 *>(p.y + (size_t)bb * p.T + 2 * l) = make_float2(tanh_fast(hacc), tanh_fast(haccb));
+                } else
                 if (p.head && valid && did) {
                     // cat([o, input], 1) -> Conv1d(C+1 -> 1, k=1) -> Tanh   (model/unet_basic.py:98-99); Cout <= 32: one chunk
                     hacc = fmaf(hw[p.Cout], mt == 0 ? xin0 : (mt == 1 ? xin1 : (mt == 2 ? xin2 : xin3)), hacc);
@@ -788,8 +819,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // since src = l*(Lin-1)/(2Lin-1)) are fetched into registers one work unit AHEAD, so their DRAM latency overlaps the
         // wait for the shared-memory stage. The head-only instantiation (HD: 24 upsampled channels = 3 vectors per row) uses
         // 8-row items: with 16-row items only 48 of its 128 producer threads had work (ncu, round 2).
-        constexpr int RPI = HD != 0 ? 8 : 16;             // rows per item
-        constexpr int WR = RPI / 2 + 2;                   // previous-level rows per item
+        // Row-pair instantiation (PR): operand row m = positions 2m (q = 0) and 2m+1 (q = 1), which interpolate between previous-level
+        // rows (m-1, m) and (m, m+1). An item is 8 operand rows x one 16-byte vector of REAL channels and writes both q halves of
+        // the chunk ([q0: range | q1: the same range], 32 channels per full chunk) from a window of 10 previous-level rows.
+        constexpr int RPI = (HD != 0 || PR != 0) ? 8 : 16;   // rows per item
+        constexpr int WR = PR != 0 ? 10 : RPI / 2 + 2;       // previous-level rows per item
         const int pt = (warp - kFirstProducer) * 32 + lane;
         int sa = 0, pa = 0;
         int tr4 = 0; (void)tr4;
@@ -802,6 +836,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // loads of item `item` of unit (frame ub0, first row ul0, K-loop position c) into the window
         auto fetch = [&](int ub0, int ul0, int c, int item) {
             const ChunkInfo u = chunk_info<UPCAT, MG, SP>(p, c);
+            if (PR != 0) {
+                const int nvr = u.nvec >> 1, creal = p.Cin0 >> 1;              // vectors of real channels in this chunk
+                if (item >= nruns * nvr) return;
+                const int run = item / nvr, vec = item - run * nvr;
+                const int ch = u.idx * 32 + vec * 8;
+                const int ms = ul0 - PAD + RPI * run;                          // operand row = previous-level row
+                const bool chok = ch < creal && ub0 < p.B;
+                const __nv_bfloat16 *pb = p.prev + (size_t)ub0 * p.Lin * creal + ch;
+#pragma unroll
+                for (int qq = 0; qq < WR; ++qq) {
+                    int m = ms - 1 + qq;
+                    m = m < 0 ? 0 : (m > p.Lin - 1 ? p.Lin - 1 : m);
+                    xr[qq] = chok ? __ldg(reinterpret_cast<const uint4 *>(pb + (size_t)m * creal)) : make_uint4(0u, 0u, 0u, 0u);
+                }
+                return;
+            }
             const int nvec = u.nvec;
             if (item >= nruns * nvec) return;
             const int run = item / nvec, vec = item - run * nvec;
@@ -821,6 +871,35 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // (trace: ~3600 cycles per item with branches, the stage hand-off was waiting on it).
         auto emit = [&](uint8_t *dst, int l0, int c, int item, const uint4 (&w)[WR]) {
             const ChunkInfo u = chunk_info<UPCAT, MG, SP>(p, c);
+            if (PR != 0) {
+                const int nvr = u.nvec >> 1;
+                const int run = item / nvr, vec = item - run * nvr;
+                const bool chok = u.idx * 32 + vec * 8 < (p.Cin0 >> 1);
+                const int mstart = l0 - PAD + RPI * run;
+                const uint32_t drow = smem_u32(dst) + (uint32_t)(RPI * run) * 128u;
+#pragma unroll
+                for (int j = 0; j < RPI; ++j) {
+                    const int m = mstart + j;
+                    const uint32_t keep = (chok && (unsigned)m < (unsigned)p.L) ? 0xffffffffu : 0u;   // zero rows = Conv1d padding
+#pragma unroll
+                    for (int qh = 0; qh < 2; ++qh) {
+                        // position l = 2m + qh lies between previous-level rows m - 1 + qh and m + qh = window rows j + qh, j + qh + 1;
+                        // lam1 = up_scale * l - (m - 1 + qh): the generic instantiation's formula (one fused rounding), packed bf16
+                        const float lam1 = fmaf(p.up_scale, (float)(2 * m + qh), -(float)(m - 1 + qh));
+                        const __nv_bfloat162 lam = __float2bfloat162_rn(lam1);
+                        const __nv_bfloat162 *a2 = reinterpret_cast<const __nv_bfloat162 *>(&w[j + qh]);
+                        const __nv_bfloat162 *b2 = reinterpret_cast<const __nv_bfloat162 *>(&w[j + qh + 1]);
+                        __nv_bfloat162 r2[4];
+#pragma unroll
+                        for (int q4 = 0; q4 < 4; ++q4) r2[q4] = __hfma2(lam, __hsub2(b2[q4], a2[q4]), a2[q4]);
+                        uint4 o = *reinterpret_cast<const uint4 *>(r2);
+                        o.x &= keep; o.y &= keep; o.z &= keep; o.w &= keep;
+                        const int dvec = u.vo + qh * nvr + vec;                     // q1 half follows the q0 half of the chunk
+                        st_shared_v4_if(drow + (uint32_t)(j * 128 + ((dvec ^ (j & 7)) << 4)), o, RPI * run + j < p.rows_used);
+                    }
+                }
+                return;
+            }
             const int nvec = u.nvec;
             const int run = item / nvec, vec = item - run * nvec;
             const int ch = u.idx * 64 + vec * 8;
@@ -935,7 +1014,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int nvec = cu.nvec;                                // 16-byte vectors per row
                     uint8_t *dst = base_ptr + sm.a + sa * p.a_stage_bytes;
                     if (fast) {
-                        const int nitems = nruns * nvec;
+                        const int nitems = nruns * (PR != 0 ? nvec >> 1 : nvec);
 #pragma unroll 1
                         for (int itx = pt; itx < nitems; itx += NPROD) {
                             if (itx != pt) fetch(b0, l0, c, itx);            // later rounds load on demand
@@ -1712,8 +1791,11 @@ __global__ void expand_gemm_weights_kernel(const float *__restrict__ w, __nv_bfl
 // -------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256, 4) enc0_kernel(const float *__restrict__ x, const float *__restrict__ w /*[C][1][15]*/,
                                                       const float *__restrict__ scale, const float *__restrict__ shift,
-                                                      __nv_bfloat16 *__restrict__ out, int B, int T, int C, int split)
+                                                      __nv_bfloat16 *__restrict__ out, int B, int T, int C, int split,
+                                                      __nv_bfloat16 *__restrict__ even_out)
 {
+    // even_out != nullptr (row-pair mode of the next block): the even positions are written a second time, densely, as
+    // [B][T/2][C] - the decimated input o[:, :, ::2] of the next encoder block as a contiguous matrix, so that [T/4][2 C] is a view of it.
     // A block owns 1024 consecutive positions of one frame; a thread owns 4 consecutive positions and sweeps the channels
     // 8 at a time (32 accumulators, 15 taps: 480 FFMA per 2x15 broadcast LDS.128 of weights). The bf16 rows are staged in
     // shared memory ([1024][C] is one contiguous range of the channels-last output) and leave with ONE bulk async copy.
@@ -1767,6 +1849,9 @@ __global__ void __launch_bounds__(256, 4) enc0_kernel(const float *__restrict__ 
             uint8_t *srow = stage + (size_t)(4 * threadIdx.x + j) * (RC * 2) + c0 * 2;
             *reinterpret_cast<uint4 *>(srow) =
                 make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+            if (even_out != nullptr && (j & 1) == 0 && l0 + 4 * (int)threadIdx.x + j < T)
+                *reinterpret_cast<uint4 *>(even_out + ((size_t)b * (T >> 1) + ((l0 + 4 * threadIdx.x + j) >> 1)) * C + c0) =
+                    make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
             if (split) {
                 float g[8];
 #pragma unroll
@@ -1785,6 +1870,55 @@ __global__ void __launch_bounds__(256, 4) enc0_kernel(const float *__restrict__ 
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
+}
+
+// -------------------------------------------------------------------------------------------------
+// row-pair mode: a K-tap conv block over positions as a K'-tap block over PAIRS of positions
+// -------------------------------------------------------------------------------------------------
+// Row m of the pair block = positions 2m (q = 0) and 2m + 1 (q = 1); output column r * Cout + co = position 2m + r. With
+// P = (K-1)/2 and P' = (P+1)/2 the pair block has K' = 2P'+1 taps dm = -P' .. P' and
+//     W'[dm + P'][r Cout + co][v] = w[co][c(v)][2 dm + q(v) - r + P]      (zero where that tap index is outside 0 .. K-1)
+// v = virtual input channel: segment 0 (2 C0 channels) then segment 1 (2 C1 channels). Segment 1 and an encoder's segment 0
+// are the contiguous view [L/2][2 C] of a channels-last tensor: v = q C + c. A decoder's segment 0 is written by the
+// producer warps 32 real channels per 64-wide chunk, [q0: range | q1: the same range]: chunk k = v / 64 holds real channels
+// 32 k .. 32 k + w - 1 (w = min(32, C0 - 32 k)), q = (v % 64) / w. Same function on the host (wunet_debug_pair_weights, tests).
+__host__ __device__ inline int pair_taps(int K) { return 2 * ((((K - 1) / 2) + 1) / 2) + 1; }
+__host__ __device__ inline float pair_weight(const float *w, int Cout, int C0, int C1, int K, int dec, int cov, int v, int tv)
+{
+    const int P = (K - 1) / 2, Pp = (P + 1) / 2;
+    const int r = cov / Cout, co = cov - r * Cout;
+    int q, c;
+    if (v < 2 * C0) {
+        if (dec) {
+            const int k = v >> 6, j = v & 63, lo = 32 * k;
+            const int wd = (C0 - lo) < 32 ? (C0 - lo) : 32;
+            q = j / wd; c = lo + (j - q * wd);
+            if (q > 1) return 0.f;
+        } else { q = v / C0; c = v - q * C0; }
+    } else {
+        const int u = v - 2 * C0;
+        if (u >= 2 * C1) return 0.f;
+        q = u / C1; c = C0 + (u - q * C1);
+    }
+    const int t = 2 * (tv - Pp) + q - r + P;
+    if (r > 1 || t < 0 || t >= K) return 0.f;
+    return w[((size_t)co * (C0 + C1) + c) * K + t];
+}
+// wv[2 Cout][2 (C0 + C1)][K'] fp32 (the layout pack_tc_kernel reads), scale / shift replicated for both halves of the columns
+__global__ void expand_pair_weights_kernel(const float *__restrict__ w, const float *__restrict__ scale, const float *__restrict__ shift,
+                                           float *__restrict__ wv, float *__restrict__ scale_v, float *__restrict__ shift_v, int Cout,
+                                           int C0, int C1, int K, int dec)
+{
+    const int Kp = pair_taps(K), Cv = 2 * (C0 + C1);
+    const long long n = (long long)2 * Cout * Cv * Kp;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const int tv = (int)(i % Kp);
+        const int v = (int)((i / Kp) % Cv);
+        const int cov = (int)(i / ((long long)Kp * Cv));
+        wv[i] = pair_weight(w, Cout, C0, C1, K, dec, cov, v, tv);
+    }
+    if (i < 2 * Cout) { scale_v[i] = scale[i % Cout]; shift_v[i] = shift[i % Cout]; }
 }
 
 // weights [Cout][Cin][K] fp32 -> [K][Npad][Ktot] bf16, K axis = [seg0 padded to 64 | seg1 padded to 64], zero padded
@@ -1920,6 +2054,7 @@ struct TcPlanLevel {
     bool upcat;
     bool small;                        // two-CTAs-per-SM kernel flavour
     int kind = 0;                      // reported by wunet_debug_plan in the 'small' field: 2 = dense GEMM over frames (gemm_tc_kernel)
+    int pair = 0;                      // row-pair mode: 1 = encoder block (conv_tc_kernel<9, false, ...>), 2 = last decoder block (<3, true, ..., PR = 1>)
 };
 
 // Per-block tiling overrides for tuning sweeps: WUNET_TC_OVR="<block>:key=val,key=val;<block>:..." with keys
@@ -1976,7 +2111,8 @@ static const TunedTiling kTuned[] = {
 
 struct TcPlan {
     std::vector<TcPlanLevel> lv;       // index 1..2n (0 = enc0 handled separately)
-    std::vector<size_t> off;           // workspace offsets of the 2n+1 block outputs
+    std::vector<size_t> off;           // workspace offsets of the 2n+1 block outputs (+ the even-row copy of block 0)
+    bool even_copy = false;            // block 1 runs in row-pair mode: enc0 also writes its even rows densely (off[2n+1])
 };
 
 struct TcState {
@@ -1996,6 +2132,12 @@ struct TcState {
     bool gemm = true;                  // dense GEMM over frames for blocks of at most 16 samples (WUNET_TC_GEMM=0 switches it off)
     bool tn = false;                   // taps-in-N kernel for the shallow blocks: correct but not yet faster than conv_tc_kernel on a B200
                                        // (profiles/r02_tn_*.txt), so opt-in: WUNET_TC_TN=1
+    // row-pair mode (WUNET_TC_PAIR bit 0: first tensor-core encoder block, bit 1: last decoder block + head): virtual blocks with
+    // doubled channel counts and Toeplitz-expanded weights (pair_weight), planned on frames of half the length
+    int pair_mask = 0;
+    TcLevel pair_lv[2];                // [0] block 1, [1] block 2n (cin0 / cin1 / cout = virtual counts, k = pair taps)
+    float *pair_w[2] = {nullptr, nullptr}, *pair_scale[2] = {nullptr, nullptr}, *pair_shift[2] = {nullptr, nullptr};
+    bool pair_ok[2] = {false, false};
     int num_sms = 148;
     cudaStream_t copy_in = nullptr, copy_out = nullptr;     // host pipeline: H2D / D2H streams
     cudaEvent_t ev_in[8] = {}, ev_out[8] = {};
@@ -2013,9 +2155,10 @@ struct TcState {
 
 const char *tc_error() { return g_tc_err; }
 
+// off[0 .. 2n] = block outputs; off[2n+1] = dense copy of block 0's even rows [B][T/2][ci] (bf16 mode; row-pair mode of block 1)
 static void tc_layout(int n, int ci, int B, int T, std::vector<size_t> &off, size_t &total, int mode = 0)
 {
-    off.resize(2 * n + 1);
+    off.resize(2 * n + 2);
     size_t cur = 0;
     for (int i = 0; i < 2 * n + 1; ++i) {
         const int L = (i <= n) ? (T >> i) : (T >> (2 * n - i));
@@ -2023,6 +2166,8 @@ static void tc_layout(int n, int ci, int B, int T, std::vector<size_t> &off, siz
         off[i] = cur;
         cur += round_up_sz((size_t)B * L * cout * sizeof(__nv_bfloat16) * (mode ? 2 : 1), 1024);
     }
+    off[2 * n + 1] = cur;
+    if (mode == 0) cur += round_up_sz((size_t)B * (T / 2) * ci * sizeof(__nv_bfloat16), 1024);
     total = cur + 1024;
 }
 
@@ -2091,6 +2236,7 @@ int tc_set_weights(TcState **pst, int n, int ci, const TcBlockSrc *blocks, int n
         if (const char *xe = getenv("WUNET_TC_HEADK")) st->headk = xe[0] == '1';
         if (const char *xe = getenv("WUNET_TC_HEADMT")) st->head_mt = std::max(1, std::min(4, atoi(xe)));
         if (const char *xe = getenv("WUNET_TC_L2PROMO")) st->enc_l2promo = atoi(xe);
+        if (const char *xe = getenv("WUNET_TC_PAIR")) st->pair_mask = atoi(xe) & 3;
 #ifdef WUNET_TC_TRACE
         if (const char *tl = getenv("WUNET_TC_TRACE_LEVEL")) {
             st->trace_level = atoi(tl);
@@ -2154,6 +2300,40 @@ int tc_set_weights(TcState **pst, int n, int ci, const TcBlockSrc *blocks, int n
                                                                                     lv.Npad, lv.Ktot, lv.mg_s, lv.mg_u);
             if (cudaGetLastError() != cudaSuccess) return tc_fail("pack_tc_merged_kernel launch failed");
         }
+    }
+    // row-pair mode: virtual blocks (doubled channel counts, pair_taps(k) taps) packed like any other block
+    for (int s = 0; s < 2; ++s) {
+        st->pair_ok[s] = false;
+        if (!(st->pair_mask & (1 << s)) || n < 2) continue;
+        const int i = s == 0 ? 1 : 2 * n;
+        const TcLevel &rl = st->levels[i];
+        // block 1: 15 taps -> 9 over pairs, the whole virtual input in one 64-channel chunk; last block: 5 taps -> 3, fused head over
+        // two samples per row (Cout a multiple of 8, at most 32), its upsampled input at least one full range of 32 channels
+        if (s == 0 && !(rl.k == 15 && rl.cin1 == 0 && rl.cin0 % 8 == 0 && 2 * rl.cin0 <= 64 && 2 * rl.cout <= 256)) continue;
+        if (s == 1 && !(rl.k == 5 && rl.cin0 % 8 == 0 && rl.cin1 % 8 == 0 && rl.cin0 >= 32 && rl.cout % 8 == 0 && rl.cout <= 32)) continue;
+        TcLevel &pv = st->pair_lv[s];
+        const int kp = pair_taps(rl.k);
+        pv.cin0 = 2 * rl.cin0; pv.cin1 = 2 * rl.cin1; pv.cout = 2 * rl.cout; pv.k = kp;
+        pv.Npad = round_up(pv.cout, 16);
+        pv.Ktot = round_up(pv.cin0, 64) + (pv.cin1 ? round_up(pv.cin1, 64) : 0);
+        pv.mg_s = pv.mg_u = 0;
+        pv.tn_cp = pv.tn_npad = pv.tn_slots = pv.tn_groups = 0;
+        const size_t nv = (size_t)pv.cout * (pv.cin0 + pv.cin1) * kp;
+        const size_t nel = (size_t)kp * pv.Npad * pv.Ktot;
+        if (!st->pair_w[s]) {
+            if (cudaMalloc(&st->pair_w[s], nv * sizeof(float)) != cudaSuccess || cudaMalloc(&st->pair_scale[s], pv.cout * sizeof(float)) != cudaSuccess ||
+                cudaMalloc(&st->pair_shift[s], pv.cout * sizeof(float)) != cudaSuccess || cudaMalloc(&pv.wp, nel * sizeof(__nv_bfloat16)) != cudaSuccess ||
+                cudaMalloc(&pv.ss, pv.Npad * sizeof(float2)) != cudaSuccess)
+                return tc_fail("cudaMalloc(row-pair weights) failed");
+        }
+        expand_pair_weights_kernel<<<(unsigned)((nv + 255) / 256), 256, 0, stream>>>(blocks[i].w, blocks[i].scale, blocks[i].shift, st->pair_w[s],
+                                                                                     st->pair_scale[s], st->pair_shift[s], rl.cout, rl.cin0,
+                                                                                     rl.cin1, rl.k, s == 1 ? 1 : 0);
+        if (cudaGetLastError() != cudaSuccess) return tc_fail("expand_pair_weights_kernel launch failed");
+        pack_tc_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, stream>>>(st->pair_w[s], st->pair_scale[s], st->pair_shift[s], pv.wp, pv.ss,
+                                                                          pv.cout, pv.cin0, pv.cin1, kp, pv.Npad, pv.Ktot);
+        if (cudaGetLastError() != cudaSuccess) return tc_fail("pack_tc_kernel (row-pair) launch failed");
+        st->pair_ok[s] = true;
     }
     return 0;
 }
@@ -2252,14 +2432,16 @@ static int sp_chunk_order(const TcLevel &lv, bool dec, unsigned char *map, Split
 // (wunet_debug_plan). Fills every tiling field of P.p and the launch shape; pointers and tensor maps are added by build_plan.
 // hd_mt > 0: the block is the last one and only the network output is wanted (head-only instantiation, see build_plan): M
 // sub-tiles per CTA for it, so that the ring of previous-level rows fits next to the input ring (small flavour only).
+// pair: row-pair mode - lv is the virtual block (doubled channel counts, pair taps) and the frames are half as long.
 static int plan_block(const TcLevel &lv, int i, int n, int B, int T, int num_sms, const std::string &ovr, TcPlanLevel &P, bool sp = false,
-                      int hd_mt = 0)
+                      int hd_mt = 0, bool pair = false)
 {
     TcParams &p = P.p;
     memset(&p, 0, sizeof(p));
     const bool dec = i > n;
     const int KS = lv.k;
-    const int L = (i <= n) ? (T >> i) : (T >> (2 * n - i));
+    const int L = ((i <= n) ? (T >> i) : (T >> (2 * n - i))) >> (pair ? 1 : 0);
+    P.pair = pair ? (dec ? 2 : 1) : 0;
     P.upcat = dec;
     p.B = B; p.L = L; p.Cout = lv.cout; p.T = T;
     p.Cin0 = lv.cin0; p.Cin1 = lv.cin1;
@@ -2303,6 +2485,7 @@ static int plan_block(const TcLevel &lv, int i, int n, int B, int T, int num_sms
     }
     // ---- tiling ---------------------------------------------------------------------------------
     TcOverride ov = parse_override(ovr, i);
+    if (pair && dec && !ov.any) parse_kv("mt=1,small=1", ov);      // fused head over row pairs: one epilogue warp per quadrant, resident weights
     if (!ov.any && B >= 128 && !sp)
         for (const TunedTiling &t : kTuned)
             if (t.L == L && t.cin0 == lv.cin0 && t.cin1 == lv.cin1 && t.cout == lv.cout && t.k == KS) parse_kv(t.kv, ov);
@@ -2452,7 +2635,8 @@ static int plan_block(const TcLevel &lv, int i, int n, int B, int T, int num_sms
     if (P.smem > (size_t)kSmemLimit) return tc_fail("level %d: smem %zu too large", i, P.smem);
 
     const bool last_block = (i == 2 * n);
-    if (last_block && lv.cout > 32) return tc_fail("fused head needs channels_interval <= 32");
+    if (last_block && lv.cout > (pair ? 64 : 32)) return tc_fail("fused head needs channels_interval <= 32");
+    if (last_block && pair && (!small || p.MT > 2)) return tc_fail("row-pair head needs the small flavour and MT <= 2");
     if (last_block && p.packed) return tc_fail("bf16 path needs frames of at least 128 samples (T=%d): the fused head works on full frames", T);
     if (last_block && p.nsplit != 1) return tc_fail("fused head needs the whole channel range in one CTA");
     return 0;
@@ -2591,10 +2775,16 @@ static int build_plan(TcState *st, const float *x, float *y, int B, int T, void 
     const uint64_t cm = sp ? 2 : 1;                      // stored channels per logical channel ([hi | lo] halves)
     char *base = static_cast<char *>(ws);
     auto lvl = [&](int i) { return reinterpret_cast<__nv_bfloat16 *>(base + pl.off[i]); };
+    pl.even_copy = false;
     for (int i = 1; i < 2 * n + 1; ++i) {
-        const TcLevel &lv = st->levels[i];
+        // row-pair mode (WUNET_TC_PAIR): block 1 and / or the last block run as virtual blocks over pairs of positions
+        const int ps = (n >= 2 && i == 1) ? 0 : ((n >= 2 && i == 2 * n) ? 1 : -1);
+        const int Lreal = (i <= n) ? (T >> i) : (T >> (2 * n - i));
+        const bool pair = ps >= 0 && !sp && st->pair_ok[ps] && Lreal % 2 == 0 && Lreal / 2 >= 128 && !st->tn &&
+                          !(ps == 1 && st->headk);
+        const TcLevel &lv = pair ? st->pair_lv[ps] : st->levels[i];
         TcPlanLevel &P = pl.lv[i];
-        if (!sp && st->gemm && parse_override(st->plan_ovr, i).any == false && plan_block_gemm(lv, i, n, B, T, st->num_sms, P)) {
+        if (!pair && !sp && st->gemm && parse_override(st->plan_ovr, i).any == false && plan_block_gemm(lv, i, n, B, T, st->num_sms, P)) {
             GemmParams &g = P.gp;
             TcLevel &lw = st->levels[i];
             const bool dec = i > n;
@@ -2626,7 +2816,7 @@ static int build_plan(TcState *st, const float *x, float *y, int B, int T, void 
                 return -1;
             continue;
         }
-        if (!sp && parse_override(st->plan_ovr, i).any == false && plan_block_tn(lv, i, n, B, T, st->num_sms, P)) {
+        if (!pair && !sp && parse_override(st->plan_ovr, i).any == false && plan_block_tn(lv, i, n, B, T, st->num_sms, P)) {
             TnParams &t = P.tn;
             const bool dec = i > n;
             const bool last = (i == 2 * n);
@@ -2649,8 +2839,8 @@ static int build_plan(TcState *st, const float *x, float *y, int B, int T, void 
             P.tmO = P.tmA;
             continue;
         }
-        const bool hd_want = (i == 2 * n) && !st->store_last && !sp && st->headk;
-        if (plan_block(lv, i, n, B, T, st->num_sms, st->plan_ovr, P, sp, hd_want ? st->head_mt : 0)) return -1;
+        const bool hd_want = (i == 2 * n) && !st->store_last && !sp && st->headk && !pair;
+        if (plan_block(lv, i, n, B, T, st->num_sms, st->plan_ovr, P, sp, hd_want ? st->head_mt : 0, pair)) return -1;
         TcParams &p = P.p;
         const bool dec = i > n;
         const int L = p.L;
@@ -2661,7 +2851,13 @@ static int build_plan(TcState *st, const float *x, float *y, int B, int T, void 
         p.x = x; p.y = y; p.head_w = st->out_w; p.head_b = st->out_b;
         p.trace = (st->trace && st->trace_level == i) ? st->trace : nullptr;
         // operand maps
-        if (!dec) {
+        if (!dec && pair) {
+            // row-pair mode: the dense copy of the previous block's even rows [B][2L][Cp/2] seen as [B][L][Cp] (two positions per row)
+            const int Cp = lv.cin0;
+            __nv_bfloat16 *even = reinterpret_cast<__nv_bfloat16 *>(base + pl.off[2 * n + 1]);
+            if (make_map(st, &P.tmA, even, Cp, L, B, (uint64_t)Cp * 2, (uint64_t)L * Cp * 2, 64, (uint32_t)p.R1, 1u)) return -1;
+            pl.even_copy = true;
+        } else if (!dec) {
             // decimated view of the previous encoder output: element (c, l, b) -> prev[b][2l][c]   (o[:, :, ::2])
             const int Cp = lv.cin0, Lp = 2 * L;
             const uint32_t b1 = p.packed ? (uint32_t)p.S : (uint32_t)p.R1, b2 = p.packed ? (uint32_t)p.FR : 1u;
@@ -2672,8 +2868,8 @@ static int build_plan(TcState *st, const float *x, float *y, int B, int T, void 
             const uint32_t b1 = p.packed ? (uint32_t)p.S : (uint32_t)p.R1, b2 = p.packed ? (uint32_t)p.FR : 1u;
             if (make_map(st, &P.tmA, lvl(e), cm * Cs, L, B, (uint64_t)cm * Cs * 2, (uint64_t)L * cm * Cs * 2, 64, b1, b2)) return -1;
             p.prev = lvl(i - 1);
-            p.Lin = L / 2;
-            p.up_scale = (L > 1) ? (float)(p.Lin - 1) / (float)(L - 1) : 0.f;
+            p.Lin = pair ? L : L / 2;                         // row-pair mode: an operand row IS a previous-level row index
+            p.up_scale = pair ? (float)(p.Lin - 1) / (float)(2 * L - 1) : ((L > 1) ? (float)(p.Lin - 1) / (float)(L - 1) : 0.f);
         }
         if (p.out != nullptr && !sp) { if (make_map_out(st, &P.tmO, p.out, (uint64_t)lv.cout, (uint64_t)B * L)) return -1; }
         else P.tmO = P.tmA;
@@ -2742,10 +2938,31 @@ int tc_debug_plan(int n, int ci, const TcBlockSrc *blocks, int nblocks, int B, i
     TcPlanLevel P{};
     const std::string ovr_s = ovr ? ovr : "";
     const char *ge = getenv("WUNET_TC_GEMM");
-    if (!(ge && ge[0] == '0') && parse_override(ovr_s, block).any == false && plan_block_gemm(levels[block], block, n, B, T, num_sms, P)) {
-    } else
-    if (!(parse_override(ovr_s, block).any == false && plan_block_tn(levels[block], block, n, B, T, num_sms, P)))
+    bool planned = false;
     {
+        // row-pair mode (WUNET_TC_PAIR bit 0: block 1, bit 1: last block), planned like build_plan does
+        const char *pe = getenv("WUNET_TC_PAIR"), *hk = getenv("WUNET_TC_HEADK");
+        const int pmask = pe ? atoi(pe) & 3 : 0;
+        const int ps = (n >= 2 && block == 1) ? 0 : ((n >= 2 && block == 2 * n) ? 1 : -1);
+        const int Lreal = (block <= n) ? (T >> block) : (T >> (2 * n - block));
+        if (ps >= 0 && (pmask & (1 << ps)) && Lreal % 2 == 0 && Lreal / 2 >= 128 && !(tne && tne[0] == '1') && !(ps == 1 && hk && hk[0] == '1')) {
+            const TcLevel &rl = levels[block];
+            const bool ok = ps == 0 ? (rl.k == 15 && rl.cin1 == 0 && rl.cin0 % 8 == 0 && 2 * rl.cin0 <= 64 && 2 * rl.cout <= 256)
+                                    : (rl.k == 5 && rl.cin0 % 8 == 0 && rl.cin1 % 8 == 0 && rl.cin0 >= 32 && rl.cout % 8 == 0 && rl.cout <= 32);
+            if (ok) {
+                TcLevel pv = rl;
+                pv.cin0 = 2 * rl.cin0; pv.cin1 = 2 * rl.cin1; pv.cout = 2 * rl.cout; pv.k = pair_taps(rl.k);
+                pv.Npad = round_up(pv.cout, 16);
+                pv.Ktot = round_up(pv.cin0, 64) + (pv.cin1 ? round_up(pv.cin1, 64) : 0);
+                pv.mg_s = pv.mg_u = 0; pv.tn_slots = 0;
+                if (plan_block(pv, block, n, B, T, num_sms, ovr_s, P, false, 0, true)) return -1;
+                planned = true;
+            }
+        }
+    }
+    if (planned) {
+    } else if (!(ge && ge[0] == '0') && parse_override(ovr_s, block).any == false && plan_block_gemm(levels[block], block, n, B, T, num_sms, P)) {
+    } else if (!(parse_override(ovr_s, block).any == false && plan_block_tn(levels[block], block, n, B, T, num_sms, P))) {
         // the last block as the forward plans it by default (head-only instantiation unless WUNET_TC_STORE_LAST=1 / WUNET_TC_HEADK=0)
         const char *sl = getenv("WUNET_TC_STORE_LAST"), *hk = getenv("WUNET_TC_HEADK"), *hm = getenv("WUNET_TC_HEADMT");
         const bool hd_want = block == 2 * n && !(sl && sl[0] == '1') && (hk && hk[0] == '1');
@@ -2776,6 +2993,9 @@ static int tc_prepare(TcState *st, const float *x, float *y, int B, int T, void 
         cudaFuncSetAttribute(conv_tc_kernel<5, true, kEpiWarpsSmall, kProducerWarpsSmall, 0, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         cudaFuncSetAttribute(conv_tc_kernel<5, true, kEpiWarpsLarge, kProducerWarpsLarge, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         cudaFuncSetAttribute(conv_tc_kernel<15, false, kEpiWarpsLarge, 0, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+        cudaFuncSetAttribute(conv_tc_kernel<9, false, kEpiWarpsLarge, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+        cudaFuncSetAttribute(conv_tc_kernel<9, false, kEpiWarpsSmall, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+        cudaFuncSetAttribute(conv_tc_kernel<3, true, kEpiWarpsSmall, kProducerWarpsSmall, 0, 0, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         cudaFuncSetAttribute(conv_tn_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         cudaFuncSetAttribute(conv_tn_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
@@ -2816,7 +3036,10 @@ static int launch_enc0(TcState *st, const float *x, int f0, int nf, int T, void 
     attr[0].val.programmaticStreamSerializationAllowed = st->pdl ? 1 : 0;
     cfg.attrs = attr; cfg.numAttrs = 1;
     __nv_bfloat16 *out0 = reinterpret_cast<__nv_bfloat16 *>(static_cast<char *>(ws) + st->plan.off[0]);
-    cudaLaunchKernelEx(&cfg, enc0_kernel, x + (size_t)f0 * T, lv.w_src, lv.scale, lv.shift, out0 + (size_t)f0 * T * RC, nf, T, C, split);
+    __nv_bfloat16 *even = (st->plan.even_copy && !split)
+                              ? reinterpret_cast<__nv_bfloat16 *>(static_cast<char *>(ws) + st->plan.off[2 * st->n + 1]) + (size_t)f0 * (T / 2) * C
+                              : nullptr;
+    cudaLaunchKernelEx(&cfg, enc0_kernel, x + (size_t)f0 * T, lv.w_src, lv.scale, lv.shift, out0 + (size_t)f0 * T * RC, nf, T, C, split, even);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return tc_fail("enc0 launch failed: %s", cudaGetErrorString(e));
     return 0;
@@ -2877,7 +3100,14 @@ static int launch_block(TcState *st, int i, int t0, int t1, cudaStream_t stream,
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = st->pdl ? 1 : 0;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    if (p.split) {
+    if (P.pair == 1) {
+        // row-pair mode of the first tensor-core encoder block: a 9-tap block over pairs of positions
+        if (!P.small) cudaLaunchKernelEx(&cfg, conv_tc_kernel<9, false, kEpiWarpsLarge, 0, 0>, P.tmA, P.tmW, P.tmO, p);
+        else cudaLaunchKernelEx(&cfg, conv_tc_kernel<9, false, kEpiWarpsSmall, 0, 0>, P.tmA, P.tmW, P.tmO, p);
+    } else if (P.pair == 2) {
+        // row-pair mode of the last decoder block + head: 3 taps over pairs, producers and head in their PR = 1 form
+        cudaLaunchKernelEx(&cfg, conv_tc_kernel<3, true, kEpiWarpsSmall, kProducerWarpsSmall, 0, 0, 0, 1>, P.tmA, P.tmW, P.tmO, p);
+    } else if (p.split) {
         if (P.upcat) cudaLaunchKernelEx(&cfg, conv_tc_kernel<5, true, kEpiWarpsLarge, kProducerWarpsLarge, 0, 1>, P.tmA, P.tmW, P.tmO, p);
         else cudaLaunchKernelEx(&cfg, conv_tc_kernel<15, false, kEpiWarpsLarge, 0, 0, 1>, P.tmA, P.tmW, P.tmO, p);
     } else if (p.hd) {
@@ -2983,6 +3213,17 @@ int tc_read_level(TcState *st, int block, const void *ws, int B, int T, float *o
     return cudaGetLastError() == cudaSuccess ? 0 : tc_fail("read_level launch failed");
 }
 
+// host-only: the row-pair expansion of one block's weights (pair_weight), as expand_pair_weights_kernel writes it
+int tc_debug_pair_weights(const float *w, int Cout, int C0, int C1, int K, int dec, float *out)
+{
+    if (!w || !out || Cout < 1 || C0 < 1 || C1 < 0 || K < 1 || (K & 1) == 0) return tc_fail("bad row-pair weight query");
+    const int Kp = pair_taps(K), Cv = 2 * (C0 + C1);
+    for (int cov = 0; cov < 2 * Cout; ++cov)
+        for (int v = 0; v < Cv; ++v)
+            for (int tv = 0; tv < Kp; ++tv) out[((size_t)cov * Cv + v) * Kp + tv] = pair_weight(w, Cout, C0, C1, K, dec, cov, v, tv);
+    return 0;
+}
+
 void tc_destroy(TcState *st)
 {
     if (!st) return;
@@ -3003,6 +3244,7 @@ void tc_destroy(TcState *st)
         cudaFree(st->trace);
     }
     for (auto &lv : st->levels) { cudaFree(lv.wp); cudaFree(lv.ss); cudaFree(lv.w_own); cudaFree(lv.wp_tn); cudaFree(lv.wp_sp); cudaFree(lv.w_f32); cudaFree(lv.wx); }
+    for (int s = 0; s < 2; ++s) { cudaFree(st->pair_lv[s].wp); cudaFree(st->pair_lv[s].ss); cudaFree(st->pair_w[s]); cudaFree(st->pair_scale[s]); cudaFree(st->pair_shift[s]); }
     delete st;
 }
 

@@ -33,4 +33,7 @@ void tc_destroy(TcState *st);
 int tc_debug_plan(int n_layers, int ci, const TcBlockSrc *blocks, int nblocks, int B, int T, int block, int num_sms, int *fields,
                   int capacity);
 
+// host-only: row-pair expansion of [Cout][C0+C1][K] weights to [2 Cout][2 (C0+C1)][K'] (tests of the WUNET_TC_PAIR packing)
+int tc_debug_pair_weights(const float *w, int Cout, int C0, int C1, int K, int dec, float *out);
+
 }  // namespace wunet
