@@ -127,6 +127,25 @@ int wunet_unframe_clips_f32(const float *frames, float *const *clips_out, const 
                             long long total_frames, int nthreads);
 
 /*
+ * Training-side data path - pure host code, no CUDA call. Replaces, per item of a batch, what
+ * dataset/waveform_dataset.py:56-67 does in a DataLoader worker: librosa.load(path, sr=None) of the mixture and the clean file
+ * (= soundfile's float32 conversion: integer PCM scaled by 2^-(bits-1), channels averaged) and the aligned random crop
+ * util/utils.py:101-113.
+ * wunet_wav_info(): header of a RIFF/WAVE file (PCM 8/16/24/32 bit, IEEE float 32/64 bit; any channel count).
+ * wunet_wav_read_f32(): frames [first_frame, first_frame + nframes) as mono float32 (so a crop can be read without decoding the
+ *   whole file).
+ * wunet_crop_pairs(): for item i copy samples [starts[i], starts[i] + sample_length) of mixture[i] and of clean[i] (both
+ *   lengths[i] samples long, float32 or - is_i16 != 0 - 16-bit PCM converted by / 32768) into rows i of
+ *   mixture_out / clean_out [nitems][sample_length] (the batch tensors [B,1,T]; pinned for the H2D copy), on `nthreads` host
+ *   threads. The random starts stay with the caller (the reference draws them from numpy's global generator,
+ *   util/utils.py:109). Errors like the reference's asserts: short clips, starts outside the clip -> WUNET_EINVAL.
+ */
+int wunet_wav_info(const char *path, int *sample_rate, int *channels, long long *frames, int *bits, int *is_float);
+int wunet_wav_read_f32(const char *path, long long first_frame, long long nframes, float *out);
+int wunet_crop_pairs(const void *const *mixture, const void *const *clean, const long long *lengths, const long long *starts, int nitems,
+                     int sample_length, int is_i16, float *mixture_out, float *clean_out, int nthreads);
+
+/*
  * Test/diagnostic hook: copy the full-resolution output of block `block` from the workspace of the
  * LAST wunet_forward() call (same ctx, same workspace, B, T, precision) to out_dev as fp32
  * [B,Cout,L] (the reference's NCL layout) — what a forward hook on encoder[i] / middle /

@@ -49,6 +49,9 @@ def load() -> ctypes.CDLL:
     lib.wunet_frame_clips_f32.argtypes = [vp, vp, ci, ci, vp, ll, ci]
     lib.wunet_frame_clips_i16.argtypes = [vp, vp, ci, ci, vp, ll, ci]
     lib.wunet_unframe_clips_f32.argtypes = [vp, vp, vp, ci, ci, ll, ci]
+    lib.wunet_wav_info.argtypes = [ctypes.c_char_p, ctypes.POINTER(ci), ctypes.POINTER(ci), ctypes.POINTER(ll), ctypes.POINTER(ci), ctypes.POINTER(ci)]
+    lib.wunet_wav_read_f32.argtypes = [ctypes.c_char_p, ll, ll, vp]
+    lib.wunet_crop_pairs.argtypes = [vp, vp, vp, vp, ci, ci, ci, vp, vp, ci]
     lib.wunet_last_launch_count.argtypes = [vp]
     lib.wunet_profile_enable.argtypes = [vp, ci]
     lib.wunet_profile_read.argtypes = [vp, vp, ci, ctypes.POINTER(ci)]
@@ -74,6 +77,7 @@ EXPORTED_SYMBOLS = [
     "wunet_last_launch_count", "wunet_profile_enable", "wunet_profile_read", "wunet_debug_plan", "wunet_debug_pair_weights",
     "wunet_train_workspace_bytes", "wunet_train_forward", "wunet_train_backward", "wunet_train_backward_part",
     "wunet_frame_clips_f32", "wunet_frame_clips_i16", "wunet_unframe_clips_f32",
+    "wunet_wav_info", "wunet_wav_read_f32", "wunet_crop_pairs",
 ]
 
 PLAN_FIELDS = ["L", "Cin0", "Cin1", "Cout", "Npad", "Nh", "nsplit", "Nstride", "MT", "nacc", "packed", "FR", "S", "m_tiles",

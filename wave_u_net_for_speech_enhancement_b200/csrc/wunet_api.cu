@@ -655,3 +655,148 @@ int wunet_unframe_clips_f32(const float *frames, float *const *clips_out, const 
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// training-side data path: what dataset/waveform_dataset.py:56-67 does per item - decode two wav files
+// (librosa.load(path, sr=None): soundfile's float32 conversion, channels averaged) and cut the same random window out of
+// both (util/utils.py:101-113) - as a wav reader plus a batched, multi-threaded crop straight into the (pinned) batch tensors.
+// ---------------------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct WavInfo { int fmt = 0, channels = 0, rate = 0, bits = 0; long long frames = 0, data_off = 0; };
+
+inline uint32_t rd_u32(const unsigned char *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+inline uint16_t rd_u16(const unsigned char *p) { return (uint16_t)(p[0] | (p[1] << 8)); }
+
+// RIFF/WAVE chunk walk: "fmt " (PCM = 1, IEEE float = 3, WAVE_FORMAT_EXTENSIBLE = 0xFFFE with the sub-format's first two bytes)
+// and "data". Returns 0, or a negative code: -1 cannot open, -2 not a RIFF/WAVE file, -3 unsupported sample format.
+int wav_parse(FILE *f, WavInfo &w)
+{
+    unsigned char h[12];
+    if (fread(h, 1, 12, f) != 12 || memcmp(h, "RIFF", 4) != 0 || memcmp(h + 8, "WAVE", 4) != 0) return -2;
+    bool have_fmt = false;
+    for (;;) {
+        unsigned char ch[8];
+        if (fread(ch, 1, 8, f) != 8) return -2;
+        const uint32_t sz = rd_u32(ch + 4);
+        if (memcmp(ch, "fmt ", 4) == 0) {
+            unsigned char b[40] = {0};
+            const size_t n = sz < 40 ? sz : 40;
+            if (n < 16 || fread(b, 1, n, f) != n) return -2;
+            w.fmt = rd_u16(b); w.channels = rd_u16(b + 2); w.rate = (int)rd_u32(b + 4); w.bits = rd_u16(b + 14);
+            if (w.fmt == 0xFFFE && n >= 26) w.fmt = rd_u16(b + 24);
+            if (sz > n) fseek(f, (long)(sz - n), SEEK_CUR);
+            if (sz & 1) fseek(f, 1, SEEK_CUR);
+            have_fmt = true;
+        } else if (memcmp(ch, "data", 4) == 0) {
+            if (!have_fmt || w.channels < 1) return -2;
+            const bool ok = (w.fmt == 1 && (w.bits == 8 || w.bits == 16 || w.bits == 24 || w.bits == 32)) || (w.fmt == 3 && (w.bits == 32 || w.bits == 64));
+            if (!ok) return -3;
+            w.data_off = ftell(f);
+            long long bytes = sz;
+            fseek(f, 0, SEEK_END);
+            const long long avail = ftell(f) - w.data_off;            // a streamed file may carry a wrong (0 / 0xFFFFFFFF) data size
+            if (bytes > avail || bytes == 0) bytes = avail;
+            w.frames = bytes / ((long long)w.channels * (w.bits / 8));
+            return 0;
+        } else {
+            if (fseek(f, (long)(sz + (sz & 1)), SEEK_CUR) != 0) return -2;
+        }
+    }
+}
+
+// one sample -> float32 the way libsndfile does for sf_read_float (librosa.load -> soundfile.read(dtype=float32)): integer PCM
+// scaled by 2^-(bits-1) (8-bit wav is unsigned), float passed through
+inline float wav_sample(const unsigned char *p, int fmt, int bits)
+{
+    if (fmt == 3) {
+        if (bits == 32) { float v; memcpy(&v, p, 4); return v; }
+        double d; memcpy(&d, p, 8); return (float)d;
+    }
+    switch (bits) {
+    case 8: return (float)((int)p[0] - 128) * (1.f / 128.f);
+    case 16: return (float)(int16_t)rd_u16(p) * (1.f / 32768.f);
+    case 24: { int32_t v = (int32_t)((uint32_t)p[0] << 8 | (uint32_t)p[1] << 16 | (uint32_t)p[2] << 24); return (float)(v >> 8) * (1.f / 8388608.f); }
+    default: return (float)(int32_t)rd_u32(p) * (1.f / 2147483648.f);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int wunet_wav_info(const char *path, int *sample_rate, int *channels, long long *frames, int *bits, int *is_float)
+{
+    if (!path) return fail(WUNET_EINVAL, "wav_info: null path");
+    FILE *f = fopen(path, "rb");
+    if (!f) return fail(WUNET_EINVAL, "wav_info: cannot open %s", path);
+    WavInfo w;
+    const int rc = wav_parse(f, w);
+    fclose(f);
+    if (rc == -3) return fail(WUNET_EINVAL, "wav_info: %s: unsupported sample format (tag %d, %d bits)", path, w.fmt, w.bits);
+    if (rc != 0) return fail(WUNET_EINVAL, "wav_info: %s is not a RIFF/WAVE file", path);
+    if (sample_rate) *sample_rate = w.rate;
+    if (channels) *channels = w.channels;
+    if (frames) *frames = w.frames;
+    if (bits) *bits = w.bits;
+    if (is_float) *is_float = w.fmt == 3;
+    return WUNET_OK;
+}
+
+int wunet_wav_read_f32(const char *path, long long first_frame, long long nframes, float *out)
+{
+    if (!path || !out || first_frame < 0 || nframes < 0) return fail(WUNET_EINVAL, "wav_read: bad argument");
+    FILE *f = fopen(path, "rb");
+    if (!f) return fail(WUNET_EINVAL, "wav_read: cannot open %s", path);
+    WavInfo w;
+    const int rc = wav_parse(f, w);
+    if (rc != 0) { fclose(f); return fail(WUNET_EINVAL, "wav_read: %s: %s", path, rc == -3 ? "unsupported sample format" : "not a RIFF/WAVE file"); }
+    if (first_frame + nframes > w.frames) { fclose(f); return fail(WUNET_EINVAL, "wav_read: %s has %lld frames, [%lld, %lld) wanted", path, w.frames, first_frame, first_frame + nframes); }
+    const int bs = w.bits / 8, fb = bs * w.channels;
+    std::vector<unsigned char> buf((size_t)std::min<long long>(nframes, 1 << 16) * fb);
+    fseek(f, (long)(w.data_off + first_frame * fb), SEEK_SET);
+    const float inv = 1.f / (float)w.channels;
+    for (long long done = 0; done < nframes;) {
+        const long long n = std::min<long long>(nframes - done, 1 << 16);
+        if ((long long)fread(buf.data(), (size_t)fb, (size_t)n, f) != n) { fclose(f); return fail(WUNET_EINVAL, "wav_read: %s is truncated", path); }
+        for (long long i = 0; i < n; ++i) {
+            const unsigned char *p = buf.data() + i * fb;
+            if (w.channels == 1) { out[done + i] = wav_sample(p, w.fmt, w.bits); continue; }
+            float s = 0.f;                                          // librosa.to_mono: np.mean over the channel axis (float32)
+            for (int c = 0; c < w.channels; ++c) s += wav_sample(p + c * bs, w.fmt, w.bits);
+            out[done + i] = s * inv;
+        }
+        done += n;
+    }
+    fclose(f);
+    return WUNET_OK;
+}
+
+int wunet_crop_pairs(const void *const *mixture, const void *const *clean, const long long *lengths, const long long *starts, int nitems,
+                     int sample_length, int is_i16, float *mixture_out, float *clean_out, int nthreads)
+{
+    if (nitems < 0 || sample_length <= 0 || (nitems > 0 && (!mixture || !clean || !lengths || !starts || !mixture_out || !clean_out)))
+        return fail(WUNET_EINVAL, "crop_pairs: bad argument");
+    for (int i = 0; i < nitems; ++i) {
+        // util/utils.py:104-105: both signals have the same length, at least sample_length; start in [0, len - sample_length]
+        if (!mixture[i] || !clean[i]) return fail(WUNET_EINVAL, "crop_pairs: null clip %d", i);
+        if (lengths[i] < sample_length) return fail(WUNET_EINVAL, "crop_pairs: item %d has %lld samples, sample_length is %d", i, lengths[i], sample_length);
+        if (starts[i] < 0 || starts[i] + sample_length > lengths[i]) return fail(WUNET_EINVAL, "crop_pairs: item %d: start %lld outside [0, %lld]", i, starts[i], lengths[i] - sample_length);
+    }
+    const long long SL = sample_length;
+    run_threads(2LL * nitems, nthreads, [=](long long j0, long long j1) {
+        for (long long j = j0; j < j1; ++j) {
+            const int i = (int)(j >> 1);
+            const void *src = (j & 1) ? clean[i] : mixture[i];
+            float *dst = ((j & 1) ? clean_out : mixture_out) + i * SL;
+            if (!is_i16) std::memcpy(dst, static_cast<const float *>(src) + starts[i], sizeof(float) * SL);
+            else {
+                const int16_t *s = static_cast<const int16_t *>(src) + starts[i];
+                for (long long k = 0; k < SL; ++k) dst[k] = (float)s[k] * (1.f / 32768.f);
+            }
+        }
+    });
+    return WUNET_OK;
+}
+
+}  // extern "C"
