@@ -208,7 +208,9 @@ int wunet_debug_plan(int n_layers, int channels_interval, int B, int T, int bloc
  * with `ksize` taps over positions (w = [cout][cin0 + cin1][ksize] fp32, reference layout; model/unet_basic.py:10,23) is the same
  * operator as a block with 2*((ksize-1)/2+1)/2+1 taps over PAIRS of positions: row m = positions 2m and 2m+1, 2*cout output
  * columns, 2*(cin0 + cin1) virtual input channels (decoder != 0: the first segment in the producers' [q0 range | q1 range] order).
- * Writes out[2*cout][2*(cin0+cin1)][taps'] fp32 - what the library packs for the tensor cores. No reference counterpart. */
+ * Writes out[2*cout][2*(cin0+cin1)][taps'] fp32 - what the library packs for the tensor cores. No reference counterpart.
+ * decoder == 2: the group-of-8 form of the first block, Conv1d(1 -> cout, k=15) (WUNET_TC_ENC0): row m = samples 8m .. 8m+7 as 8
+ * virtual input channels, 8*cout output columns, 3 taps; writes out[8*cout][8][3]. */
 int wunet_debug_pair_weights(const float *w, int cout, int cin0, int cin1, int ksize, int decoder, float *out);
 
 #ifdef __cplusplus

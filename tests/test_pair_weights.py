@@ -81,3 +81,17 @@ def test_pair_weights_zero_pattern():
     # each original tap t of (co, c) appears once per output parity r (q = (t - P + r) mod 2 and dm follow): 2 copies in total
     assert np.count_nonzero(wp) == 2 * w.size
     assert sorted(np.unique(wp[wp != 0]).tolist()) == sorted(np.unique(w).tolist())
+
+
+def test_group8_block_equals_conv():
+    """Block 0, Conv1d(1 -> C, k=15), over groups of 8 samples (WUNET_TC_ENC0): 3 taps over rows of 8 samples, 8 C columns."""
+    rng = np.random.default_rng(8)
+    C, K, L = 24, 15, 256
+    w = rng.standard_normal((C, 1, K)).astype(np.float32)
+    x = rng.standard_normal((L, 1)).astype(np.float32)
+    want = conv1d_same(x, w)                                            # [L][C]
+    out = np.zeros((8 * C, 8, 3), dtype=np.float32)
+    _lib.check(_lib.load().wunet_debug_pair_weights(w.ctypes.data_as(ctypes.c_void_p), C, 1, 0, K, 2, out.ctypes.data_as(ctypes.c_void_p)))
+    got = conv1d_same(x.reshape(L // 8, 8), out)                        # [L/8][8 C]: column r*C + co of row m = sample 8m + r
+    assert np.abs(got.reshape(L, C) - want).max() < 1e-9 * np.abs(want).max()
+    assert np.count_nonzero(out) == 8 * w.size                          # every tap once per output phase r

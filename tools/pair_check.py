@@ -27,7 +27,7 @@ from wave_u_net_for_speech_enhancement_b200 import Model  # noqa: E402
 n, ci, T = 12, 24, 16384
 st = wo.make_state(n, ci, seed=0)
 sd = {k: torch.from_numpy(np.asarray(v)) for k, v in st.items()}
-res = {"pair": int(MASK), "ovr": OVR}
+res = {"pair": int(MASK), "ovr": OVR, "enc0_tc": os.environ.get("WUNET_TC_ENC0", "0")}
 
 
 def make():
@@ -66,11 +66,11 @@ for b in (0, 1, 2, 2 * n - 1, 2 * n):
     res[f"blk{b}_rel_vs_oracle"] = float(np.abs(a - olv[b]).max() / np.abs(olv[b]).max())
 # the default path's blocks, for a direct A/B of the blocks themselves (bf16 rounding of the same arithmetic)
 ref_file = os.path.join(ROOT, "gpurun_out", "pair", "blk_ref.npz")
-if MASK == "0" and not OVR:
+if MASK == "0" and not OVR and os.environ.get("WUNET_TC_ENC0", "0") != "1":
     np.savez(ref_file, **{f"b{k}": v for k, v in blk.items()}, y=yh)
 elif os.path.exists(ref_file):
     ref = np.load(ref_file)
-    for b in (1, 2 * n):
+    for b in (0, 1, 2 * n):
         d = np.abs(blk[b] - ref[f"b{b}"])
         scale = float(np.abs(ref[f"b{b}"]).max())
         res[f"blk{b}_vs_default_max"] = float(d.max())

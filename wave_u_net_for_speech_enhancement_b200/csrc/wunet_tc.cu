@@ -1921,6 +1921,42 @@ __global__ void expand_pair_weights_kernel(const float *__restrict__ w, const fl
     if (i < 2 * Cout) { scale_v[i] = scale[i % Cout]; shift_v[i] = shift[i % Cout]; }
 }
 
+// -------------------------------------------------------------------------------------------------
+// block 0 (Conv1d(1 -> C, k = 15)) on the tensor cores: groups of 8 samples
+// -------------------------------------------------------------------------------------------------
+// The raw input [T] IS the matrix [T/8][8]; row m = samples 8m .. 8m+7 (virtual input channels q = 0..7, one K16 step with the
+// upper half zero-filled by TMA), output row m = the 8 x C results of those samples = [T/8][8 C], the same memory as the
+// channels-last [T][C]. The 15 taps become 3 taps over rows (dm = -1, 0, 1):
+//     W'[dm + 1][r C + co][q] = w[co][8 dm + q - r + 7]      (zero where that index is outside 0 .. 14)
+// so the block is 3 MMAs of N = 8 C per 128 rows = 1024 samples, and its cost is its epilogue and its HBM traffic - it runs as a
+// plain 3-tap encoder block of conv_tc_kernel. The input is needed in bf16 for that (x_to_bf16_kernel): the products then carry
+// bf16-rounded samples and weights like those of every other block of this path.
+__host__ __device__ inline float group8_weight(const float *w, int Cout, int K, int cov, int q, int tv)
+{
+    const int r = cov / Cout, co = cov - r * Cout;
+    const int t = 8 * (tv - 1) + q - r + (K - 1) / 2;
+    if (r > 7 || q > 7 || t < 0 || t >= K) return 0.f;
+    return w[(size_t)co * K + t];
+}
+__global__ void expand_group8_weights_kernel(const float *__restrict__ w, const float *__restrict__ scale, const float *__restrict__ shift,
+                                             float *__restrict__ wv, float *__restrict__ scale_v, float *__restrict__ shift_v, int Cout, int K)
+{
+    const int n = 8 * Cout * 8 * 3;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const int tv = i % 3, q = (i / 3) % 8, cov = i / 24;
+        wv[i] = group8_weight(w, Cout, K, cov, q, tv);
+    }
+    if (i < 8 * Cout) { scale_v[i] = scale[i % Cout]; shift_v[i] = shift[i % Cout]; }
+}
+__global__ void x_to_bf16_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ xb, long long n4)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const float4 v = __ldg(reinterpret_cast<const float4 *>(x) + i);
+    reinterpret_cast<uint2 *>(xb)[i] = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+}
+
 // weights [Cout][Cin][K] fp32 -> [K][Npad][Ktot] bf16, K axis = [seg0 padded to 64 | seg1 padded to 64], zero padded
 __global__ void pack_tc_kernel(const float *__restrict__ w, const float *__restrict__ scale, const float *__restrict__ shift,
                                __nv_bfloat16 *__restrict__ wp, float2 *__restrict__ ss, int Cout, int Cin0, int Cin1, int K,
@@ -2054,7 +2090,8 @@ struct TcPlanLevel {
     bool upcat;
     bool small;                        // two-CTAs-per-SM kernel flavour
     int kind = 0;                      // reported by wunet_debug_plan in the 'small' field: 2 = dense GEMM over frames (gemm_tc_kernel)
-    int pair = 0;                      // row-pair mode: 1 = encoder block (conv_tc_kernel<9, false, ...>), 2 = last decoder block (<3, true, ..., PR = 1>)
+    int pair = 0;                      // row-pair mode: 1 = encoder block (conv_tc_kernel<9, false, ...>), 2 = last decoder block (<3, true, ..., PR = 1>);
+                                       // 3 = block 0 over groups of 8 samples (<3, false, ...>)
 };
 
 // Per-block tiling overrides for tuning sweeps: WUNET_TC_OVR="<block>:key=val,key=val;<block>:..." with keys
@@ -2113,6 +2150,7 @@ struct TcPlan {
     std::vector<TcPlanLevel> lv;       // index 1..2n (0 = enc0 handled separately)
     std::vector<size_t> off;           // workspace offsets of the 2n+1 block outputs (+ the even-row copy of block 0)
     bool even_copy = false;            // block 1 runs in row-pair mode: enc0 also writes its even rows densely (off[2n+1])
+    bool enc0_tc = false;              // block 0 runs on the tensor cores (lv[0]; input converted to bf16 at off[2n+2])
 };
 
 struct TcState {
@@ -2135,6 +2173,10 @@ struct TcState {
     // row-pair mode (WUNET_TC_PAIR bit 0: first tensor-core encoder block, bit 1: last decoder block + head): virtual blocks with
     // doubled channel counts and Toeplitz-expanded weights (pair_weight), planned on frames of half the length
     int pair_mask = 0;
+    bool enc0_tc = false;              // WUNET_TC_ENC0=1: block 0 on the tensor cores in its group-of-8 form (group8_weight); bf16 mode only
+    bool enc0_ok = false;
+    TcLevel g8_lv;                     // its virtual block: 8 input channels, 8 C columns, 3 taps
+    float *g8_w = nullptr, *g8_scale = nullptr, *g8_shift = nullptr;
     TcLevel pair_lv[2];                // [0] block 1, [1] block 2n (cin0 / cin1 / cout = virtual counts, k = pair taps)
     float *pair_w[2] = {nullptr, nullptr}, *pair_scale[2] = {nullptr, nullptr}, *pair_shift[2] = {nullptr, nullptr};
     bool pair_ok[2] = {false, false};
@@ -2155,10 +2197,11 @@ struct TcState {
 
 const char *tc_error() { return g_tc_err; }
 
-// off[0 .. 2n] = block outputs; off[2n+1] = dense copy of block 0's even rows [B][T/2][ci] (bf16 mode; row-pair mode of block 1)
+// off[0 .. 2n] = block outputs; off[2n+1] = dense copy of block 0's even rows [B][T/2][ci] (bf16 mode; row-pair mode of block 1);
+// off[2n+2] = the raw input in bf16
 static void tc_layout(int n, int ci, int B, int T, std::vector<size_t> &off, size_t &total, int mode = 0)
 {
-    off.resize(2 * n + 2);
+    off.resize(2 * n + 3);
     size_t cur = 0;
     for (int i = 0; i < 2 * n + 1; ++i) {
         const int L = (i <= n) ? (T >> i) : (T >> (2 * n - i));
@@ -2168,6 +2211,8 @@ static void tc_layout(int n, int ci, int B, int T, std::vector<size_t> &off, siz
     }
     off[2 * n + 1] = cur;
     if (mode == 0) cur += round_up_sz((size_t)B * (T / 2) * ci * sizeof(__nv_bfloat16), 1024);
+    off[2 * n + 2] = cur;                                 // bf16 copy of the raw input [B][T] (block 0 on the tensor cores)
+    if (mode == 0) cur += round_up_sz((size_t)B * T * sizeof(__nv_bfloat16), 1024);
     total = cur + 1024;
 }
 
@@ -2237,6 +2282,7 @@ int tc_set_weights(TcState **pst, int n, int ci, const TcBlockSrc *blocks, int n
         if (const char *xe = getenv("WUNET_TC_HEADMT")) st->head_mt = std::max(1, std::min(4, atoi(xe)));
         if (const char *xe = getenv("WUNET_TC_L2PROMO")) st->enc_l2promo = atoi(xe);
         if (const char *xe = getenv("WUNET_TC_PAIR")) st->pair_mask = atoi(xe) & 3;
+        if (const char *xe = getenv("WUNET_TC_ENC0")) st->enc0_tc = xe[0] == '1';
 #ifdef WUNET_TC_TRACE
         if (const char *tl = getenv("WUNET_TC_TRACE_LEVEL")) {
             st->trace_level = atoi(tl);
@@ -2300,6 +2346,30 @@ int tc_set_weights(TcState **pst, int n, int ci, const TcBlockSrc *blocks, int n
                                                                                     lv.Npad, lv.Ktot, lv.mg_s, lv.mg_u);
             if (cudaGetLastError() != cudaSuccess) return tc_fail("pack_tc_merged_kernel launch failed");
         }
+    }
+    // block 0 on the tensor cores: virtual block of 8 input channels x 8 C columns x 3 taps
+    st->enc0_ok = false;
+    if (st->enc0_tc && st->levels[0].k == 15 && blocks[0].cin == 1 && 8 * st->levels[0].cout <= 256 && st->levels[0].cout % 8 == 0) {
+        const TcLevel &rl = st->levels[0];
+        TcLevel &pv = st->g8_lv;
+        pv.cin0 = 8; pv.cin1 = 0; pv.cout = 8 * rl.cout; pv.k = 3;
+        pv.Npad = round_up(pv.cout, 16); pv.Ktot = 64;
+        pv.mg_s = pv.mg_u = 0;
+        pv.tn_cp = pv.tn_npad = pv.tn_slots = pv.tn_groups = 0;
+        const size_t nv = (size_t)pv.cout * 8 * 3, nel = (size_t)3 * pv.Npad * pv.Ktot;
+        if (!st->g8_w) {
+            if (cudaMalloc(&st->g8_w, nv * sizeof(float)) != cudaSuccess || cudaMalloc(&st->g8_scale, pv.cout * sizeof(float)) != cudaSuccess ||
+                cudaMalloc(&st->g8_shift, pv.cout * sizeof(float)) != cudaSuccess || cudaMalloc(&pv.wp, nel * sizeof(__nv_bfloat16)) != cudaSuccess ||
+                cudaMalloc(&pv.ss, pv.Npad * sizeof(float2)) != cudaSuccess)
+                return tc_fail("cudaMalloc(block 0 tensor-core weights) failed");
+        }
+        expand_group8_weights_kernel<<<(unsigned)((nv + 255) / 256), 256, 0, stream>>>(blocks[0].w, blocks[0].scale, blocks[0].shift, st->g8_w,
+                                                                                       st->g8_scale, st->g8_shift, rl.cout, rl.k);
+        if (cudaGetLastError() != cudaSuccess) return tc_fail("expand_group8_weights_kernel launch failed");
+        pack_tc_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, stream>>>(st->g8_w, st->g8_scale, st->g8_shift, pv.wp, pv.ss, pv.cout, 8, 0, 3,
+                                                                          pv.Npad, pv.Ktot);
+        if (cudaGetLastError() != cudaSuccess) return tc_fail("pack_tc_kernel (block 0) launch failed");
+        st->enc0_ok = true;
     }
     // row-pair mode: virtual blocks (doubled channel counts, pair_taps(k) taps) packed like any other block
     for (int s = 0; s < 2; ++s) {
@@ -2434,14 +2504,14 @@ static int sp_chunk_order(const TcLevel &lv, bool dec, unsigned char *map, Split
 // sub-tiles per CTA for it, so that the ring of previous-level rows fits next to the input ring (small flavour only).
 // pair: row-pair mode - lv is the virtual block (doubled channel counts, pair taps) and the frames are half as long.
 static int plan_block(const TcLevel &lv, int i, int n, int B, int T, int num_sms, const std::string &ovr, TcPlanLevel &P, bool sp = false,
-                      int hd_mt = 0, bool pair = false)
+                      int hd_mt = 0, bool pair = false, bool group8 = false)
 {
     TcParams &p = P.p;
     memset(&p, 0, sizeof(p));
     const bool dec = i > n;
     const int KS = lv.k;
-    const int L = ((i <= n) ? (T >> i) : (T >> (2 * n - i))) >> (pair ? 1 : 0);
-    P.pair = pair ? (dec ? 2 : 1) : 0;
+    const int L = ((i <= n) ? (T >> i) : (T >> (2 * n - i))) >> (pair ? 1 : (group8 ? 3 : 0));   // group8: block 0 over groups of 8 samples
+    P.pair = pair ? (dec ? 2 : 1) : (group8 ? 3 : 0);
     P.upcat = dec;
     p.B = B; p.L = L; p.Cout = lv.cout; p.T = T;
     p.Cin0 = lv.cin0; p.Cin1 = lv.cin1;
@@ -2776,12 +2846,32 @@ static int build_plan(TcState *st, const float *x, float *y, int B, int T, void 
     char *base = static_cast<char *>(ws);
     auto lvl = [&](int i) { return reinterpret_cast<__nv_bfloat16 *>(base + pl.off[i]); };
     pl.even_copy = false;
+    pl.enc0_tc = false;
+    if (!sp && st->enc0_ok && T % 8 == 0 && T / 8 >= 128) {
+        // block 0 on the tensor cores: a 3-tap encoder block over groups of 8 samples, reading the bf16 copy of the input
+        TcPlanLevel &P = pl.lv[0];
+        const TcLevel &lv = st->g8_lv;
+        if (plan_block(lv, 0, n, B, T, st->num_sms, st->plan_ovr, P, false, 0, false, true)) return -1;
+        TcParams &p = P.p;
+        const int L = p.L;
+        p.ss = lv.ss; p.out = lvl(0); p.head = 0;
+        p.x = x; p.y = y; p.head_w = st->out_w; p.head_b = st->out_b; p.trace = nullptr;
+        __nv_bfloat16 *xb = reinterpret_cast<__nv_bfloat16 *>(base + pl.off[2 * n + 2]);
+        if (make_map(st, &P.tmA, xb, 8, L, B, (uint64_t)8 * 2, (uint64_t)L * 8 * 2, 64, (uint32_t)p.R1, 1u)) return -1;
+        if (p.bulk_store) { if (make_map_out(st, &P.tmO, p.out, (uint64_t)lv.cout, (uint64_t)B * L)) return -1; }
+        else P.tmO = P.tmA;
+        p.hd = 0; p.ps_n = 0; p.ps_rows = p.ps_rows2 = 0; p.ps_bytes = 0; p.ps_tx = p.ps_tx2 = 0;
+        if (make_map(st, &P.tmW, lv.wp, (uint64_t)lv.Ktot, lv.Npad, lv.k, (uint64_t)lv.Ktot * 2, (uint64_t)lv.Npad * lv.Ktot * 2, 64, (uint32_t)p.Nh,
+                     (uint32_t)p.tg))
+            return -1;
+        pl.enc0_tc = true;
+    }
     for (int i = 1; i < 2 * n + 1; ++i) {
         // row-pair mode (WUNET_TC_PAIR): block 1 and / or the last block run as virtual blocks over pairs of positions
         const int ps = (n >= 2 && i == 1) ? 0 : ((n >= 2 && i == 2 * n) ? 1 : -1);
         const int Lreal = (i <= n) ? (T >> i) : (T >> (2 * n - i));
         const bool pair = ps >= 0 && !sp && st->pair_ok[ps] && Lreal % 2 == 0 && Lreal / 2 >= 128 && !st->tn &&
-                          !(ps == 1 && st->headk);
+                          !(ps == 1 && st->headk) && !(ps == 0 && pl.enc0_tc);      // the even-row copy comes from the CUDA-core enc0
         const TcLevel &lv = pair ? st->pair_lv[ps] : st->levels[i];
         TcPlanLevel &P = pl.lv[i];
         if (!pair && !sp && st->gemm && parse_override(st->plan_ovr, i).any == false && plan_block_gemm(lv, i, n, B, T, st->num_sms, P)) {
@@ -2902,7 +2992,7 @@ static int build_plan(TcState *st, const float *x, float *y, int B, int T, void 
             return -1;
     }
     if (getenv("WUNET_TC_DEBUG")) {
-        for (int i = 1; i < 2 * n + 1; ++i) {
+        for (int i = pl.enc0_tc ? 0 : 1; i < 2 * n + 1; ++i) {
             const TcParams &p = pl.lv[i].p;
             if (pl.lv[i].is_gemm) {
                 const GemmParams &g = pl.lv[i].gp;
@@ -2927,9 +3017,26 @@ static int build_plan(TcState *st, const float *x, float *y, int B, int T, void 
 
 int tc_debug_plan(int n, int ci, const TcBlockSrc *blocks, int nblocks, int B, int T, int block, int num_sms, int *f, int cap)
 {
-    if (nblocks != 2 * n + 1 || block < 1 || block >= nblocks) return tc_fail("block %d out of range (1..%d)", block, 2 * n);
+    const char *e0 = getenv("WUNET_TC_ENC0");
+    const bool g8 = block == 0 && e0 && e0[0] == '1';        // block 0 has a tensor-core plan only in its group-of-8 form
+    if (nblocks != 2 * n + 1 || (block < 1 && !g8) || block >= nblocks) return tc_fail("block %d out of range (1..%d)", block, 2 * n);
     if (ci % 8 != 0 || ci > 32) return tc_fail("bf16 tcgen05 path needs channels_interval %% 8 == 0 and <= 32 (got %d)", ci);
     if (cap < 32 || !f) return tc_fail("need room for 32 fields");
+    if (g8) {
+        if (blocks[0].k != 15 || blocks[0].cin != 1 || 8 * blocks[0].cout > 256 || T % 8 != 0 || T / 8 < 128) return tc_fail("block 0 has no group-of-8 plan for this shape");
+        TcLevel pv;
+        pv.cin0 = 8; pv.cin1 = 0; pv.cout = 8 * blocks[0].cout; pv.k = 3; pv.Npad = round_up(pv.cout, 16); pv.Ktot = 64;
+        TcPlanLevel P{};
+        const char *ovr = getenv("WUNET_TC_OVR");
+        if (plan_block(pv, 0, n, B, T, num_sms, ovr ? ovr : "", P, false, 0, false, true)) return -1;
+        const TcParams &p = P.p;
+        const int v[32] = {p.L, p.Cin0, p.Cin1, p.Cout, p.Npad, p.Nh, p.nsplit, p.Nstride, p.MT, p.nacc, p.packed, p.FR, p.S, p.m_tiles,
+                           p.nchunks, p.resident, p.bulk_store, p.na, p.nb, p.tg, p.ngroups, (int)p.a_stage_bytes, (int)p.b_stage_bytes,
+                           p.a_tx_bytes, p.rows_used, (int)p.tmem_cols, (int)P.smem, P.threads, P.per_sm, (int)P.grid.x, (int)P.small,
+                           p.tiles_per_frame};
+        for (int k = 0; k < 32; ++k) f[k] = v[k];
+        return 0;
+    }
     std::vector<TcLevel> levels(nblocks);
     const char *mge = getenv("WUNET_TC_MERGE");
     const char *tne = getenv("WUNET_TC_TN");
@@ -2993,6 +3100,8 @@ static int tc_prepare(TcState *st, const float *x, float *y, int B, int T, void 
         cudaFuncSetAttribute(conv_tc_kernel<5, true, kEpiWarpsSmall, kProducerWarpsSmall, 0, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         cudaFuncSetAttribute(conv_tc_kernel<5, true, kEpiWarpsLarge, kProducerWarpsLarge, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         cudaFuncSetAttribute(conv_tc_kernel<15, false, kEpiWarpsLarge, 0, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+        cudaFuncSetAttribute(conv_tc_kernel<3, false, kEpiWarpsLarge, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+        cudaFuncSetAttribute(conv_tc_kernel<3, false, kEpiWarpsSmall, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         cudaFuncSetAttribute(conv_tc_kernel<9, false, kEpiWarpsLarge, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         cudaFuncSetAttribute(conv_tc_kernel<9, false, kEpiWarpsSmall, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         cudaFuncSetAttribute(conv_tc_kernel<3, true, kEpiWarpsSmall, kProducerWarpsSmall, 0, 0, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
@@ -3020,9 +3129,22 @@ static int tc_prepare(TcState *st, const float *x, float *y, int B, int T, void 
     return 0;
 }
 
-// enc0 over frames [f0, f0 + nf)
-static int launch_enc0(TcState *st, const float *x, int f0, int nf, int T, void *ws, cudaStream_t stream)
+static int launch_block(TcState *st, int i, int t0, int t1, cudaStream_t stream, const float *x = nullptr, float *y = nullptr);
+
+// enc0 over frames [f0, f0 + nf); *launches receives the number of kernels enqueued
+static int launch_enc0(TcState *st, const float *x, int f0, int nf, int T, void *ws, cudaStream_t stream, int *launches = nullptr)
 {
+    if (launches) *launches = 1;
+    if (st->plan.enc0_tc) {
+        // tensor-core form: bf16 copy of the frames' samples, then block 0 as a 3-tap block over groups of 8 samples
+        __nv_bfloat16 *xb = reinterpret_cast<__nv_bfloat16 *>(static_cast<char *>(ws) + st->plan.off[2 * st->n + 2]) + (size_t)f0 * T;
+        const long long n4 = (long long)nf * T / 4;
+        x_to_bf16_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(x + (size_t)f0 * T, xb, n4);
+        if (cudaGetLastError() != cudaSuccess) return tc_fail("x_to_bf16_kernel launch failed");
+        const int tpf = st->plan.lv[0].p.tiles_per_frame;
+        if (launches) *launches = 2;
+        return launch_block(st, 0, f0 * tpf, (f0 + nf) * tpf, stream, nullptr, nullptr);
+    }
     const TcLevel &lv = st->levels[0];
     const int C = lv.cout;
     const int split = st->plan_mode != 0 ? 1 : 0;
@@ -3046,7 +3168,7 @@ static int launch_enc0(TcState *st, const float *x, int f0, int nf, int T, void 
 }
 
 // conv block i over the tile range [t0, t1) (t1 < 0: all tiles)
-static int launch_block(TcState *st, int i, int t0, int t1, cudaStream_t stream, const float *x = nullptr, float *y = nullptr)
+static int launch_block(TcState *st, int i, int t0, int t1, cudaStream_t stream, const float *x, float *y)
 {
     TcPlanLevel &P = st->plan.lv[i];
     if (P.is_gemm) {
@@ -3100,7 +3222,11 @@ static int launch_block(TcState *st, int i, int t0, int t1, cudaStream_t stream,
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = st->pdl ? 1 : 0;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    if (P.pair == 1) {
+    if (P.pair == 3) {
+        // block 0 over groups of 8 samples: a 3-tap encoder block
+        if (!P.small) cudaLaunchKernelEx(&cfg, conv_tc_kernel<3, false, kEpiWarpsLarge, 0, 0>, P.tmA, P.tmW, P.tmO, p);
+        else cudaLaunchKernelEx(&cfg, conv_tc_kernel<3, false, kEpiWarpsSmall, 0, 0>, P.tmA, P.tmW, P.tmO, p);
+    } else if (P.pair == 1) {
         // row-pair mode of the first tensor-core encoder block: a 9-tap block over pairs of positions
         if (!P.small) cudaLaunchKernelEx(&cfg, conv_tc_kernel<9, false, kEpiWarpsLarge, 0, 0>, P.tmA, P.tmW, P.tmO, p);
         else cudaLaunchKernelEx(&cfg, conv_tc_kernel<9, false, kEpiWarpsSmall, 0, 0>, P.tmA, P.tmW, P.tmO, p);
@@ -3132,8 +3258,9 @@ int tc_forward(TcState *st, const float *x, float *y, int B, int T, void *ws, cu
     const int n = st->n;
     int nl = 0;
     if (ev) cudaEventRecord(ev[0], stream);
-    if (launch_enc0(st, x, 0, B, T, ws, stream)) return -1;
-    ++nl;
+    int l0n = 1;
+    if (launch_enc0(st, x, 0, B, T, ws, stream, &l0n)) return -1;
+    nl += l0n;
     if (ev) cudaEventRecord(ev[1], stream);
     for (int i = 1; i < 2 * n + 1; ++i) {
         if (launch_block(st, i, 0, -1, stream, x, y)) return -1;
@@ -3174,8 +3301,9 @@ int tc_forward_host(TcState *st, const float *x_host, float *y_host, float *x_de
         cudaMemcpyAsync(x_dev + c * chunk, x_host + c * chunk, chunk * sizeof(float), cudaMemcpyHostToDevice, st->copy_in);
         cudaEventRecord(st->ev_in[c], st->copy_in);
         cudaStreamWaitEvent(stream, st->ev_in[c], 0);
-        if (launch_enc0(st, x_dev, c * bc, bc, T, ws, stream)) return -1;
-        ++nl;
+        int l0n = 1;
+        if (launch_enc0(st, x_dev, c * bc, bc, T, ws, stream, &l0n)) return -1;
+        nl += l0n;
     }
     for (int i = 1; i < 2 * n; ++i) {
         if (launch_block(st, i, 0, -1, stream)) return -1;
@@ -3217,6 +3345,13 @@ int tc_read_level(TcState *st, int block, const void *ws, int B, int T, float *o
 int tc_debug_pair_weights(const float *w, int Cout, int C0, int C1, int K, int dec, float *out)
 {
     if (!w || !out || Cout < 1 || C0 < 1 || C1 < 0 || K < 1 || (K & 1) == 0) return tc_fail("bad row-pair weight query");
+    if (dec == 2) {                                       // block 0 over groups of 8 samples: out[8 Cout][8][3]
+        if (C0 != 1 || C1 != 0 || K > 15) return tc_fail("the group-of-8 form is for Conv1d(1 -> C, k <= 15)");
+        for (int cov = 0; cov < 8 * Cout; ++cov)
+            for (int q = 0; q < 8; ++q)
+                for (int tv = 0; tv < 3; ++tv) out[((size_t)cov * 8 + q) * 3 + tv] = group8_weight(w, Cout, K, cov, q, tv);
+        return 0;
+    }
     const int Kp = pair_taps(K), Cv = 2 * (C0 + C1);
     for (int cov = 0; cov < 2 * Cout; ++cov)
         for (int v = 0; v < Cv; ++v)
@@ -3244,6 +3379,7 @@ void tc_destroy(TcState *st)
         cudaFree(st->trace);
     }
     for (auto &lv : st->levels) { cudaFree(lv.wp); cudaFree(lv.ss); cudaFree(lv.w_own); cudaFree(lv.wp_tn); cudaFree(lv.wp_sp); cudaFree(lv.w_f32); cudaFree(lv.wx); }
+    cudaFree(st->g8_lv.wp); cudaFree(st->g8_lv.ss); cudaFree(st->g8_w); cudaFree(st->g8_scale); cudaFree(st->g8_shift);
     for (int s = 0; s < 2; ++s) { cudaFree(st->pair_lv[s].wp); cudaFree(st->pair_lv[s].ss); cudaFree(st->pair_w[s]); cudaFree(st->pair_scale[s]); cudaFree(st->pair_shift[s]); }
     delete st;
 }
