@@ -3,7 +3,9 @@ oracle/wunet_bf16_model.py — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
 
 The arithmetic of the bf16 tensor-core path (csrc/wunet_tc.cu) restated on the CPU, rounding where the kernels round:
 
-* first encoder block: fp32 operands (CUDA cores), folded BatchNorm scale/shift in fp32, LeakyReLU, bf16 store;
+* first encoder block: fp32 operands (CUDA cores), folded BatchNorm scale/shift in fp32, LeakyReLU, bf16 store; with
+  ``enc0_tc`` (the library's tensor-core form of that block, 3 taps over groups of 8 samples) bf16-rounded samples and weights
+  like every other block;
 * every other block: bf16 activations x bf16 weights (round-to-nearest-even of the fp32 parameters), wide accumulation
   (float64 here; the tensor core accumulates exact products in fp32 — the difference is ~1e-6 relative and only matters
   where it flips a bf16 rounding), fp32 scale/shift + LeakyReLU, bf16 store;
@@ -112,7 +114,7 @@ def _upsample_fp32(prev: torch.Tensor) -> torch.Tensor:
 
 
 def forward_bf16_model(state, x: np.ndarray, n_layers: int = 12, channels_interval: int = 24, return_levels: bool = False,
-                       forced=None, dense_bottom=None):
+                       forced=None, dense_bottom=None, enc0_tc: bool = False):
     """-> y [B,1,T] fp32 (and the bf16-valued outputs of the 2n+1 blocks as fp32 arrays; the last one unrounded).
 
     ``dense_bottom``: whether decoder blocks of at most 16 samples use the folded-interpolation weights of gemm_tc_kernel (the
@@ -132,7 +134,7 @@ def forward_bf16_model(state, x: np.ndarray, n_layers: int = 12, channels_interv
         levels.append(t)
         return torch.from_numpy(np.asarray(forced[i], np.float32)) if (forced is not None and i < 2 * n) else t
 
-    o = keep(0, _bf16(_block(xt, state, plan[0][0], 15, quantise_operands=False)))
+    o = keep(0, _bf16(_block(_bf16(xt) if enc0_tc else xt, state, plan[0][0], 15, quantise_operands=enc0_tc)))
     skips.append(o)
     o = o[:, :, ::2]
     for i in range(1, n):

@@ -20,6 +20,12 @@ pytestmark = [pytest.mark.gpu]
 ABS_FLOOR = 2.0 ** -11       # of the level's max |value|
 
 
+def lib_enc0_tc(ci, T):
+    """Does the library run the first block on the tensor cores (3 taps over groups of 8 samples, bf16 samples and weights) for
+    this shape? Mirrors build_plan: WUNET_TC_ENC0, frames of at least 1024 samples, 8 C <= 256 columns."""
+    return os.environ.get("WUNET_TC_ENC0", "0") == "1" and T % 8 == 0 and T // 8 >= 128 and ci % 8 == 0 and 8 * ci <= 256
+
+
 def ulp_bf16(v):
     """spacing of bf16 numbers at |v| (8 significant bits)"""
     return np.exp2(np.floor(np.log2(np.maximum(np.abs(v), 1e-30))) - 7)
@@ -39,7 +45,8 @@ def test_levels_match_the_arithmetic_model(n, ci, B, T, seed, monkeypatch):
         y = m(torch.from_numpy(x).cuda()).cpu().numpy()
     got_levels = [m.read_level(i, B, T).cpu().numpy() for i in range(2 * n + 1)]
     # every block of the model is evaluated on the GPU's own outputs of the blocks before it: a rounding flip stays local
-    want_y, want = wb.forward_bf16_model(st, x, n, ci, return_levels=True, forced=got_levels[:2 * n])
+    want_y, want = wb.forward_bf16_model(st, x, n, ci, return_levels=True, forced=got_levels[:2 * n],
+                                            enc0_tc=lib_enc0_tc(ci, T))
     report = []
     for i in range(2 * n + 1):
         got = got_levels[i]

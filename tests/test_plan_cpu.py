@@ -41,6 +41,13 @@ def test_plan_invariants(n, ci, B):
         for i in blocks(n):
             d = _lib.debug_plan(n, ci, B, T, i, SMS)
             ks = 15 if i <= n else 5
+            cout_ref = (i + 1) * ci if i < n else (n * ci if i == n else (2 * n - i + 1) * ci)
+            pair = d["Cout"] == 2 * cout_ref            # row-pair mode (block 1 by default): half the rows, twice the columns,
+            if pair:                                    # 9 taps for 15 (3 for 5)
+                assert i in (1, 2 * n) and n >= 2 and d["L"] * 2 == (T >> i if i <= n else T >> (2 * n - i)) and d["L"] >= 128, (n, ci, B, T, i, d)
+                ks = 9 if i <= n else 3
+            else:
+                assert d["Cout"] == cout_ref, (n, ci, B, T, i, d)
             ctx = (n, ci, B, T, i, d)
             if d["small"] == 2:
                 # dense GEMM over frames (blocks of at most 16 samples): 256 frames x Nh columns per CTA, K = 64-channel chunks
@@ -90,7 +97,7 @@ def test_plan_invariants(n, ci, B):
             assert 1 <= d["grid"] <= min(tiles, SMS * d["per_sm"]), ctx
             assert d["threads"] * d["per_sm"] <= 2048 and d["threads"] % 32 == 0, ctx
             if i == 2 * n:                      # fused head: whole channel range of full frames in one CTA
-                assert d["nsplit"] == 1 and not d["packed"] and d["Cout"] <= 32, ctx
+                assert d["nsplit"] == 1 and not d["packed"] and d["Cout"] <= (64 if pair else 32), ctx
 
 
 def test_packed_levels_run_in_one_wave_at_the_benchmark_batch():
@@ -116,8 +123,29 @@ def test_override_string(monkeypatch):
 
 def test_unsupported_queries_fail_loudly():
     with pytest.raises(_lib.WunetError):
-        _lib.debug_plan(12, 24, 256, 16384, 0, SMS)             # block 0 runs on CUDA cores
+        _lib.debug_plan(12, 24, 256, 16384, 0, SMS)             # block 0 runs on CUDA cores (unless WUNET_TC_ENC0=1)
     with pytest.raises(_lib.WunetError):
         _lib.debug_plan(12, 20, 256, 16384, 3, SMS)             # channels_interval must be a multiple of 8
     with pytest.raises(_lib.WunetError):
         _lib.debug_plan(12, 24, 256, 1000, 3, SMS)              # T must be a multiple of 2^n_layers
+
+
+def test_row_pair_and_group_modes(monkeypatch):
+    """Block 1 runs over pairs of positions by default (9 taps, 48 -> 96 channels at half the rows); WUNET_TC_PAIR=0 gives the
+    plain 15-tap block, bit 1 the last block's pair form, WUNET_TC_ENC0=1 a tensor-core plan for block 0 (groups of 8 samples)."""
+    d = _lib.debug_plan(12, 24, 256, 16384, 1, SMS)
+    assert (d["L"], d["Cin0"], d["Cout"], d["nchunks"], d["resident"]) == (4096, 48, 96, 1, 1)
+    monkeypatch.setenv("WUNET_TC_PAIR", "0")
+    d = _lib.debug_plan(12, 24, 256, 16384, 1, SMS)
+    assert (d["L"], d["Cin0"], d["Cout"]) == (8192, 24, 48)
+    assert _lib.debug_plan(12, 24, 256, 16384, 24, SMS)["Cout"] == 24
+    monkeypatch.setenv("WUNET_TC_PAIR", "2")
+    d = _lib.debug_plan(12, 24, 256, 16384, 24, SMS)
+    assert (d["L"], d["Cin0"], d["Cin1"], d["Cout"], d["small"], d["MT"], d["resident"], d["nchunks"]) == (8192, 96, 48, 48, 1, 1, 1, 3)
+    assert _lib.debug_plan(12, 24, 256, 16384, 1, SMS)["Cout"] == 48
+    # frames too short for the pair form (fewer than 128 row pairs) keep the plain block
+    monkeypatch.setenv("WUNET_TC_PAIR", "3")
+    assert _lib.debug_plan(4, 8, 4, 256, 1, SMS)["Cout"] == 16
+    monkeypatch.setenv("WUNET_TC_ENC0", "1")
+    d = _lib.debug_plan(12, 24, 256, 16384, 0, SMS)
+    assert (d["L"], d["Cin0"], d["Cout"], d["nchunks"], d["tg"]) == (2048, 8, 192, 1, 3)

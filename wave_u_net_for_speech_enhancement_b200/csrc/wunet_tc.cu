@@ -2172,7 +2172,8 @@ struct TcState {
                                        // (profiles/r02_tn_*.txt), so opt-in: WUNET_TC_TN=1
     // row-pair mode (WUNET_TC_PAIR bit 0: first tensor-core encoder block, bit 1: last decoder block + head): virtual blocks with
     // doubled channel counts and Toeplitz-expanded weights (pair_weight), planned on frames of half the length
-    int pair_mask = 0;
+    int pair_mask = 1;                 // default: block 1 in row-pair mode (127 -> 97 us at batch 256; +8 us in enc0 for the even-row copy),
+                                       // the last block not (its pair form is slower: 241 -> 300 us, profiles/r02_row_pair_ab.txt)
     bool enc0_tc = false;              // WUNET_TC_ENC0=1: block 0 on the tensor cores in its group-of-8 form (group8_weight); bf16 mode only
     bool enc0_ok = false;
     TcLevel g8_lv;                     // its virtual block: 8 input channels, 8 C columns, 3 taps
@@ -2556,6 +2557,7 @@ static int plan_block(const TcLevel &lv, int i, int n, int B, int T, int num_sms
     // ---- tiling ---------------------------------------------------------------------------------
     TcOverride ov = parse_override(ovr, i);
     if (pair && dec && !ov.any) parse_kv("mt=1,small=1", ov);      // fused head over row pairs: one epilogue warp per quadrant, resident weights
+    if (pair && !dec && !ov.any && B >= 128) parse_kv("mt=2,na=3", ov);   // block 1 over pairs, swept on a B200 at batch 256: 97 us (rules: 100)
     if (!ov.any && B >= 128 && !sp)
         for (const TunedTiling &t : kTuned)
             if (t.L == L && t.cin0 == lv.cin0 && t.cin1 == lv.cin1 && t.cout == lv.cout && t.k == KS) parse_kv(t.kv, ov);
@@ -3049,7 +3051,7 @@ int tc_debug_plan(int n, int ci, const TcBlockSrc *blocks, int nblocks, int B, i
     {
         // row-pair mode (WUNET_TC_PAIR bit 0: block 1, bit 1: last block), planned like build_plan does
         const char *pe = getenv("WUNET_TC_PAIR"), *hk = getenv("WUNET_TC_HEADK");
-        const int pmask = pe ? atoi(pe) & 3 : 0;
+        const int pmask = pe ? atoi(pe) & 3 : 1;
         const int ps = (n >= 2 && block == 1) ? 0 : ((n >= 2 && block == 2 * n) ? 1 : -1);
         const int Lreal = (block <= n) ? (T >> block) : (T >> (2 * n - block));
         if (ps >= 0 && (pmask & (1 << ps)) && Lreal % 2 == 0 && Lreal / 2 >= 128 && !(tne && tne[0] == '1') && !(ps == 1 && hk && hk[0] == '1')) {
