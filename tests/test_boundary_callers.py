@@ -202,3 +202,39 @@ def test_unchanged_enhancement_script_runs_the_dropin(reference_env, tmp_path, m
     assert results["ref"]["a.wav"].shape == (16384 + 4000,) and results["ref"]["b.wav"].shape == (16384,)
     for k in results["ref"]:
         assert np.abs(results["ref"][k] - results["dropin"][k]).max() <= 1e-6, k
+
+
+def test_dataset_plugin_is_selected_by_the_config_stanza_and_feeds_the_unchanged_trainer(reference_env, tmp_path):
+    """config/train/train.json:37-47 with only the "module" string changed: the reference's own initialize_config builds the
+    drop-in Dataset, a stock DataLoader batches it (train.py:15-27), and the unchanged Trainer trains on those batches."""
+    import scipy.io.wavfile as wavfile
+    from torch.utils.data import DataLoader
+    rng = np.random.default_rng(2)
+    lines = []
+    for i in range(6):
+        n = 400 + 13 * i
+        clean = rng.integers(-8000, 8000, n, dtype=np.int16)
+        noisy = (clean + rng.integers(-900, 900, n)).astype(np.int16)
+        wavfile.write(str(tmp_path / f"c{i}.wav"), 16000, clean)
+        wavfile.write(str(tmp_path / f"n{i}.wav"), 16000, noisy)
+        lines.append(f"{tmp_path / f'n{i}.wav'} {tmp_path / f'c{i}.wav'}")
+    (tmp_path / "train.txt").write_text("\n".join(lines) + "\n")
+    utils = importlib.import_module("util.utils")
+    stanza = {"module": "wave_u_net_for_speech_enhancement_b200.dataset", "main": "Dataset",
+              "args": {"dataset": str(tmp_path / "train.txt"), "limit": None, "offset": 0, "sample_length": 64, "mode": "train"}}
+    dataset = utils.initialize_config(stanza)                                        # train.py:15
+    assert type(dataset).__module__ == "wave_u_net_for_speech_enhancement_b200.dataset" and len(dataset) == 6
+    np.random.seed(0)
+    loader = DataLoader(dataset=dataset, batch_size=3, num_workers=0, shuffle=False)
+    batches = list(loader)
+    assert len(batches) == 2 and batches[0][0].shape == (3, 1, 64) and batches[0][0].dtype == torch.float32
+    assert list(batches[1][2]) == ["n3", "n4", "n5"]
+    cfg = train_config(tmp_path, 1)
+    model = utils.initialize_config(cfg["model"])
+    optimizer = torch.optim.Adam(params=model.parameters(), lr=1e-3, betas=(0.9, 0.999))
+    trainer_class = utils.initialize_config(cfg["trainer"], pass_args=False)
+    t = trainer_class(config=cfg, resume=False, model=model, loss_function=utils.initialize_config(cfg["loss_function"]),
+                      optimizer=optimizer, train_dataloader=loader, validation_dataloader=[])
+    before = [p.detach().clone() for p in t.model.parameters()]
+    t.train()
+    assert any(not torch.equal(a, b) for a, b in zip(before, t.model.parameters()))
