@@ -1872,6 +1872,106 @@ __global__ void __launch_bounds__(256, 4) enc0_kernel(const float *__restrict__ 
     }
 }
 
+// enc0, persistent form (round 2, last session): the same arithmetic in the same order (bit-identical output), but a block loops over
+// tiles: the weights are loaded once, the samples of the NEXT tile stream into shared memory by cp.async while this tile is
+// computed, and the bulk store of a tile's rows drains while the next tile's first channel pass is computed (the one-shot
+// kernel above spends ~35 % of its time in the un-overlapped load -> compute -> store -> drain phases of its 4 resident blocks).
+__global__ void __launch_bounds__(256, 4) enc0_kernel_v2(const float *__restrict__ x, const float *__restrict__ w /*[C][1][15]*/,
+                                                         const float *__restrict__ scale, const float *__restrict__ shift,
+                                                         __nv_bfloat16 *__restrict__ out, int B, int T, int C, int split,
+                                                         __nv_bfloat16 *__restrict__ even_out)
+{
+    constexpr int KS = 15, PAD = 7, TILE = 1024;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    extern __shared__ uint8_t smem_raw[];
+    float *ws = reinterpret_cast<float *>(smem_raw);          // [15][C]
+    float *sc = ws + KS * C, *sh = sc + C;
+    float *xs = sh + C + ((4 - ((KS * C + 2 * C) & 3)) & 3);  // 16-byte aligned: xs[i] = x[l0 - 8 + i], i < TILE + 16
+    uint8_t *stage = reinterpret_cast<uint8_t *>(xs + TILE + 16);
+    const int RC = split ? 2 * C : C;
+    const int tpf = (T + TILE - 1) / TILE;                    // tiles per frame
+    const int total = B * tpf;
+    for (int i = threadIdx.x; i < KS * C; i += 256) { const int k = i / C, c = i - k * C; ws[i] = w[c * KS + k]; }
+    for (int i = threadIdx.x; i < C; i += 256) { sc[i] = scale[i]; sh[i] = shift[i]; }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // samples of a tile -> xs by 4-byte cp.async (zero fill outside the frame = Conv1d padding)
+    auto prefetch = [&](int tile) {
+        const int b = tile / tpf, l0 = (tile - b * tpf) * TILE;
+        for (int i = threadIdx.x; i < TILE + 16; i += 256) {
+            const int l = l0 - PAD + i - 1;
+            const bool ok = l >= 0 && l < T;
+            const float *src = x + (size_t)b * T + (ok ? l : 0);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(xs + i)), "l"(src), "r"(ok ? 4 : 0) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    int tile = blockIdx.x;
+    if (tile < total) prefetch(tile);
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+    for (; tile < total; tile += gridDim.x) {
+        const int b = tile / tpf, l0 = (tile - b * tpf) * TILE;
+        float xw[20];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+            const float4 v = *reinterpret_cast<const float4 *>(&xs[4 * threadIdx.x + 4 * q]);
+            xw[4 * q] = v.x; xw[4 * q + 1] = v.y; xw[4 * q + 2] = v.z; xw[4 * q + 3] = v.w;
+        }
+        __syncthreads();                                      // every thread has its window: xs may be overwritten
+        if (tile + (int)gridDim.x < total) prefetch(tile + gridDim.x);
+        for (int c0 = 0; c0 < C; c0 += 8) {
+            float acc[4][8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int m = 0; m < 8; ++m) acc[j][m] = 0.f;
+#pragma unroll
+            for (int k = 0; k < KS; ++k) {
+                const float4 w0 = *reinterpret_cast<const float4 *>(&ws[k * C + c0]);
+                const float4 w1 = *reinterpret_cast<const float4 *>(&ws[k * C + c0 + 4]);
+                const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int m = 0; m < 8; ++m) acc[j][m] = fmaf(wv[m], xw[j + k + 1], acc[j][m]);
+            }
+            if (c0 == 0) {
+                // the previous tile's bulk store must have read the staging rows before they are overwritten
+                if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncthreads();
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float f[8];
+#pragma unroll
+                for (int m = 0; m < 8; ++m) f[m] = lrelu(fmaf(acc[j][m], sc[c0 + m], sh[c0 + m]));
+                uint8_t *srow = stage + (size_t)(4 * threadIdx.x + j) * (RC * 2) + c0 * 2;
+                const uint4 o = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+                *reinterpret_cast<uint4 *>(srow) = o;
+                if (even_out != nullptr && (j & 1) == 0 && l0 + 4 * (int)threadIdx.x + j < T)
+                    *reinterpret_cast<uint4 *>(even_out + ((size_t)b * (T >> 1) + ((l0 + 4 * threadIdx.x + j) >> 1)) * C + c0) = o;
+                if (split) {
+                    float g[8];
+#pragma unroll
+                    for (int m = 0; m < 8; ++m) g[m] = f[m] - __bfloat162float(__float2bfloat16_rn(f[m]));
+                    *reinterpret_cast<uint4 *>(srow + C * 2) =
+                        make_uint4(pack_bf16(g[0], g[1]), pack_bf16(g[2], g[3]), pack_bf16(g[4], g[5]), pack_bf16(g[6], g[7]));
+                }
+            }
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");           // the next tile's samples have landed (this thread's copies)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();                                          // staging rows complete, xs of the next tile visible to all
+        if (threadIdx.x == 0) {
+            const int rows = min(TILE, T - l0);
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                         ::"l"(out + ((size_t)b * T + l0) * RC), "r"(smem_u32(stage)), "r"((uint32_t)(rows * RC * 2)) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 // -------------------------------------------------------------------------------------------------
 // row-pair mode: a K-tap conv block over positions as a K'-tap block over PAIRS of positions
 // -------------------------------------------------------------------------------------------------
@@ -2174,6 +2274,9 @@ struct TcState {
     // doubled channel counts and Toeplitz-expanded weights (pair_weight), planned on frames of half the length
     int pair_mask = 1;                 // default: block 1 in row-pair mode (127 -> 97 us at batch 256; +8 us in enc0 for the even-row copy),
                                        // the last block not (its pair form is slower: 241 -> 300 us, profiles/r02_row_pair_ab.txt)
+    int enc0_v = 0;                    // WUNET_TC_ENC0V: 2 = persistent form of the CUDA-core enc0 kernel (bit-identical), 1 = one tile per block,
+                                       // 0 (default) = persistent for the split-precision path (two blocks per SM there: 64 -> 53 us at batch 64), one
+                                       // tile per block for bf16 (four blocks per SM overlap their phases already: 115 vs 117 us, tools/enc0v_check.py)
     bool enc0_tc = false;              // WUNET_TC_ENC0=1: block 0 on the tensor cores in its group-of-8 form (group8_weight); bf16 mode only
     bool enc0_ok = false;
     TcLevel g8_lv;                     // its virtual block: 8 input channels, 8 C columns, 3 taps
@@ -2284,6 +2387,7 @@ int tc_set_weights(TcState **pst, int n, int ci, const TcBlockSrc *blocks, int n
         if (const char *xe = getenv("WUNET_TC_L2PROMO")) st->enc_l2promo = atoi(xe);
         if (const char *xe = getenv("WUNET_TC_PAIR")) st->pair_mask = atoi(xe) & 3;
         if (const char *xe = getenv("WUNET_TC_ENC0")) st->enc0_tc = xe[0] == '1';
+        if (const char *xe = getenv("WUNET_TC_ENC0V")) st->enc0_v = atoi(xe) == 2 ? 2 : (atoi(xe) == 1 ? 1 : 0);
 #ifdef WUNET_TC_TRACE
         if (const char *tl = getenv("WUNET_TC_TRACE_LEVEL")) {
             st->trace_level = atoi(tl);
@@ -3115,6 +3219,7 @@ static int tc_prepare(TcState *st, const float *x, float *y, int B, int T, void 
         TN_ATTR(1) TN_ATTR(2) TN_ATTR(4) TN_ATTR(8) TN_ATTR(16) TN_ATTR(32) TN_ATTR(3) TN_ATTR(7) TN_ATTR(24) TN_ATTR(56) TN_ATTR(63)
 #endif
         cudaFuncSetAttribute(enc0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(enc0_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         int dev = 0, sms = 0;
         if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
             st->num_sms = sms;
@@ -3163,6 +3268,11 @@ static int launch_enc0(TcState *st, const float *x, int f0, int nf, int T, void 
     __nv_bfloat16 *even = (st->plan.even_copy && !split)
                               ? reinterpret_cast<__nv_bfloat16 *>(static_cast<char *>(ws) + st->plan.off[2 * st->n + 1]) + (size_t)f0 * (T / 2) * C
                               : nullptr;
+    if (st->enc0_v == 2 || (st->enc0_v == 0 && split)) {
+        const int total = nf * ((T + 1023) / 1024);
+        cfg.gridDim = dim3((unsigned)std::min(total, st->num_sms * 4), 1, 1);
+        cudaLaunchKernelEx(&cfg, enc0_kernel_v2, x + (size_t)f0 * T, lv.w_src, lv.scale, lv.shift, out0 + (size_t)f0 * T * RC, nf, T, C, split, even);
+    } else
     cudaLaunchKernelEx(&cfg, enc0_kernel, x + (size_t)f0 * T, lv.w_src, lv.scale, lv.shift, out0 + (size_t)f0 * T * RC, nf, T, C, split, even);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return tc_fail("enc0 launch failed: %s", cudaGetErrorString(e));
