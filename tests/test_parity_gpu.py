@@ -334,3 +334,55 @@ def test_fp32_tc_config2_batch64_edges_and_odd_lengths(golden_dir, state_full):
         assert np.abs(run(m, wo.make_input(1, Tx, seed=77 + Tx)) - g[f"T{Tx}"]).max() <= FP32_TOL, Tx
     yh = m.forward_host(torch.from_numpy(x[:8]).pin_memory())
     assert np.array_equal(yh.numpy(), run(m, x[:8]))
+
+
+# ---- row-pair / row-group forms of the narrow blocks: every switch position against the oracle ------------
+@pytest.mark.parametrize("pair,enc0_tc", [("0", "0"), ("1", "0"), ("2", "0"), ("3", "0"), ("0", "1")])
+def test_bf16_row_pair_and_group_forms_vs_oracle(state_full, pair, enc0_tc, monkeypatch):
+    """WUNET_TC_PAIR bit 0 (block 1 over pairs of positions: the default), bit 1 (last block + head over pairs), WUNET_TC_ENC0=1
+    (block 0 on the tensor cores over groups of 8 samples): the same operator, so the same bounds as the plain blocks hold - per
+    block against the oracle's activations, on the output, with impulses at both frame edges (zero padding of the row-pair rows,
+    end points of the upsampling) - and the benchmarked variant (last block not stored) gives the same output."""
+    monkeypatch.setenv("WUNET_TC_PAIR", pair)
+    monkeypatch.setenv("WUNET_TC_ENC0", enc0_tc)
+    B, T = 2, 16384
+    x = wo.make_input(B, T, seed=4321)
+    x[1, 0, 0] += 0.9
+    x[1, 0, T - 1] -= 0.9
+    want, levels = wo.COracle(12, 24).forward(state_full, x, return_levels=True)
+    m = bf16_model(12, 24, state_full, store_last=True)
+    y = run(m, x)
+    assert m.last_launch_count() == (26 if enc0_tc == "1" else 25)
+    for i in (0, 1, 2, 23, 24):
+        lv = m.read_level(i, B, T).cpu().numpy()
+        err = np.abs(lv - levels[i]).max()
+        assert err <= BF16_LEVEL_REL * np.abs(levels[i]).max(), f"block {i}: {err}"
+    assert np.abs(y - want).max() <= BF16_OUT_TOL
+    m._release()
+    y2 = run(bf16_model(12, 24, state_full), x)
+    assert np.array_equal(y2, y)
+    # a short-frame network where the forms do not apply (fewer than 128 row pairs / 1024 samples): plain blocks, still correct
+    st = wo.make_state(4, 8, seed=3)
+    xs = wo.make_input(3, 256, seed=9)
+    ms = bf16_model(4, 8, st)
+    assert np.abs(run(ms, xs) - wo.COracle(4, 8).forward(st, xs)).max() <= BF16_OUT_TOL
+
+
+def test_enc0_persistent_form_is_bit_identical(state_full, monkeypatch):
+    """The two CUDA-core forms of block 0 (WUNET_TC_ENC0V=1: one tile per block, 2: persistent blocks with cp.async prefetch) run
+    the same arithmetic in the same order, also for frames that are not a multiple of the 1024-sample tile."""
+    outs = {}
+    for v in ("1", "2"):
+        monkeypatch.setenv("WUNET_TC_ENC0V", v)
+        m = bf16_model(12, 24, state_full, store_last=True)
+        x = wo.make_input(3, 16384, seed=77)
+        y = run(m, x)
+        b0 = m.read_level(0, 3, 16384).cpu().numpy()
+        m._release()
+        st = wo.make_state(4, 8, seed=2)
+        ms = make_model(4, 8, st, "fp32_tc")
+        ys = run(ms, wo.make_input(5, 2064, seed=6))
+        ms._release()
+        outs[v] = (y, b0, ys)
+    for a, b in zip(outs["1"], outs["2"]):
+        assert np.array_equal(a, b)
