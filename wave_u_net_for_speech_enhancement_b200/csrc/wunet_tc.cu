@@ -837,10 +837,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         auto fetch = [&](int ub0, int ul0, int c, int item) {
             const ChunkInfo u = chunk_info<UPCAT, MG, SP>(p, c);
             if (PR != 0) {
-                const int nvr = u.nvec >> 1, creal = p.Cin0 >> 1;              // vectors of real channels in this chunk
-                if (item >= nruns * nvr) return;
-                const int run = item / nvr, vec = item - run * nvr;
-                const int ch = u.idx * 32 + vec * 8;
+                // `item` counts through ALL upsampled chunks of the tile (K-loop positions 0 .. nchunks0 - 1, produced in one phase)
+                int cc = 0, it = item;
+                for (; cc < p.nchunks0; ++cc) {
+                    const int nci = nruns * (chunk_info<UPCAT, MG, SP>(p, cc).nvec >> 1);
+                    if (it < nci) break;
+                    it -= nci;
+                }
+                if (cc >= p.nchunks0) return;
+                const ChunkInfo uu = chunk_info<UPCAT, MG, SP>(p, cc);
+                const int nvr = uu.nvec >> 1, creal = p.Cin0 >> 1;             // vectors of real channels in this chunk
+                const int run = it / nvr, vec = it - run * nvr;
+                const int ch = uu.idx * 32 + vec * 8;
                 const int ms = ul0 - PAD + RPI * run;                          // operand row = previous-level row
                 const bool chok = ch < creal && ub0 < p.B;
                 const __nv_bfloat16 *pb = p.prev + (size_t)ub0 * p.Lin * creal + ch;
@@ -872,11 +880,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         auto emit = [&](uint8_t *dst, int l0, int c, int item, const uint4 (&w)[WR]) {
             const ChunkInfo u = chunk_info<UPCAT, MG, SP>(p, c);
             if (PR != 0) {
-                const int nvr = u.nvec >> 1;
-                const int run = item / nvr, vec = item - run * nvr;
-                const bool chok = u.idx * 32 + vec * 8 < (p.Cin0 >> 1);
+                // dst = base of the operand ring, c = ring stage of the tile's first upsampled chunk; `item` as in fetch
+                int cc = 0, it = item;
+                for (; cc < p.nchunks0; ++cc) {
+                    const int nci = nruns * (chunk_info<UPCAT, MG, SP>(p, cc).nvec >> 1);
+                    if (it < nci) break;
+                    it -= nci;
+                }
+                if (cc >= p.nchunks0) return;
+                const ChunkInfo uu = chunk_info<UPCAT, MG, SP>(p, cc);
+                int stg = c + cc;
+                if (stg >= p.na) stg -= p.na;
+                const int nvr = uu.nvec >> 1;
+                const int run = it / nvr, vec = it - run * nvr;
+                const bool chok = uu.idx * 32 + vec * 8 < (p.Cin0 >> 1);
                 const int mstart = l0 - PAD + RPI * run;
-                const uint32_t drow = smem_u32(dst) + (uint32_t)(RPI * run) * 128u;
+                const uint32_t drow = smem_u32(dst) + (uint32_t)stg * p.a_stage_bytes + (uint32_t)(RPI * run) * 128u;
 #pragma unroll
                 for (int j = 0; j < RPI; ++j) {
                     const int m = mstart + j;
@@ -894,7 +913,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         for (int q4 = 0; q4 < 4; ++q4) r2[q4] = __hfma2(lam, __hsub2(b2[q4], a2[q4]), a2[q4]);
                         uint4 o = *reinterpret_cast<const uint4 *>(r2);
                         o.x &= keep; o.y &= keep; o.z &= keep; o.w &= keep;
-                        const int dvec = u.vo + qh * nvr + vec;                     // q1 half follows the q0 half of the chunk
+                        const int dvec = uu.vo + qh * nvr + vec;                    // q1 half follows the q0 half of the chunk
                         st_shared_v4_if(drow + (uint32_t)(j * 128 + ((dvec ^ (j & 7)) << 4)), o, RPI * run + j < p.rows_used);
                     }
                 }
@@ -997,6 +1016,44 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (SP != 0 && lo_done) {                                            // (already arrived on its barrier)
                     lo_done = false;
                     if (++sa == p.na) { sa = 0; pa ^= 1; }
+                    continue;
+                }
+                if (PR != 0 && c < p.nchunks0) {
+                    // Row-pair instantiation: ALL upsampled chunks of the tile (K-loop positions 0 .. nchunks0 - 1, consecutive ring
+                    // stages) are produced in ONE phase - one round of items over the producer threads, one fence, one hand-off. (Its
+                    // first version produced them chunk by chunk: two phases per tile made the block 25 % slower than the plain form
+                    // although it issues half the MMAs, profiles/r02_row_pair_ab.txt.)
+                    if (c > 0) continue;
+                    const int nup = p.nchunks0;
+                    if (!pref) fetch(b0, l0, 0, pt);
+                    {
+                        int s2 = sa, par = pa;
+                        for (int u2 = 0; u2 < nup; ++u2) {
+                            mbar_wait(a_empty + 8 * s2, par ^ 1);
+                            if (++s2 == p.na) { s2 = 0; par ^= 1; }
+                        }
+                    }
+                    int nitems = 0;
+                    for (int u2 = 0; u2 < nup; ++u2) nitems += nruns * (chunk_info<UPCAT, MG, SP>(p, u2).nvec >> 1);
+#pragma unroll 1
+                    for (int itx = pt; itx < nitems; itx += NPROD) {
+                        if (itx != pt) fetch(b0, l0, 0, itx);
+                        emit(base_ptr + sm.a, l0, sa, itx, xr);
+                    }
+                    pref = false;
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    for (int u2 = 0; u2 < nup; ++u2) {
+                        if (lane == 0) mbar_arrive(a_full + 8 * sa);
+                        if (++sa == p.na) { sa = 0; pa ^= 1; }
+                    }
+                    const int nt = tile + (int)gridDim.x;
+                    if (nt < total_tiles) {
+                        int nb0, nl0, nn0;
+                        tile_coords(nt, nb0, nl0, nn0);
+                        fetch(nb0, nl0, 0, pt);
+                        pref = true;
+                    }
                     continue;
                 }
                 const bool fast = unit_fast(c);
@@ -2631,7 +2688,12 @@ static int plan_block(const TcLevel &lv, int i, int n, int B, int T, int num_sms
             p.split = 1;
             p.nchunks = sp_chunk_order(lv, dec, p.chunk_map, nullptr);
         } else if (!dec) { for (int c = 0; c < p.nchunks; ++c) p.chunk_map[k++] = (unsigned char)c; }
-        else if (lv.mg_s && L >= 128) {
+        else if (pair) {
+            // row-pair decoder: all upsampled chunks first (they are produced in one phase into consecutive ring stages), then the skip chunks
+            const int n1 = p.nchunks - p.nchunks0;
+            for (int c = 0; c < p.nchunks0; ++c) p.chunk_map[k++] = (unsigned char)(0x80 | c);
+            for (int c = 0; c < n1; ++c) p.chunk_map[k++] = (unsigned char)c;
+        } else if (lv.mg_s && L >= 128) {
             // experimental: [full upsampled chunks][full skip chunks][skip tail | upsampled tail] - one chunk fewer
             const int nfull0 = lv.cin0 / 64, nfull1 = lv.cin1 / 64;
             for (int c = 0; c < nfull0; ++c) p.chunk_map[k++] = (unsigned char)(0x80 | c);
@@ -2813,6 +2875,7 @@ static int plan_block(const TcLevel &lv, int i, int n, int B, int T, int num_sms
     const bool last_block = (i == 2 * n);
     if (last_block && lv.cout > (pair ? 64 : 32)) return tc_fail("fused head needs channels_interval <= 32");
     if (last_block && pair && (!small || p.MT > 2)) return tc_fail("row-pair head needs the small flavour and MT <= 2");
+    if (dec && pair && p.na < p.nchunks0) return tc_fail("level %d: the row-pair producers fill %d ring stages at once, the ring has %d", i, p.nchunks0, p.na);
     if (last_block && p.packed) return tc_fail("bf16 path needs frames of at least 128 samples (T=%d): the fused head works on full frames", T);
     if (last_block && p.nsplit != 1) return tc_fail("fused head needs the whole channel range in one CTA");
     return 0;
