@@ -66,7 +66,7 @@ for b in (0, 1, 2, 2 * n - 1, 2 * n):
     res[f"blk{b}_rel_vs_oracle"] = float(np.abs(a - olv[b]).max() / np.abs(olv[b]).max())
 # the default path's blocks, for a direct A/B of the blocks themselves (bf16 rounding of the same arithmetic)
 ref_file = os.path.join(ROOT, "gpurun_out", "pair", "blk_ref.npz")
-if MASK == "0" and not OVR and os.environ.get("WUNET_TC_ENC0", "0") != "1":
+if MASK in ("0", "1") and not OVR and os.environ.get("WUNET_TC_ENC0", "0") != "1" and not os.path.exists(ref_file):
     np.savez(ref_file, **{f"b{k}": v for k, v in blk.items()}, y=yh)
 elif os.path.exists(ref_file):
     ref = np.load(ref_file)
