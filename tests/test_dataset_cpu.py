@@ -7,6 +7,8 @@ import sys
 import types
 import wave
 
+import torch
+
 import numpy as np
 import pytest
 import scipy.io.wavfile as wavfile
@@ -195,3 +197,29 @@ def test_cached_pairs_from_files(tmp_path):
     mix, clean = cp.batch([2, 1], starts=[5, 0])
     assert np.array_equal(mix[0, 0].numpy(), soundfile_like(lines[2].split(" ")[0])[0][5:5 + 16384])
     assert np.array_equal(clean[1, 0].numpy(), soundfile_like(lines[1].split(" ")[1])[0][:16384])
+
+
+def test_batch_stream_prefetches_in_order_and_keeps_buffers_valid():
+    rng = np.random.default_rng(4)
+    pairs = [(rng.standard_normal(17000 + 33 * i).astype(np.float32), rng.standard_normal(17000 + 33 * i).astype(np.float32))
+             for i in range(7)]
+    cp = ds.CachedPairs(pairs, sample_length=16384, pin=False)
+    batches = [[0, 1, 2], [3, 4], [5, 6, 0], [1, 1, 1], [2]]
+    stream = ds.BatchStream(cp, batches, depth=3, rng=np.random.default_rng(123))
+    ref_rng = np.random.default_rng(123)
+    got = []
+    for k, (mix, clean) in enumerate(stream):
+        starts = [int(ref_rng.integers(len(pairs[i][0]) - 16384 + 1)) for i in batches[k]]
+        assert stream.last_starts == starts and mix.shape == (len(batches[k]), 1, 16384)
+        for row, (i, s) in enumerate(zip(batches[k], starts)):
+            assert np.array_equal(mix[row, 0].numpy(), pairs[i][0][s:s + 16384])
+            assert np.array_equal(clean[row, 0].numpy(), pairs[i][1][s:s + 16384])
+        got.append((mix, mix.clone()))
+        if len(got) >= 2:                              # the previous batch's buffers are still intact (depth 3: two stay valid)
+            assert torch.equal(got[-2][0], got[-2][1])
+    assert len(got) == len(batches)
+    # errors of the producer thread surface in the consumer
+    bad = ds.BatchStream(cp, [[0], [99]], depth=2)
+    with pytest.raises(IndexError):
+        for _ in bad:
+            pass

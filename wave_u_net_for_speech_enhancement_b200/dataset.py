@@ -9,6 +9,7 @@ the library's host code instead of librosa + numpy slicing.
 * :class:`CachedPairs` keeps decoded clips (float32, or 16-bit PCM as stored in the wav file) in memory and cuts a whole batch
   of aligned random crops straight into pinned ``[B,1,T]`` batch tensors on several host threads (``wunet_crop_pairs``): the
   pre-framed, pinned input stage for one-process-per-GPU training where the DataLoader workers are the bottleneck.
+* :class:`BatchStream` runs that cut for step k+1 on a background thread while step k trains (a ring of pinned buffer pairs).
 """
 from __future__ import annotations
 
@@ -139,3 +140,89 @@ class CachedPairs:
         _lib.check(_lib.load().wunet_crop_pairs(mix, cln, lens, st, B, self.sample_length, int(self.is_i16), om.data_ptr(),
                                                 oc.data_ptr(), HOST_THREADS))
         return om, oc
+
+
+class BatchStream:
+    """Background producer of training batches over a :class:`CachedPairs`: while the GPU runs step k, ONE host thread cuts the
+    crops of step k+1 (``wunet_crop_pairs``, itself multi-threaded) into the next of ``depth`` pinned buffer pairs - what the
+    reference gets from DataLoader worker processes (train.py:15-27), without pickling tensors between processes.
+
+    ``batches``: iterable of index lists (one per step; e.g. a shuffled permutation cut into batches). The crop positions are
+    drawn in the producer thread, in batch order, from ``rng`` (a ``numpy.random.Generator``; default: a fresh default_rng() -
+    NOT numpy's global generator, which is not thread-safe to share with the training thread).
+    Iterating yields ``(mixture, clean)`` pinned ``[B,1,T]`` tensors; a pair stays valid until ``depth - 1`` further batches have
+    been taken (copy it to the device before that - ``.cuda(non_blocking=True)`` + one stream sync per step is enough)."""
+
+    def __init__(self, pairs: CachedPairs, batches, depth: int = 3, rng: Optional[np.random.Generator] = None):
+        import queue
+        import threading
+        assert depth >= 2
+        self.pairs, self.depth = pairs, depth
+        self._rng = rng if rng is not None else np.random.default_rng()
+        self._q: "queue.Queue" = queue.Queue(maxsize=depth - 1)
+        self._free: "queue.Queue" = queue.Queue()
+        self._bufs = []
+        self._batches = iter(batches)
+        self._err = None
+        self._thread = threading.Thread(target=self._run, name="wunet-batch-stream", daemon=True)
+        self._started = False
+
+    def _buffers(self, B: int):
+        T = self.pairs.sample_length
+        m = torch.empty(B, 1, T, dtype=torch.float32)
+        c = torch.empty(B, 1, T, dtype=torch.float32)
+        if self.pairs.pin:
+            m, c = m.pin_memory(), c.pin_memory()
+        return m, c
+
+    def _run(self):
+        try:
+            lib = _lib.load()
+            for indices in self._batches:
+                indices = list(indices)
+                B = len(indices)
+                slot = self._free.get()                                   # a buffer pair the consumer has released
+                if slot is None:
+                    return
+                m, c = self._bufs[slot]
+                if m.shape[0] < B:
+                    m, c = self._buffers(B)
+                    self._bufs[slot] = (m, c)
+                P = self.pairs
+                starts = [int(self._rng.integers(len(P.mix[i]) - P.sample_length + 1)) for i in indices]
+                mix = (ctypes.c_void_p * B)(*[P.mix[i].ctypes.data for i in indices])
+                cln = (ctypes.c_void_p * B)(*[P.clean[i].ctypes.data for i in indices])
+                lens = (ctypes.c_longlong * B)(*[len(P.mix[i]) for i in indices])
+                st = (ctypes.c_longlong * B)(*starts)
+                _lib.check(lib.wunet_crop_pairs(mix, cln, lens, st, B, P.sample_length, int(P.is_i16), m.data_ptr(), c.data_ptr(),
+                                                HOST_THREADS))
+                self._q.put((slot, m[:B], c[:B], starts))
+        except BaseException as e:  # noqa: BLE001 - handed to the consumer
+            self._err = e
+        finally:
+            self._q.put(None)
+
+    def __iter__(self):
+        if self._started:
+            raise RuntimeError("a BatchStream can be iterated once")
+        self._started = True
+        for s in range(self.depth):
+            self._bufs.append(self._buffers(1))
+            self._free.put(s)
+        self._thread.start()
+        held = []
+        try:
+            while True:
+                item = self._q.get()
+                if item is None:
+                    if self._err is not None:
+                        raise self._err
+                    return
+                slot, m, c, starts = item
+                held.append(slot)
+                if len(held) > self.depth - 1:                            # the oldest batch handed out may be overwritten now
+                    self._free.put(held.pop(0))
+                self.last_starts = starts
+                yield m, c
+        finally:
+            self._free.put(None)                                          # lets a blocked producer exit
