@@ -95,3 +95,28 @@ def test_group8_block_equals_conv():
     got = conv1d_same(x.reshape(L // 8, 8), out)                        # [L/8][8 C]: column r*C + co of row m = sample 8m + r
     assert np.abs(got.reshape(L, C) - want).max() < 1e-9 * np.abs(want).max()
     assert np.count_nonzero(out) == 8 * w.size                          # every tap once per output phase r
+
+
+def test_pair_block_equals_conv_property():
+    """hypothesis: any channel counts (multiples of 8 as the library requires), both layouts, odd tap counts up to 15."""
+    from hypothesis import given, settings, strategies as stt
+
+    @settings(max_examples=40, deadline=None)
+    @given(c0=stt.integers(1, 12).map(lambda v: 8 * v), c1=stt.integers(0, 6).map(lambda v: 8 * v), cout=stt.integers(1, 6).map(lambda v: 8 * v),
+           K=stt.sampled_from([1, 3, 5, 7, 9, 15]), dec=stt.booleans(), L=stt.sampled_from([2, 8, 30]), seed=stt.integers(0, 2**16))
+    def check(c0, c1, cout, K, dec, L, seed):
+        if not dec:
+            c1 = 0
+        rng = np.random.default_rng(seed)
+        w = rng.standard_normal((cout, c0 + c1, K)).astype(np.float32)
+        x0 = rng.standard_normal((L, c0)).astype(np.float32)
+        x1 = rng.standard_normal((L, c1)).astype(np.float32) if c1 else None
+        x = x0 if x1 is None else np.concatenate([x0, x1], axis=1)
+        wp, kp = pair_weights(w, c0, c1, dec)
+        P = (K - 1) // 2
+        assert kp == 2 * ((P + 1) // 2) + 1
+        got = conv1d_same(virtual_rows(x0, x1, dec), wp).reshape(L // 2, 2, cout).reshape(L, cout)
+        want = conv1d_same(x, w)
+        assert np.abs(got - want).max() <= 1e-9 * max(1.0, np.abs(want).max())
+
+    check()
