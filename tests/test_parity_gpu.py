@@ -386,3 +386,17 @@ def test_enc0_persistent_form_is_bit_identical(state_full, monkeypatch):
         outs[v] = (y, b0, ys)
     for a, b in zip(outs["1"], outs["2"]):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("n,ci,B,T", [(5, 32, 3, 4096), (5, 16, 2, 4096), (6, 8, 3, 2048), (5, 32, 130, 1024)])
+def test_bf16_other_channel_plans_vs_oracle(n, ci, B, T):
+    """Channel plans other than the reference's 24 base filters (block 1 in row-pair form: 2 x ci = 16 .. 64 virtual input
+    channels, one K chunk; the last case at a batch that takes the swept tiling): output and block 1 against the oracle."""
+    st = wo.make_state(n, ci, seed=1)
+    x = wo.make_input(B, T, seed=2)
+    want, levels = wo.COracle(n, ci).forward(st, x, return_levels=True)
+    m = bf16_model(n, ci, st, store_last=True)
+    y = run(m, x)
+    b1 = m.read_level(1, B, T).cpu().numpy()
+    assert np.abs(b1 - levels[1]).max() <= BF16_LEVEL_REL * np.abs(levels[1]).max()
+    assert np.abs(y - want).max() <= BF16_OUT_TOL
