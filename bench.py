@@ -723,6 +723,8 @@ def main():
         "config": {"workload": f"unet_basic forward, batch {B}/GPU x 16384 samples, {N_LAYERS} levels, {CH_INT} base "
                                f"filters, eval-mode BatchNorm, {precision} path",
                    "global_batch": B * world, "parallelism": f"dp{world} (batch sharded, no collective on the forward)",
+                   "kernel_forms": "WUNET_TC_PAIR=%s WUNET_TC_ENC0=%s (defaults: block 1 over pairs of positions, block 0 on CUDA cores)"
+                                   % (os.environ.get("WUNET_TC_PAIR", "1"), os.environ.get("WUNET_TC_ENC0", "0")),
                    "l2": f"{NBUF} rotating input batches; per-step activation working set "
                          f"{sum(b for _n, _f, b in tab) / 2**30:.2f} GiB >> 126 MB L2"},
         "clocks": clocks,
