@@ -223,3 +223,34 @@ def test_batch_stream_prefetches_in_order_and_keeps_buffers_valid():
     with pytest.raises(IndexError):
         for _ in bad:
             pass
+
+
+def test_wav_reader_skips_other_chunks_and_reads_extensible_headers(tmp_path):
+    """A LIST chunk (odd size, padded) before "data", and a WAVE_FORMAT_EXTENSIBLE header whose sub-format says PCM: what
+    ffmpeg / soundfile write for multi-channel or 24-bit files."""
+    import struct
+    rng = np.random.default_rng(1)
+    pcm = rng.integers(-32768, 32767, 3001, dtype=np.int16)
+    data = pcm.tobytes()
+    fmt_ext = struct.pack("<HHIIHHHHIH14s", 0xFFFE, 1, 16000, 32000, 2, 16, 22, 16, 4, 1, b"\x00\x00\x00\x00\x10\x00\x80\x00\x00\xaa\x00\x38\x9b\x71")
+    lst = b"INFOISFT\x05\x00\x00\x00Lavf\x00"                      # odd-sized sub-chunk inside, total length odd
+    body = b"WAVE" + b"fmt " + struct.pack("<I", len(fmt_ext)) + fmt_ext
+    body += b"LIST" + struct.pack("<I", len(lst)) + lst + (b"\x00" if len(lst) & 1 else b"")
+    body += b"data" + struct.pack("<I", len(data)) + data
+    p = tmp_path / "ext.wav"
+    p.write_bytes(b"RIFF" + struct.pack("<I", len(body)) + body)
+    info = ds.wav_info(str(p))
+    assert info == {"sample_rate": 16000, "channels": 1, "frames": 3001, "bits": 16, "is_float": False}
+    got, _ = ds.load_wav(str(p))
+    assert np.array_equal(got, pcm.astype(np.float32) / 32768.0)
+    # a streamed file with a zero data size: the rest of the file is the data
+    body0 = b"WAVE" + b"fmt " + struct.pack("<IHHIIHH", 16, 1, 1, 8000, 16000, 2, 16) + b"data" + struct.pack("<I", 0) + data
+    q = tmp_path / "stream.wav"
+    q.write_bytes(b"RIFF" + struct.pack("<I", 0xFFFFFFFF) + body0)
+    assert ds.wav_info(str(q))["frames"] == 3001 and np.array_equal(ds.load_wav(str(q))[0], got)
+    # ADPCM (format tag 2) is refused loudly
+    bad = b"WAVE" + b"fmt " + struct.pack("<IHHIIHH", 16, 2, 1, 8000, 4000, 256, 4) + b"data" + struct.pack("<I", 8) + b"\x00" * 8
+    r = tmp_path / "adpcm.wav"
+    r.write_bytes(b"RIFF" + struct.pack("<I", len(bad)) + bad)
+    with pytest.raises(_lib.WunetError, match="unsupported"):
+        ds.wav_info(str(r))
